@@ -1,0 +1,105 @@
+"""Pins the CPU oracle (oracle/) against vectors produced by running the reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import dap, fm_tail, margins, partial_fc
+
+FM = ["fm_c64_sigmoid_mul", "fm_c128_tanh_add", "fm_c64_sigmoid_div", "fm_c256_tanh_sub",
+      "fm_c512_sigmoid_mul"]
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", FM)
+def test_fm_tail_matches_reference(name):
+    g = load_golden(name)
+    act, arith = str(g["act"]), str(g["arith"])
+    close(fm_tail.fm_gate_fwd(g["yf"], g["z"], act, arith), g["out"], 2e-5, 2e-5)
+    dyf, dz = fm_tail.fm_gate_bwd(g["dout"], g["yf"], g["z"], act, arith)
+    close(dyf, g["dyf_direct"], 1e-4, 2e-5)
+    close(dz, g["dz"], 1e-4, 2e-5)
+
+
+def test_fm_mask_extension_identity_case():
+    # with Cm == C and (Hm, Wm) == (H, W) the resize/broadcast extension is the plain tail
+    g = load_golden("fm_c64_sigmoid_mul")
+    yf = g["yf"].transpose(0, 2, 3, 1)
+    z = g["z"].transpose(0, 2, 3, 1)
+    d = g["dout"].transpose(0, 2, 3, 1)
+    close(fm_tail.fm_mask_fwd(yf, z), g["out"].transpose(0, 2, 3, 1), 2e-5, 2e-5)
+    dyf, dm = fm_tail.fm_mask_bwd(d, yf, z)
+    close(dm, g["dz"].transpose(0, 2, 3, 1), 1e-4, 2e-5)
+
+
+def test_dap_matches_reference():
+    g = load_golden("dap")
+    y = dap.dap_fwd(g["x"])
+    close(y, g["y"], 1e-6, 1e-6)
+    close(dap.dap_bwd(g["dy"]), g["dx"], 1e-6, 1e-7)
+    # argmax on the reference's own fp32 y is bit-exact, including the planted ties
+    assert np.array_equal(dap.argmax_mask(g["y"]), g["mask"])
+    assert g["mask"][0, 0, 0] == 0 and g["mask"][1, 3, 4] == 0
+
+
+@pytest.mark.parametrize("tag", ["arc_p", "arc_f", "arc_am_p", "arc_am_f", "cos_p", "cos_f", "cos_am_p", "cos_am_f"])
+def test_margin_heads_match_reference(tag):
+    g = load_golden("margins")
+    kind = "arc" if tag.startswith("arc") else "cos"
+    s, m, a, k = g[tag + ".smak"]
+    logits, *_ = margins.am_head_fwd(g[tag + ".e"], g[tag + ".w"], g[tag + ".label"], kind, s, m, a, k)
+    close(logits, g[tag + ".logits"], 2e-5, 2e-5 * s)
+    de, dw = margins.am_head_bwd(g[tag + ".e"], g[tag + ".w"], g[tag + ".label"], g[tag + ".dl"], kind, s, m, a, k)
+    close(de, g[tag + ".de"], 2e-4, 1e-5 * s)
+    close(dw, g[tag + ".dw"], 2e-4, 1e-5 * s)
+
+
+def test_softmax_head_matches_reference():
+    g = load_golden("margins")
+    close(margins.softmax_head_fwd(g["softmax.e"], g["softmax.w"], g["softmax.b"]), g["softmax.logits"], 1e-5, 1e-6)
+
+
+PFC = ["pfc_w1_full", "pfc_w1_sample", "pfc_w2_full", "pfc_w2_sample", "pfc_w2_am", "pfc_w1_d512",
+       "pfc_w1_overflow"]
+
+
+@pytest.mark.parametrize("name", PFC)
+def test_partial_fc_step_matches_reference(name):
+    g = load_golden(name)
+    W, C, sr = int(g["W"]), int(g["C"]), float(g["sample_rate"])
+    kind = str(g["kind"])
+    s, m, a, k = g["smak"]
+    # step 0 only depends on the initial weights; later steps on the ref's own updated weights
+    weights = [g[f"r{r}.w0"] for r in range(W)]
+    for step in range(int(g["steps"])):
+        p = f"s{step}."
+        feats = [g[f"r{r}.{p}feat"] for r in range(W)]
+        labels = [g[f"r{r}.{p}label"] for r in range(W)]
+        perms = [g[f"r{r}.{p}perm"] for r in range(W)]
+        res = partial_fc.step(feats, labels, weights, C, kind, s, m, a, k, sr,
+                              perms if int(sr) != 1 else None)
+        for r in range(W):
+            if int(sr) != 1:   # bit-exact: sampled class indices
+                assert np.array_equal(res["index"][r], g[f"r{r}.{p}index"]), (name, step, r)
+            close(res["x_grad"][r], g[f"r{r}.{p}x_grad"], 5e-4, 2e-5)
+            close(res["w_grad"][r], g[f"r{r}.{p}w_grad"], 5e-4, 2e-5)
+            assert abs(res["loss"] - float(g[f"r{r}.{p}loss"])) <= 1e-5 * abs(res["loss"])
+        weights = [g[f"r{r}.{p}weight_after"] for r in range(W)]
+
+
+def test_shard_geometry():
+    # ref partial_fc.py:34-36 at BASELINE config 3 (93,431 classes over 8 ranks)
+    geo = [partial_fc.shard_geometry(93431, 8, r) for r in range(8)]
+    assert [g[0] for g in geo] == [11679] * 7 + [11678]
+    assert geo[7][1] == 11679 * 7 and sum(g[0] for g in geo) == 93431
+    assert partial_fc.shard_geometry(1_000_000, 8, 3, 0.1) == (125000, 375000, 12500)
+
+
+def test_sample_overflow_uses_positive_set():
+    g = load_golden("pfc_w1_overflow")
+    tl, index = partial_fc.sample(g["r0.s0.label"], g["r0.s0.perm"], 0, 40, 4, 0.1)
+    assert np.array_equal(index, np.unique(g["r0.s0.label"]))
+    assert np.array_equal(index, g["r0.s0.index"])
