@@ -1,0 +1,170 @@
+/*
+ * msml_b200 — C ABI of the B200-native (sm_100a) MSML hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference
+ * (ygtxr1997/MSML) has no native code on this path — every entry point below replaces a chain
+ * of ATen / cuBLAS calls made from the reference's Python operators, cited per function as
+ * ref <file>:<lines>.  The Python host (msml_b200/) binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory; the library borrows pointers for the duration of the enqueue,
+ *     allocates nothing persistent and never frees caller memory;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on that stream;
+ *   - return 0 on success; a negative msml_status or a positive cudaError_t otherwise, with
+ *     msml_last_error() (thread-local) describing it.  Shape/dtype/alignment violations are
+ *     errors — there is no fallback path of any kind.
+ */
+#ifndef MSML_B200_H_
+#define MSML_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSML_B200_ABI_VERSION 1
+
+typedef enum { MSML_OK = 0, MSML_EINVAL = -1, MSML_EALIGN = -2, MSML_EWORKSPACE = -3, MSML_EUNSUPPORTED = -4 } msml_status;
+typedef enum { MSML_F32 = 0, MSML_BF16 = 1, MSML_F16 = 2 } msml_dtype;
+typedef enum { MSML_ACT_TANH = 0, MSML_ACT_SIGMOID = 1 } msml_act;       /* ref fmoperator.py:113-117 */
+typedef enum { MSML_ARITH_ADD = 0, MSML_ARITH_SUB = 1, MSML_ARITH_DIV = 2, MSML_ARITH_MUL = 3 } msml_arith; /* :71-81 */
+typedef enum { MSML_MARGIN_ARC = 0, MSML_MARGIN_COS = 1 } msml_margin;   /* ref margin_losses.py:318,203 */
+typedef enum { MSML_RESIZE_NEAREST = 0 } msml_resize;
+
+int msml_abi_version(void);
+const char* msml_last_error(void);
+/* Number of kernel launches this library enqueued (process-wide) since the last reset. */
+int64_t msml_launch_count(void);
+void msml_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K-A  mask fusion: FMCnn elementwise tail.           ref backbones/fm/fmoperator.py:288,304-310
+ *   out = arith(yf, act(z)) [+ f_out] + yf            (default act=sigmoid, arith=mul)
+ * All tensors share one shape AND one memory format (channels-last NHWC in the drop-in), so the
+ * op is a flat stream of n elements.  16-byte alignment of every pointer is required.
+ * bwd:  dyf = direct gradient wrt yf (the cat->conv path is autograd's), dz = gradient wrt z.
+ * ------------------------------------------------------------------------------------------ */
+int msml_fm_gate_fwd(const void* yf, const void* z, const void* f_out /*nullable*/, void* out,
+                     int64_t n, int dtype, int act, int arith, void* stream);
+int msml_fm_gate_bwd(const void* dout, const void* yf, const void* z, void* dyf, void* dz,
+                     int64_t n, int dtype, int act, int arith, void* stream);
+/* One launch over up to 8 segments (the 4 feature scales of the backbone).  Pointer / size
+ * arrays are HOST arrays of length nseg. */
+#define MSML_MAX_SEGMENTS 8
+int msml_fm_gate_fwd_multi(int nseg, const void* const* yf_host, const void* const* z_host,
+                           void* const* out_host, const int64_t* n_host,
+                           int dtype, int act, int arith, void* stream);
+int msml_fm_gate_bwd_multi(int nseg, const void* const* dout_host, const void* const* yf_host,
+                           const void* const* z_host, void* const* dyf_host, void* const* dz_host,
+                           const int64_t* n_host, int dtype, int act, int arith, void* stream);
+
+/* Extension named by BASELINE.json north_star (not taken by the reference):
+ * a low-resolution / single-channel mask  m (B,Hm,Wm,Cm), Cm in {1,C}, resized (nearest) to the
+ * feature resolution, normalised into a gate and fused into yf (B,H,W,C), all NHWC.
+ * bwd: dyf (B,H,W,C) and dm (B,Hm,Wm,Cm) in FP32 (reduced over broadcast channels by warp
+ * shuffles and over the resize fan-out); dm must be zero-filled by the caller. */
+int msml_fm_mask_fwd(const void* yf, const void* m, void* out, int64_t B, int64_t H, int64_t W,
+                     int64_t C, int64_t Hm, int64_t Wm, int64_t Cm, int dtype, int act, int arith,
+                     void* stream);
+int msml_fm_mask_bwd(const void* dout, const void* yf, const void* m, void* dyf, float* dm,
+                     int64_t B, int64_t H, int64_t W, int64_t C, int64_t Hm, int64_t Wm, int64_t Cm,
+                     int dtype, int act, int arith, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K-B  DAP head of the segmentation branch + argmax mask.
+ *   ref backbones/osb/unet.py:158-161,223 (PixelShuffle(k)+AvgPool2d(k) == mean over k*k channel
+ *   groups), train.py:357 / eval/qeval_mxnet.py:347 (final_seg[b].max(0)[1]).
+ * x (B, G*kk, H, W) -> y (B, G, H, W) [+ mask (B,H,W) int64 = argmax over G, first index on ties;
+ * nullable].  channels_last != 0 means the PHYSICAL layout of x and y is NHWC.
+ * ------------------------------------------------------------------------------------------ */
+int msml_dap_fwd(const void* x, void* y, int64_t* mask /*nullable*/, int64_t B, int64_t G, int64_t kk,
+                 int64_t H, int64_t W, int channels_last, int dtype, void* stream);
+int msml_dap_bwd(const void* dy, void* dx, int64_t B, int64_t G, int64_t kk, int64_t H, int64_t W,
+                 int channels_last, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K-D  PartialFC label remap + class sampling.          ref headers/partial_fc.py:77-94
+ * ------------------------------------------------------------------------------------------ */
+/* :79-81  in place: off-shard -> -1, on-shard -= class_start */
+int msml_pfc_remap(int64_t* total_label, int64_t n, int64_t class_start, int64_t num_local, void* stream);
+/* :86  perm[label] = 2.0 for every label != -1 (duplicates are idempotent: no unique needed) */
+int msml_pfc_mark_positive(float* perm, const int64_t* total_label, int64_t n, int64_t num_local, void* stream);
+/* :87-90  index = sort(topk(perm, k).indices) with k = max(num_sample, #positives): exact radix
+ * select of the k-th largest value + ordered compaction (ties at the k-th value: lowest class
+ * index first).  n_index (device scalar) receives k.  index must hold max(num_sample, n_labels)
+ * entries. */
+size_t msml_pfc_select_workspace(int64_t num_local);
+int msml_pfc_select(const float* perm, int64_t num_local, int64_t num_sample, int64_t* index,
+                    int64_t* n_index, void* workspace, size_t workspace_bytes, void* stream);
+/* :92  in place: label != -1 -> lower_bound(index, label) */
+int msml_pfc_searchsorted(int64_t* total_label, int64_t n, const int64_t* index, const int64_t* n_index,
+                          void* stream);
+/* :93-94 gather  dst[i,:] = src[index[i],:]   and  :103-104 scatter  dst[index[i],:] = src[i,:]
+ * (fp32 rows of d elements, d % 4 == 0) */
+int msml_gather_rows_f32(const float* src, const int64_t* index, float* dst, int64_t n_rows, int64_t d, void* stream);
+int msml_scatter_rows_f32(float* dst, const int64_t* index, const float* src, int64_t n_rows, int64_t d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K-E..K-H  PartialFC head.                              ref headers/partial_fc.py:96-99,115,118-177
+ * Per rank: X (B_tot, D) gathered features, W (n_s, D) sub-weights, tl (B_tot) remapped labels.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int   kind;   /* msml_margin */
+  float s, m, a, k;
+} msml_margin_params;
+
+/* :115  wn = bf16(w / max(||w||, 1e-12)), inv_norm = 1 / max(||w||, 1e-12).  wn_t (nullable) gets
+ * the transposed copy (D, ld_t) used by the dX contraction.  D % 8 == 0. */
+int msml_wnorm_cast(const float* w, void* wn_bf16, void* wn_t_bf16 /*nullable*/, int64_t ld_t,
+                    float* inv_norm, int64_t n, int64_t D, void* stream);
+/* fp32 (rows, D) -> bf16 (rows, D) and optionally the transposed bf16 copy (D, ld_t) */
+int msml_cast_bf16(const float* x, void* x_bf16, void* x_t_bf16 /*nullable*/, int64_t ld_t,
+                   int64_t rows, int64_t D, void* stream);
+
+/* bf16 (rows, cols) row-major -> (cols, ld_t) row-major (ld_t >= rows, ld_t % 8 == 0) */
+int msml_transpose_bf16(const void* src, void* dst, int64_t rows, int64_t cols, int64_t ld_t, void* stream);
+
+/* Workspace (bytes) for one head step of the given geometry. */
+size_t msml_head_workspace(int64_t B_tot, int64_t n_s, int64_t D);
+
+/* :98,132,135,139-140  logits = margin(X Wn^T) never materialised: tcgen05 GEMM whose epilogue
+ * applies margin + scale and reduces per-row (max, sum exp, target logit) of THIS rank's shard.
+ * stats (3, B_tot) fp32 = [rowmax | rowsum (relative to rowmax) | target logit or -inf]. */
+int msml_head_fwd(const void* x_bf16, const void* wn_bf16, const int64_t* tl, int64_t B_tot,
+                  int64_t n_s, int64_t D, const msml_margin_params* margin_host, float* stats,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* :136,141,144,162-163  merge the stats of W ranks (gathered: (W, 3, B_tot)) into the global
+ * row max / log-sum and the loss  -mean(log(max(p_target, 1e-30))).
+ * gstats (2, B_tot) = [global max | global sum]; loss: device scalar. */
+int msml_head_merge_stats(const float* gathered, int64_t W, int64_t B_tot, float* gstats, float* loss,
+                          void* stream);
+/* :144-169  recompute the logits tile by tile, form grad = (softmax - smoothed one-hot) / B_tot,
+ * chain through the margin, and contract: dX_full = dcos Wn (B_tot, D) fp32 (this rank's partial,
+ * to be reduce-scattered), dW = normalize_bwd(dcos^T X) (n_s, D) fp32. */
+int msml_head_bwd(const void* x_bf16, const void* x_t_bf16, int64_t ld_xt, const void* wn_bf16,
+                  const void* wn_t_bf16, int64_t ld_wt, const float* inv_norm, const int64_t* tl,
+                  int64_t B_tot, int64_t n_s, int64_t D, const msml_margin_params* margin_host,
+                  const float* gstats, float* dx_full, float* dw,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* In-model full-FC margin heads (ref headers/margin_losses.py:275-303, 390-418) on a
+ * materialised cosine matrix (B, C) fp32, in place:  fwd applies margin + scale, bwd multiplies
+ * dlogits by d logit / d cos (needs the pre-margin cosine). */
+int msml_margin_fwd(float* cos_inout, const int64_t* label, int64_t B, int64_t C, int64_t ld,
+                    const msml_margin_params* margin_host, void* stream);
+int msml_margin_bwd(float* dlogits_inout, const float* cos, const int64_t* label, int64_t B, int64_t C,
+                    int64_t ld, const msml_margin_params* margin_host, void* stream);
+
+/* Plain tcgen05 GEMM used by the tests to validate the tensor-core mainloop in isolation:
+ * C (M, N) fp32 = A (M, K) bf16 * B (N, K)^T bf16, K-major operands, lda/ldb in elements (%8). */
+int msml_gemm_bf16_tn(const void* a, int64_t lda, const void* b, int64_t ldb, float* c, int64_t ldc,
+                      int64_t M, int64_t N, int64_t K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSML_B200_H_ */

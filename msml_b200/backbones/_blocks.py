@@ -1,0 +1,43 @@
+"""Building blocks shared by the FRB trunk and the OSB encoder (both use the same improved-residual
+unit in the reference: ref backbones/frb/iresnet.py:38-67 and backbones/osb/unet.py:62-91).
+Module / parameter names are kept so reference checkpoints load unchanged."""
+from torch import nn
+
+
+def conv3x3(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False)
+
+
+def conv1x1(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, 1, stride=stride, bias=False)
+
+
+class IBasicBlock(nn.Module):
+    """BN -> conv3x3 -> BN -> PReLU -> conv3x3(stride) -> BN, plus (projected) identity."""
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.bn1 = nn.BatchNorm2d(inplanes, eps=1e-05)
+        self.conv1 = conv3x3(inplanes, planes)
+        self.bn2 = nn.BatchNorm2d(planes, eps=1e-05)
+        self.prelu = nn.PReLU(planes)
+        self.conv2 = conv3x3(planes, planes, stride)
+        self.bn3 = nn.BatchNorm2d(planes, eps=1e-05)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        out = self.bn3(self.conv2(self.prelu(self.bn2(self.conv1(self.bn1(x))))))
+        skip = x if self.downsample is None else self.downsample(x)
+        return out + skip
+
+
+def make_stage(inplanes, planes, blocks, stride):
+    """One resolution stage: the first block strides / projects, the rest keep the shape."""
+    down = None
+    if stride != 1 or inplanes != planes:
+        down = nn.Sequential(conv1x1(inplanes, planes, stride), nn.BatchNorm2d(planes, eps=1e-05))
+    layers = [IBasicBlock(inplanes, planes, stride, down)]
+    layers += [IBasicBlock(planes, planes) for _ in range(1, blocks)]
+    return nn.Sequential(*layers)

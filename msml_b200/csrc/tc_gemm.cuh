@@ -1,0 +1,312 @@
+// tcgen05 / TMA / TMEM GEMM core for sm_100a (hand-written PTX, no CUTLASS on the product path).
+//
+//   D[m, n] = sum_k A[m, k] * B[n, k]       A (M x K) and B (N x K) bf16, both K-major ("TN")
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0  lane 0 : TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem ring (STAGES deep)
+//   warp 1  lane 0 : MMA issuer     tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM
+//   warps 2..5     : epilogue       tcgen05.ld (32x32b): one thread = one accumulator ROW, so row
+//                                   reductions (max / sum-exp / dot) need no shuffles
+// Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue; ACC_STAGES
+// accumulators of BLOCK_N fp32 columns each so the epilogue of tile i overlaps the MMAs of tile
+// i+1), and the static persistent tile loop (m fastest so that concurrently running CTAs share
+// the same B tile in L2).  Split-K work units are supported for short-M / long-K contractions.
+//
+// Layout contract: tile rows are 64 bf16 = 128 bytes, TMA writes them with SWIZZLE_128B and the
+// UMMA smem descriptors read them as the canonical K-major SW128 layout (8-row x 128 B atoms,
+// SBO = 1024 B).  K-steps inside the 128-byte atom advance the descriptor start address by 32 B.
+// Out-of-bounds rows / k are zero-filled by TMA, so M, N, K need not be tile multiples.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace msml {
+namespace tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;          // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kSpinLimit = 1u << 26;  // bounded waits: trap instead of hanging the GPU
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on `bar` when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B canonical layout: start>>4 | LBO(16B, ignored)=1 | SBO=1024B | version=1 | layout=2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // [0,14)  start address
+  d |= (uint64_t)1 << 16;                             // [16,30) leading byte offset (unused for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // [32,46) stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                             // [46,48) descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // [61,64) SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------- problem
+struct GemmShape {
+  int M, N, K;           // logical extents (TMA zero-fills beyond them)
+  int m_blocks, n_blocks;
+  int k_splits;          // split-K work units
+  int k_blocks_per_split;
+};
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + tmem ptr, + slack for 1024-B alignment
+};
+
+// Epilogue concept:
+//   struct Epi { __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int k_split,
+//                                           int quarter, int lane) const; };
+// tmem_acc already carries the accumulator-stage column offset; the callee adds
+// ((quarter*32) << 16) + column.  Called by all 128 epilogue threads (warp-convergent).
+
+template <int BLOCK_N, int ACC_STAGES, int STAGES, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const GemmShape shape, const Epi epi) {
+  static_assert(BLOCK_N % 128 == 0 && BLOCK_N <= 512, "BLOCK_N in {128,256,384,512}");
+  static_assert(BLOCK_N * ACC_STAGES <= kTmemCols, "accumulators exceed TMEM");
+  constexpr int UMMA_N = BLOCK_N >= 256 ? 256 : BLOCK_N;
+  constexpr int N_SUB = BLOCK_N / UMMA_N;
+  using L = SmemLayout<BLOCK_N, STAGES>;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_units = shape.m_blocks * shape.n_blocks * shape.k_splits;
+  const int total_k_blocks = (shape.K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int m_blk = u % shape.m_blocks;
+        const int n_blk = (u / shape.m_blocks) % shape.n_blocks;
+        const int ks = u / (shape.m_blocks * shape.n_blocks);
+        const int kb0 = ks * shape.k_blocks_per_split;
+        int kb1 = kb0 + shape.k_blocks_per_split;
+        if (kb1 > total_k_blocks) kb1 = total_k_blocks;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+#pragma unroll
+          for (int j = 0; j < N_SUB; ++j)
+            tma_load_2d(sb + j * UMMA_N * kBlockK * 2, &map_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N + j * UMMA_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc(kBlockM, UMMA_N);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int ks = u / (shape.m_blocks * shape.n_blocks);
+        const int kb0 = ks * shape.k_blocks_per_split;
+        int kb1 = kb0 + shape.k_blocks_per_split;
+        if (kb1 > total_k_blocks) kb1 = total_k_blocks;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * kUmmaK * 2);
+#pragma unroll
+            for (int j = 0; j < N_SUB; ++j) {
+              const uint64_t db = make_smem_desc(sb + j * UMMA_N * kBlockK * 2 + k * kUmmaK * 2);
+              umma_bf16(d_tmem + j * UMMA_N, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int m_blk = u % shape.m_blocks;
+      const int n_blk = (u / shape.m_blocks) % shape.n_blocks;
+      const int ks = u / (shape.m_blocks * shape.n_blocks);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------- host side
+// cuTensorMapEncodeTiled is fetched through the runtime (no link-time libcuda dependency).
+int encode_tmap_bf16_kmajor(CUtensorMap* out, const void* base, int64_t rows, int64_t k, int64_t ld_elems, int box_rows);
+
+template <int BLOCK_N, int ACC_STAGES, int STAGES, class Epi>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& shape, const Epi& epi, cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  auto kern = gemm_kernel<BLOCK_N, ACC_STAGES, STAGES, Epi>;
+  static thread_local bool configured = false;   // per template instantiation
+  if (!configured) {
+    MSML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int units = shape.m_blocks * shape.n_blocks * shape.k_splits;
+  int grid = num_sms();
+  if (units < grid) grid = units;
+  if (grid < 1) grid = 1;
+  kern<<<grid, kThreads, L::kTotal, st>>>(ma, mb, shape, epi);
+  MSML_LAUNCH_CHECK();
+  return 0;
+}
+
+inline GemmShape make_shape(int64_t M, int64_t N, int64_t K, int block_n, int k_splits = 1) {
+  GemmShape s;
+  s.M = (int)M; s.N = (int)N; s.K = (int)K;
+  s.m_blocks = (int)((M + kBlockM - 1) / kBlockM);
+  s.n_blocks = (int)((N + block_n - 1) / block_n);
+  const int total_kb = (int)((K + kBlockK - 1) / kBlockK);
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > total_kb) k_splits = total_kb;
+  s.k_blocks_per_split = (total_kb + k_splits - 1) / k_splits;
+  s.k_splits = (total_kb + s.k_blocks_per_split - 1) / s.k_blocks_per_split;  // no empty splits
+  return s;
+}
+
+}  // namespace tc
+}  // namespace msml

@@ -1,0 +1,274 @@
+"""torch.autograd wrappers over the C ABI (include/msml_b200.h).  PyTorch is plumbing here: it
+owns device memory and streams and supplies the autograd graph; every op below is one or more
+hand-written sm_100a kernels from libmsml_b200.so.  No op has a PyTorch/CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT, ARITH, check, dtype_code, load, require_cuda, stream_ptr
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _dense_like(ref, t):
+    """Return t laid out with exactly ref's strides (ref is dense)."""
+    if t.stride() == ref.stride() and t.dtype == ref.dtype:
+        return t
+    out = torch.empty_like(ref)
+    out.copy_(t)
+    return out
+
+
+def _dense(t):
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# K-A  mask fusion tail of the FM operator      ref backbones/fm/fmoperator.py:288,304-310
+# --------------------------------------------------------------------------------------------
+class _FMGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, yf, z, f_out, act, arith):
+        require_cuda(yf, z, f_out)
+        lib = load()
+        yf_d = _dense(yf)
+        z_d = _dense_like(yf_d, z)
+        fo_d = _dense_like(yf_d, f_out) if f_out is not None else None
+        out = torch.empty_like(yf_d)
+        check(lib.msml_fm_gate_fwd(_ptr(yf_d), _ptr(z_d), _ptr(fo_d), _ptr(out), yf_d.numel(),
+                                   dtype_code(yf_d.dtype), ACT[act], ARITH[arith], stream_ptr()))
+        ctx.save_for_backward(yf_d, z_d)
+        ctx.cfg = (act, arith, f_out is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        yf, z = ctx.saved_tensors
+        act, arith, has_fout = ctx.cfg
+        lib = load()
+        d = _dense_like(yf, dout)
+        dyf = torch.empty_like(yf)
+        dz = torch.empty_like(yf)
+        check(lib.msml_fm_gate_bwd(_ptr(d), _ptr(yf), _ptr(z), _ptr(dyf), _ptr(dz), yf.numel(),
+                                   dtype_code(yf.dtype), ACT[act], ARITH[arith], stream_ptr()))
+        return dyf, dz, (d if has_fout else None), None, None
+
+
+def fm_gate(yf, z, act="sigmoid", arith="mul", f_out=None):
+    """out = arith(yf, act(z)) [+ f_out] + yf, fused forward and backward."""
+    if act not in ACT:
+        raise ValueError("activation type error")
+    if arith not in ARITH:
+        raise ValueError("arith type error")
+    if yf.shape != z.shape:
+        raise ValueError("fm_gate: yf %s and z %s must have the same shape" % (tuple(yf.shape), tuple(z.shape)))
+    if z.dtype != yf.dtype:
+        z = z.to(yf.dtype)
+    return _FMGate.apply(yf, z, f_out, act, arith)
+
+
+def fm_gate_multi_fwd(yfs, zs, act="sigmoid", arith="mul"):
+    """One launch over several scales (inference / microbench).  Returns the list of outputs."""
+    lib = load()
+    require_cuda(*yfs, *zs)
+    n = len(yfs)
+    outs = [torch.empty_like(y) for y in yfs]
+    arr = ctypes.c_void_p * n
+    sizes = (ctypes.c_int64 * n)(*[y.numel() for y in yfs])
+    check(lib.msml_fm_gate_fwd_multi(n, arr(*[y.data_ptr() for y in yfs]), arr(*[z.data_ptr() for z in zs]),
+                                     arr(*[o.data_ptr() for o in outs]), sizes, dtype_code(yfs[0].dtype),
+                                     ACT[act], ARITH[arith], stream_ptr()))
+    return outs
+
+
+def fm_gate_multi_bwd(douts, yfs, zs, act="sigmoid", arith="mul"):
+    lib = load()
+    require_cuda(*douts, *yfs, *zs)
+    n = len(yfs)
+    dyfs = [torch.empty_like(y) for y in yfs]
+    dzs = [torch.empty_like(y) for y in yfs]
+    arr = ctypes.c_void_p * n
+    sizes = (ctypes.c_int64 * n)(*[y.numel() for y in yfs])
+    check(lib.msml_fm_gate_bwd_multi(n, arr(*[d.data_ptr() for d in douts]), arr(*[y.data_ptr() for y in yfs]),
+                                     arr(*[z.data_ptr() for z in zs]), arr(*[o.data_ptr() for o in dyfs]),
+                                     arr(*[o.data_ptr() for o in dzs]), sizes, dtype_code(yfs[0].dtype),
+                                     ACT[act], ARITH[arith], stream_ptr()))
+    return dyfs, dzs
+
+
+# Extension (north_star): low-resolution / single-channel mask, NHWC.
+class _FMMask(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, yf, m, act, arith):
+        require_cuda(yf, m)
+        lib = load()
+        B, C, H, W = yf.shape
+        _, Cm, Hm, Wm = m.shape
+        yf_d = yf.contiguous(memory_format=torch.channels_last)
+        m_d = m.to(yf.dtype).contiguous(memory_format=torch.channels_last)
+        out = torch.empty_like(yf_d)
+        check(lib.msml_fm_mask_fwd(_ptr(yf_d), _ptr(m_d), _ptr(out), B, H, W, C, Hm, Wm, Cm,
+                                   dtype_code(yf_d.dtype), ACT[act], ARITH[arith], stream_ptr()))
+        ctx.save_for_backward(yf_d, m_d)
+        ctx.cfg = (act, arith)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        yf, m = ctx.saved_tensors
+        act, arith = ctx.cfg
+        lib = load()
+        B, C, H, W = yf.shape
+        _, Cm, Hm, Wm = m.shape
+        d = _dense_like(yf, dout)
+        dyf = torch.empty_like(yf)
+        dm = torch.zeros(m.shape, dtype=torch.float32, device=m.device).contiguous(memory_format=torch.channels_last)
+        check(lib.msml_fm_mask_bwd(_ptr(d), _ptr(yf), _ptr(m), _ptr(dyf), _ptr(dm), B, H, W, C, Hm, Wm, Cm,
+                                   dtype_code(yf.dtype), ACT[act], ARITH[arith], stream_ptr()))
+        return dyf, dm.to(m.dtype), None, None
+
+
+def fm_mask(yf, m, act="sigmoid", arith="mul"):
+    """yf (B,C,H,W), m (B,Cm,Hm,Wm) mask logits with Cm in {1, C}: resize(nearest) + gate + fuse."""
+    if act not in ACT:
+        raise ValueError("activation type error")
+    if arith not in ARITH:
+        raise ValueError("arith type error")
+    return _FMMask.apply(yf, m, act, arith)
+
+
+# --------------------------------------------------------------------------------------------
+# K-B  DAP + argmax mask                        ref backbones/osb/unet.py:158-161,223; train.py:357
+# --------------------------------------------------------------------------------------------
+class _DAP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, want_mask):
+        require_cuda(x)
+        lib = load()
+        B, CK, H, W = x.shape
+        kk = k * k
+        if CK % kk:
+            raise ValueError("DAP: channels %d not divisible by k*k=%d" % (CK, kk))
+        G = CK // kk
+        x_d = _dense(x)
+        cl = x_d.is_contiguous(memory_format=torch.channels_last) and not x_d.is_contiguous()
+        y = torch.empty((B, G, H, W), dtype=x.dtype, device=x.device,
+                        memory_format=torch.channels_last if cl else torch.contiguous_format)
+        mask = torch.empty((B, H, W), dtype=torch.int64, device=x.device) if want_mask else None
+        check(lib.msml_dap_fwd(_ptr(x_d), _ptr(y), _ptr(mask), B, G, kk, H, W, int(cl), dtype_code(x.dtype), stream_ptr()))
+        ctx.cfg = (kk, G, cl)
+        if want_mask:
+            ctx.mark_non_differentiable(mask)
+            return y, mask
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, *_):
+        kk, G, cl = ctx.cfg
+        lib = load()
+        B, _, H, W = dy.shape
+        dy_d = dy.contiguous(memory_format=torch.channels_last) if cl else dy.contiguous()
+        dx = torch.empty((B, G * kk, H, W), dtype=dy.dtype, device=dy.device,
+                         memory_format=torch.channels_last if cl else torch.contiguous_format)
+        check(lib.msml_dap_bwd(_ptr(dy_d), _ptr(dx), B, G, kk, H, W, int(cl), dtype_code(dy.dtype), stream_ptr()))
+        return dx, None, None
+
+
+def dap(x, k=3):
+    """PixelShuffle(k)+AvgPool2d(k) == mean over k*k channel groups; (B, G*k*k, H, W) -> (B, G, H, W)."""
+    return _DAP.apply(x, k, False)
+
+
+def dap_with_mask(x, k=3):
+    """-> (seg (B,G,H,W), argmax mask (B,H,W) int64 with first-index tie rule), one kernel."""
+    return _DAP.apply(x, k, True)
+
+
+# --------------------------------------------------------------------------------------------
+# tcgen05 GEMM + in-model margin heads          ref headers/margin_losses.py:275-303,390-418
+# --------------------------------------------------------------------------------------------
+def _pad_k(t):
+    """bf16 (rows, k) -> contiguous with k padded to a multiple of 8 (TMA pitch rule)."""
+    t = t.to(torch.bfloat16)
+    k = t.shape[1]
+    if k % 8:
+        t = torch.nn.functional.pad(t, (0, 8 - k % 8))
+    return t.contiguous(), k
+
+
+def gemm_tn(a, b):
+    """fp32 (M, N) = a (M, K) @ b (N, K)^T on tcgen05 tensor cores (operands rounded to bf16)."""
+    require_cuda(a, b)
+    lib = load()
+    a_p, k = _pad_k(a)
+    b_p, k2 = _pad_k(b)
+    if k != k2:
+        raise ValueError("gemm_tn: K mismatch %d vs %d" % (k, k2))
+    M, N = a.shape[0], b.shape[0]
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    check(lib.msml_gemm_bf16_tn(_ptr(a_p), a_p.shape[1], _ptr(b_p), b_p.shape[1], _ptr(c), N, M, N, k, stream_ptr()))
+    return c
+
+
+class _CosineGemm(torch.autograd.Function):
+    """cos = en @ wn^T with both gradients, all three contractions on tcgen05."""
+
+    @staticmethod
+    def forward(ctx, en, wn):
+        ctx.save_for_backward(en, wn)
+        return gemm_tn(en, wn)
+
+    @staticmethod
+    def backward(ctx, dcos):
+        en, wn = ctx.saved_tensors
+        d_en = gemm_tn(dcos, wn.t())          # (B, C) x (D, C)^T
+        d_wn = gemm_tn(dcos.t(), en.t())      # (C, B) x (D, B)^T
+        return d_en.to(en.dtype), d_wn.to(wn.dtype)
+
+
+class _Margin(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cos, label, kind, s, m, a, k):
+        require_cuda(cos, label)
+        lib = load()
+        cos = cos.contiguous()
+        label = label.contiguous().to(torch.int64)
+        mp = _lib.margin_params(kind, s, m, a, k)
+        ctx.save_for_backward(cos, label)
+        ctx.mp = mp
+        out = cos.clone()
+        B, C = out.shape
+        check(lib.msml_margin_fwd(_ptr(out), _ptr(label), B, C, C, ctypes.byref(mp), stream_ptr()))
+        return out
+
+    @staticmethod
+    def backward(ctx, dl):
+        cos, label = ctx.saved_tensors
+        lib = load()
+        g = dl.to(torch.float32).contiguous().clone()
+        B, C = g.shape
+        check(lib.msml_margin_bwd(_ptr(g), _ptr(cos), _ptr(label), B, C, C, ctypes.byref(ctx.mp), stream_ptr()))
+        return g, None, None, None, None, None, None
+
+
+def cosine_logits(en, wn):
+    return _CosineGemm.apply(en, wn)
+
+
+def margin_logits(cos, label, kind, s, m, a=0.0, k=0.0):
+    """In-place-free margin + scale on a cosine matrix (rows with label -1 get scale only)."""
+    return _Margin.apply(cos.float(), label, kind, s, m, a, k)
+
+
+def launch_count():
+    return load().msml_launch_count()
+
+
+def launch_count_reset():
+    load().msml_launch_count_reset()

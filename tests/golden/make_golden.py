@@ -237,13 +237,13 @@ def cpu_shims(record):
 
 
 PFC_CASES = [  # name, W, B, C, D, sample_rate, kind, (s,m,a,k), steps
-    ("pfc_w1_full", 1, 8, 37, 32, 1.0, "arc", (64.0, 0.5, 0.0, 0.0), 2),
-    ("pfc_w1_sample", 1, 8, 101, 32, 0.3, "arc", (64.0, 0.5, 0.0, 0.0), 2),
-    ("pfc_w2_full", 2, 4, 37, 32, 1.0, "cos", (64.0, 0.4, 0.0, 0.0), 2),
-    ("pfc_w2_sample", 2, 6, 203, 32, 0.25, "arc", (64.0, 0.5, 0.0, 0.0), 2),
-    ("pfc_w2_am", 2, 4, 50, 32, 0.5, "arc", (32.0, 0.45, 1.2, 0.1), 1),
+    ("pfc_w1_full", 1, 8, 37, 64, 1.0, "arc", (64.0, 0.5, 0.0, 0.0), 2),
+    ("pfc_w1_sample", 1, 8, 101, 64, 0.3, "arc", (64.0, 0.5, 0.0, 0.0), 2),
+    ("pfc_w2_full", 2, 4, 37, 64, 1.0, "cos", (64.0, 0.4, 0.0, 0.0), 2),
+    ("pfc_w2_sample", 2, 6, 203, 64, 0.25, "arc", (64.0, 0.5, 0.0, 0.0), 2),
+    ("pfc_w2_am", 2, 4, 50, 64, 0.5, "arc", (32.0, 0.45, 1.2, 0.1), 1),
     ("pfc_w1_d512", 1, 16, 96, 512, 1.0, "arc", (64.0, 0.5, 0.0, 0.0), 1),
-    ("pfc_w1_overflow", 1, 16, 40, 32, 0.1, "arc", (64.0, 0.5, 0.0, 0.0), 1),  # n_pos > num_sample
+    ("pfc_w1_overflow", 1, 16, 40, 64, 0.1, "arc", (64.0, 0.5, 0.0, 0.0), 1),  # n_pos > num_sample
 ]
 
 

@@ -1,0 +1,153 @@
+"""GPU parity: mask-fusion kernels (K-A), DAP (K-B) vs the oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import assert_close, dev, host, need_gpu
+from oracle import dap as odap
+from oracle import fm_tail
+
+pytestmark = pytest.mark.gpu
+
+FM = ["fm_c64_sigmoid_mul", "fm_c128_tanh_add", "fm_c64_sigmoid_div", "fm_c256_tanh_sub", "fm_c512_sigmoid_mul"]
+
+
+@pytest.mark.parametrize("name", FM)
+@pytest.mark.parametrize("cl", [False, True])
+def test_fm_gate_fp32_matches_reference_golden(name, cl):
+    need_gpu()
+    from msml_b200 import ops
+    g = load_golden(name)
+    act, arith = str(g["act"]), str(g["arith"])
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    yf = dev(g["yf"]).contiguous(memory_format=fmt).requires_grad_(True)
+    z = dev(g["z"]).contiguous(memory_format=fmt).requires_grad_(True)
+    out = ops.fm_gate(yf, z, act, arith)
+    out.backward(dev(g["dout"]))
+    assert_close(host(out), g["out"], 1e-5, atol=1e-5, what="out")
+    assert_close(host(yf.grad), g["dyf_direct"], 1e-4, atol=1e-5, what="dyf")
+    assert_close(host(z.grad), g["dz"], 1e-4, atol=1e-5, what="dz")
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "tanh"])
+@pytest.mark.parametrize("arith", ["add", "sub", "div", "mul"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_fm_gate_all_modes_vs_oracle(act, arith, dtype):
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(1)
+    shape = (3, 64, 9, 7)     # 12096 elements: vector body + ragged tail for every dtype
+    yf = torch.randn(shape, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    z = (torch.randn(shape, device="cuda") + (1.5 if arith == "div" else 0.0)).to(dtype).contiguous(memory_format=torch.channels_last)
+    if arith == "div" and act == "tanh":
+        z = z.abs() + 0.5
+    fo = torch.randn(shape, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    d = torch.randn(shape, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    yf.requires_grad_(True); z.requires_grad_(True); fo.requires_grad_(True)
+    out = ops.fm_gate(yf, z, act, arith, fo)
+    out.backward(d)
+    rt = 2e-2 if dtype != torch.float32 else 2e-5
+    want = fm_tail.fm_gate_fwd(host(yf), host(z), act, arith, host(fo))
+    assert_close(host(out), want, rt, atol=1e-5 if dtype == torch.float32 else 1e-2, what="out")
+    wdyf, wdz = fm_tail.fm_gate_bwd(host(d), host(yf), host(z), act, arith)
+    assert_close(host(yf.grad), wdyf, rt, atol_frac=1e-5 if dtype == torch.float32 else 4e-3, what="dyf")
+    assert_close(host(z.grad), wdz, rt, atol_frac=1e-5 if dtype == torch.float32 else 4e-3, what="dz")
+    assert_close(host(fo.grad), host(d), 0, what="df_out")
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 4096 + 3])
+def test_fm_gate_ragged_sizes(n):
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(n)
+    yf = torch.randn(n, device="cuda", dtype=torch.bfloat16).view(1, n, 1, 1)
+    z = torch.randn(n, device="cuda", dtype=torch.bfloat16).view(1, n, 1, 1)
+    out = ops.fm_gate(yf, z, "sigmoid", "mul")
+    assert_close(host(out), fm_tail.fm_gate_fwd(host(yf), host(z)), 2e-2, atol=1e-2, what="ragged")
+
+
+def test_fm_gate_multi_scale_single_launch():
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(2)
+    shapes = [(4, 64, 56, 56), (4, 128, 28, 28), (4, 256, 14, 14), (4, 512, 7, 7)]
+    mk = lambda s: torch.randn(s, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    yfs, zs, ds = [mk(s) for s in shapes], [mk(s) for s in shapes], [mk(s) for s in shapes]
+    ops.launch_count_reset()
+    outs = ops.fm_gate_multi_fwd(yfs, zs)
+    dyfs, dzs = ops.fm_gate_multi_bwd(ds, yfs, zs)
+    assert ops.launch_count() == 2
+    for yf, z, d, o, dy, dz in zip(yfs, zs, ds, outs, dyfs, dzs):
+        assert_close(host(o), fm_tail.fm_gate_fwd(host(yf), host(z)), 2e-2, atol=1e-2, what="multi out")
+        wdy, wdz = fm_tail.fm_gate_bwd(host(d), host(yf), host(z))
+        assert_close(host(dy), wdy, 2e-2, atol_frac=4e-3, what="multi dyf")
+        assert_close(host(dz), wdz, 2e-2, atol_frac=4e-3, what="multi dz")
+
+
+def test_fm_gate_linearity_at_full_size():
+    """Size-independent property at the BASELINE config-2 scale shape (B=512, 64x56x56):
+    with arith=mul the op is linear in yf:  f(a*yf, z) == a * f(yf, z)  up to rounding."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(3)
+    shape = (512, 64, 56, 56)
+    yf = torch.randn(shape, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    z = torch.randn(shape, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    a = ops.fm_gate(yf, z, "sigmoid", "mul")
+    b = ops.fm_gate(yf * 2, z, "sigmoid", "mul")       # exact doubling in bf16
+    assert torch.equal(b, a * 2)
+    ref = yf.float() * (1 + torch.sigmoid(z.float()))
+    assert (a.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("Cm,Hm,Wm", [(1, 8, 6), (1, 4, 3), (64, 8, 6), (64, 4, 3)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fm_mask_resize_broadcast_extension(Cm, Hm, Wm, dtype):
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(5)
+    B, C, H, W = 3, 64, 8, 6
+    yf = torch.randn(B, C, H, W, device="cuda").to(dtype).requires_grad_(True)
+    m = torch.randn(B, Cm, Hm, Wm, device="cuda").to(dtype).requires_grad_(True)
+    d = torch.randn(B, C, H, W, device="cuda").to(dtype)
+    out = ops.fm_mask(yf, m, "sigmoid", "mul")
+    out.backward(d)
+    nhwc = lambda t: host(t).transpose(0, 2, 3, 1)
+    want = fm_tail.fm_mask_fwd(nhwc(yf), nhwc(m))
+    wdyf, wdm = fm_tail.fm_mask_bwd(nhwc(d), nhwc(yf), nhwc(m))
+    rt = 2e-2 if dtype == torch.bfloat16 else 2e-5
+    assert_close(nhwc(out), want, rt, atol=1e-2 if dtype == torch.bfloat16 else 1e-5, what="mask out")
+    assert_close(nhwc(yf.grad), wdyf, rt, atol_frac=4e-3 if dtype == torch.bfloat16 else 1e-5, what="mask dyf")
+    assert_close(nhwc(m.grad), wdm, rt, atol_frac=1e-2 if dtype == torch.bfloat16 else 1e-5, what="mask dm")
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_dap_matches_reference_golden(cl):
+    need_gpu()
+    from msml_b200 import ops
+    g = load_golden("dap")
+    x = dev(g["x"])
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    y, mask = ops.dap_with_mask(x, 3)
+    y.backward(dev(g["dy"]))
+    assert_close(host(y), g["y"], 1e-6, atol=1e-6, what="dap y")
+    assert_close(host(x.grad), g["dx"], 1e-6, atol=1e-7, what="dap dx")
+    assert np.array_equal(mask.cpu().numpy(), g["mask"])      # bit-exact, planted ties included
+    y2 = ops.dap(x.detach(), 3)
+    assert torch.equal(y2, y)
+
+
+def test_dap_full_size_properties():
+    """112x112, batch 128: constant-in-group input is reproduced exactly; mask == 2-way argmax."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(7)
+    base = torch.randn(128, 2, 112, 112, device="cuda", dtype=torch.bfloat16)
+    x = base.repeat_interleave(9, dim=1)
+    y, mask = ops.dap_with_mask(x.float(), 3)
+    assert_close(host(y), host(base), 1e-6, atol=1e-6, what="dap const groups")
+    assert torch.equal(mask, (base[:, 1].float() > base[:, 0].float()).long())
+    assert np.array_equal(odap.argmax_mask(host(y)), mask.cpu().numpy())

@@ -1,0 +1,97 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the drop-in classes keep the reference's surface, and errors are loud (no fallback)."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from msml_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "msml_b200.h")).read()
+    declared = set(re.findall(r"\b(msml_[a-z0-9_]+)\s*\(", header))
+    declared -= {"msml_status", "msml_dtype", "msml_act", "msml_arith", "msml_margin", "msml_resize", "msml_margin_params"}
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.msml_abi_version() == 1
+    assert lib.msml_head_workspace(1024, 11679, 512) > 0
+    assert lib.msml_pfc_select_workspace(125000) > 0
+
+
+def test_argument_errors_are_reported_not_swallowed():
+    from msml_b200 import _lib
+    lib = _lib.load()
+    # null pointers / bad enum -> negative status + message, no crash, no compute
+    code = lib.msml_fm_gate_fwd(None, None, None, None, 16, 0, 1, 3, None)
+    assert code < 0 and b"null" in lib.msml_last_error()
+    code = lib.msml_fm_gate_fwd(ctypes.c_void_p(16), ctypes.c_void_p(16), None, ctypes.c_void_p(16), 16, 0, 7, 3, None)
+    assert code < 0 and b"activation" in lib.msml_last_error()
+    code = lib.msml_fm_gate_fwd(ctypes.c_void_p(8), ctypes.c_void_p(16), None, ctypes.c_void_p(16), 16, 0, 1, 3, None)
+    assert code == -2      # MSML_EALIGN
+    with pytest.raises(RuntimeError):
+        _lib.check(code)
+
+
+def test_ops_refuse_cpu_tensors():
+    from msml_b200 import ops
+    x = torch.randn(2, 8, 4, 4)
+    with pytest.raises(RuntimeError, match="only a CUDA"):
+        ops.fm_gate(x, x)
+    with pytest.raises(RuntimeError, match="only a CUDA"):
+        ops.dap(torch.randn(1, 18, 4, 4))
+    with pytest.raises(ValueError, match="activation type error"):
+        ops.fm_gate(x, x, act="relu")
+    with pytest.raises(ValueError, match="arith type error"):
+        ops.fm_gate(x, x, arith="pow")
+
+
+def test_msml_state_dict_matches_reference_layout():
+    """Key names and shapes recorded from the reference models (tests/golden/state_keys.json)."""
+    from msml_b200.backbones import MSML
+    ref = json.load(open(os.path.join(GOLDEN, "state_keys.json")))
+    for frb, classes in (("iresnet18", 10572), ("iresnet50", 97)):
+        net = MSML(frb, "unet", (1, 1, 1, 1), classes, header_type="AMArcFace", fm_params=(3, 2, "sigmoid", "mul"))
+        got = {k: list(v.shape) for k, v in net.state_dict().items()}
+        assert got == ref[frb], set(got) ^ set(ref[frb])
+    net = MSML("iresnet18", "unet", (1, 0, 1, 0), 10, header_type=None)
+    assert net.classification is None and type(net.frb.fm_ops[1]).__name__ == "FMNone"
+
+
+def test_msml_constructor_errors_mirror_reference():
+    from msml_b200.backbones import MSML
+    with pytest.raises(AssertionError):
+        MSML("iresnet18", "unet", (1, 1, 1), 10)
+    with pytest.raises(ValueError, match="FRB type error"):
+        MSML("vgg", "unet", (1, 1, 1, 1), 10)
+    with pytest.raises(ValueError, match="OSB type error"):
+        MSML("iresnet18", "fcn", (1, 1, 1, 1), 10)
+    with pytest.raises(ValueError, match="FM Operators type error"):
+        MSML("iresnet18", "unet", (1, 2, 1, 1), 10)
+    with pytest.raises(ValueError, match="not found"):
+        MSML("iresnet99", "unet", (1, 1, 1, 1), 10)
+
+
+def test_margin_heads_surface():
+    from msml_b200.headers import AMArcFace, AMCosFace, ArcFace, CosFace, Softmax
+    h = AMArcFace(16, 8, None, s=64.0, m=0.5, a=0.0, k=0.0)
+    assert tuple(h.weight.shape) == (8, 16) and (h.kind, h.s, h.m) == ("arc", 64.0, 0.5)
+    assert AMCosFace(16, 8, None).kind == "cos"
+    with pytest.raises(ValueError, match="DataParallel"):
+        Softmax(16, 8, [0])(torch.randn(2, 16), torch.zeros(2, dtype=torch.long))
+    with pytest.raises(ValueError, match="DataParallel"):
+        AMArcFace(16, 8, [0])(torch.randn(2, 16), torch.zeros(2, dtype=torch.long))
+    assert ArcFace().kind == "arc" and CosFace().m == 0.4
+
+
+def test_partial_fc_rejects_unfusable_margin_callable():
+    from msml_b200.headers import PartialFC
+    with pytest.raises(TypeError, match="kind, s, m, a, k"):
+        PartialFC(0, 0, 1, 8, False, lambda logits, label: logits, 100)
