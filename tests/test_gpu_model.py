@@ -64,11 +64,13 @@ def test_train_step_fp32_matches_reference(no_tf32):
     assert_close(host(final_seg), g["train_seg"], 1e-3, atol_frac=1e-3, what="train seg")
     assert abs(float(loss) - float(g["loss"])) <= 2e-2 * abs(float(g["loss"]))
     named = dict(net.named_parameters())
-    for key in [k[5:] for k in g if k.startswith("grad.")]:
+    # frb.fc.bias feeds BatchNorm1d (batch statistics): its true gradient is zero, the stored one is
+    # rounding noise in both implementations
+    for key in [k[5:] for k in g if k.startswith("grad.") and k != "grad.frb.fc.bias"]:
         assert_close(host(named[key].grad), g["grad." + key], 5e-2, atol_frac=3e-2, what="grad " + key)
     checked = 0
     for key in [k[9:] for k in g if k.startswith("gradnorm.")]:
-        if named[key].grad is None:
+        if named[key].grad is None or key == "frb.fc.bias":
             continue
         want = float(g["gradnorm." + key])
         got = float(named[key].grad.float().norm())
