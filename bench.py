@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native MSML hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N=1; N>1 under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W     CPU port of the reference step
+    python bench.py --workload fusion|head ...               micro-benchmarks (BASELINE configs 2 / 4)
+
+Default workload = BASELINE.json config 3: ires50_msml + PartialFC(ArcFace s=64 m=0.5, 93,431
+classes, sample_rate 1) bf16 training step, 112x112 synthetic images, batch 128 per GPU.
+One step = backbone forward -> F.normalize -> PartialFC.forward_backward -> features.backward(x_grad)
+-> clip_grad_norm_(5) -> SGD steps -> pfc.update()   (ref train.py:283-300, the PartialFC variant).
+
+Prints ONE JSON line (rank 0).  `value` = imgs/s with inputs resident in HBM; `e2e` = the same step
+fed from pinned host memory each step with the loss read back each step.  `roofline` is measured
+live: every launch of this library is bracketed by CUDA events on its own stream inside the timed
+region (msml_profile_*), work = algorithmic bytes / flops of that launch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NUM_CLASSES = 93431
+BATCH = 128
+S, M = 64.0, 0.5
+FM_PARAMS = (3, 2, "sigmoid", "mul")
+FEAT_ELEMS_PER_IMG = 376320       # 64*56^2 + 128*28^2 + 256*14^2 + 512*7^2  
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------ CPU port
+def cpu_step_factory(batch, frb="iresnet50", threads=None):
+    """The reference's step restated on CPU (oracle/): torch-CPU fp32 backbone + numpy PartialFC."""
+    import numpy as np
+    import torch
+    from msml_b200.backbones import MSML
+    from oracle import model_cpu, partial_fc as opfc
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(1)
+    net = MSML(frb, "unet", (1, 1, 1, 1), NUM_CLASSES, header_type=None, fm_params=FM_PARAMS)   # weights only (CPU init)
+    sd = model_cpu.trainable_state(net)
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.1 * batch / 512, momentum=0.9, weight_decay=5e-4)
+    rng = np.random.default_rng(1)
+    weight = rng.normal(0, 0.01, (NUM_CLASSES, 512))
+    mom = np.zeros_like(weight)
+
+    def step():
+        img = torch.randn(batch, 3, 112, 112)
+        label = torch.randint(0, NUM_CLASSES, (batch,))
+        feat, _seg = model_cpu.msml_forward(sd, img, frb, training=True, fm_params=FM_PARAMS)
+        featn = torch.nn.functional.normalize(feat)
+        res = opfc.step([featn.detach().numpy()], [label.numpy()], [weight], NUM_CLASSES, "arc", S, M)
+        featn.backward(torch.from_numpy(res["x_grad"][0]).float())
+        torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 5)
+        opt.step()
+        opt.zero_grad()
+        g = res["w_grad"][0] + 5e-4 * weight          # SGD(momentum .9, wd 5e-4) on the class centres
+        mom[...] = 0.9 * mom + g
+        weight[...] -= 0.1 * mom
+        return float(res["loss"])
+    return step
+
+
+def run_cpu(batch, steps, warmup):
+    import torch
+    cores = os.cpu_count() or 1
+    step = cpu_step_factory(batch, threads=cores)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return dict(value=steps * batch / dt, unit="imgs/s", cores=torch.get_num_threads(), kind="port",
+                sample="%d steps of batch %d (of the %d/GPU workload), fp32, oracle/model_cpu.py + oracle/partial_fc.py" % (steps, batch, BATCH),
+                ms_per_step=dt / steps * 1e3)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def collect_profile(lib):
+    import ctypes
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.msml_profile_collect(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, work = line.split()
+        out[name] = dict(launches=int(n), total_ms=float(ms), work=float(work))
+    return out
+
+
+def roofline_entry(name, rec, pk, sustained=True):
+    avg_s = rec["total_ms"] / rec["launches"] * 1e-3
+    per_launch = rec["work"] / rec["launches"]
+    if name.endswith("_gemm"):
+        peak = pk["tf_sustained"] if sustained else pk["tf_burst"]
+        ach = per_launch / avg_s / 1e12
+        return dict(kernel=name, bound="tensor", achieved=round(ach, 2), peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4),
+                    traffic=None, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
+                    peak_source=pk["source"] + (", sustained" if sustained else ", burst"))
+    ach = per_launch / avg_s / 1e9
+    return dict(kernel=name, bound="hbm", achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4),
+                traffic=None, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
+                peak_source=pk["source"])
+
+
+def fusion_microbench(iters=20, batch=512):
+    """BASELINE config 2: 4-scale mask fusion fwd+bwd, bf16 NHWC, one batched launch each way."""
+    import torch
+    from msml_b200 import ops
+    shapes = [(batch, 64, 56, 56), (batch, 128, 28, 28), (batch, 256, 14, 14), (batch, 512, 7, 7)]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mk = lambda s: torch.randn(s, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    yfs, zs, ds = [mk(s) for s in shapes], [mk(s) for s in shapes], [mk(s) for s in shapes]
+    for _ in range(3):
+        ops.fm_gate_multi_fwd(yfs, zs); ops.fm_gate_multi_bwd(ds, yfs, zs)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * iters)]
+    for i in range(iters):      # 385 MB per tensor pass >> 126 MB L2: no flush needed
+        ev[3 * i].record()
+        outs = ops.fm_gate_multi_fwd(yfs, zs)
+        ev[3 * i + 1].record()
+        dyfs, dzs = ops.fm_gate_multi_bwd(ds, yfs, zs)
+        ev[3 * i + 2].record()
+        del outs, dyfs, dzs
+    torch.cuda.synchronize()
+    fwd = sorted(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(iters))[iters // 2]
+    bwd = sorted(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(iters))[iters // 2]
+    elems = FEAT_ELEMS_PER_IMG * batch
+    return dict(batch=batch, fwd_ms=round(fwd, 4), bwd_ms=round(bwd, 4), fwd_gbs=round(3 * elems * 2 / fwd / 1e6, 1),
+                bwd_gbs=round(5 * elems * 2 / bwd / 1e6, 1), fwd_bwd_gbs=round(8 * elems * 2 / (fwd + bwd) / 1e6, 1),
+                algorithmic_bytes=8 * elems * 2)
+
+
+def run_train(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from msml_b200 import _lib, ops
+    from msml_b200.backbones import MSML
+    from msml_b200.headers import ArcFace, PartialFC
+
+    lib = _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True
+    pk = peaks()
+
+    torch.manual_seed(1)                                     # same init on every rank (ref train.py:133-134)
+    net = MSML("iresnet50", "unet", (1, 1, 1, 1), NUM_CLASSES, fp16=True, header_type=None, fm_params=FM_PARAMS).to(dev).train()
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], broadcast_buffers=False,
+                                                          find_unused_parameters=True)
+    pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), NUM_CLASSES, sample_rate=1.0, embedding_size=512)
+    lr = 0.1 * BATCH * world / 512
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=lr, momentum=0.9, weight_decay=5e-4)
+    opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4)
+
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    n_buf = 4
+    imgs = [torch.randn(BATCH, 3, 112, 112, device=dev, generator=gen) for _ in range(n_buf)]
+    labels = [torch.randint(0, NUM_CLASSES, (BATCH,), device=dev, generator=gen) for _ in range(n_buf)]
+    imgs_h = [t.cpu().pin_memory() for t in imgs]
+    labels_h = [t.cpu().pin_memory() for t in labels]
+
+    def step(img, label):
+        feat, _seg = model(img)
+        featn = torch.nn.functional.normalize(feat)
+        x_grad, loss = pfc.forward_backward(label, featn, opt_pfc)
+        featn.backward(x_grad)
+        torch.nn.utils.clip_grad_norm_([p for p in net.parameters() if p.grad is not None], 5, foreach=True)
+        opt.step(); opt_pfc.step(); pfc.update()
+        opt.zero_grad(set_to_none=True); opt_pfc.zero_grad(set_to_none=True)
+        return loss
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, host_fed):
+        fence()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = 0.0
+        for i in range(n):
+            if host_fed:
+                img = imgs_h[i % n_buf].to(dev, non_blocking=True)
+                label = labels_h[i % n_buf].to(dev, non_blocking=True)
+                last = step(img, label).item()              # D2H read of the step's loss
+            else:
+                last = step(imgs[i % n_buf], labels[i % n_buf])
+        b.record()
+        fence()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, float(last)
+
+    for i in range(args.warmup):
+        step(imgs[i % n_buf], labels[i % n_buf])
+    fence()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ops.launch_count_reset()
+    lib.msml_profile_enable(1)
+    ms, loss = timed(args.steps, host_fed=False)
+    lib.msml_profile_enable(0)
+    launches = ops.launch_count()
+    prof = collect_profile(lib)
+    ms_e2e, loss_e2e = timed(args.steps, host_fed=True)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        return None
+    value = args.steps * BATCH * world / (ms * 1e-3)
+    rl = sorted((roofline_entry(k, v, pk) for k, v in prof.items()), key=lambda r: -r["avg_us"] * r["launches"])
+    mine_ms = sum(v["total_ms"] for v in prof.values()) / args.steps
+    res = {
+        "metric": "train imgs/s ires50-MSML+PartialFC", "value": round(value, 1), "unit": "imgs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ires50_msml + PartialFC(ArcFace s=64 m=0.5, 93431 classes, sample_rate 1) bf16 training step, "
+                               "112x112, batch 128/GPU (BASELINE config 3)",
+                   "global_batch": BATCH * world, "parallelism": "dp%d backbone (DDP) + class-sharded head" % world,
+                   "l2": "per-step working set (activations, GBs) >> 126 MB L2; 4 rotating input batches"},
+        "e2e": {"value": round(args.steps * BATCH * world / (ms_e2e * 1e-3), 1), "unit": "imgs/s",
+                "h2d_bytes_per_step": imgs_h[0].numel() * 4 + labels_h[0].numel() * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "own_kernel_ms_per_step": round(mine_ms, 4),
+        "roofline": rl[0] if rl else None,
+        "rooflines": rl,
+        "clocks": clocks,
+        "loss": round(loss, 4),
+    }
+    return res
+
+
+def run_head(args, rank, local_rank, world):
+    """BASELINE config 4 style head-only sweep (per-rank shard of `classes`, B=128/GPU)."""
+    import torch
+    import torch.distributed as dist
+    from msml_b200 import _lib, ops
+    from msml_b200.headers import ArcFace, PartialFC
+    lib = _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    pk = peaks()
+    torch.manual_seed(1)
+    pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), args.classes, sample_rate=args.sample_rate, embedding_size=512)
+    opt = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.1, momentum=0.9, weight_decay=5e-4)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    feat = torch.nn.functional.normalize(torch.randn(BATCH, 512, device=dev, generator=g))
+    label = torch.randint(0, args.classes, (BATCH,), device=dev, generator=g)
+    for _ in range(args.warmup):
+        pfc.forward_backward(label, feat, opt); opt.step(); pfc.update()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    lib.msml_profile_enable(1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        pfc.forward_backward(label, feat, opt); opt.step(); pfc.update()
+    b.record()
+    torch.cuda.synchronize()
+    lib.msml_profile_enable(0)
+    prof = collect_profile(lib)
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    if rank != 0:
+        return None
+    n_s = pfc.sub_weight.shape[0]
+    flops = 6.0 * BATCH * world * n_s * 512
+    rl = sorted((roofline_entry(k, v, pk, sustained=False) for k, v in prof.items()), key=lambda r: -r["avg_us"] * r["launches"])
+    gemm_ms = sum(v["total_ms"] for k, v in prof.items() if k.endswith("_gemm")) / args.steps
+    return {"metric": "PartialFC head step", "value": round(args.steps * BATCH * world / (ms * 1e-3), 1), "unit": "imgs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "PartialFC head only, %d classes, sample_rate %g, B=%d/GPU" % (args.classes, args.sample_rate, BATCH),
+                       "n_s_per_rank": n_s},
+            "head_algorithmic_tflops_over_gemm_time": round(flops / (gemm_ms * 1e-3) / 1e12, 2),
+            "rooflines": rl, "roofline": rl[0] if rl else None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "fusion", "head"])
+    ap.add_argument("--classes", type=int, default=1_000_000)
+    ap.add_argument("--sample-rate", type=float, default=1.0)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = min(args.steps, 12)
+        cb = run_cpu(args.cpu_batch, steps, min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": "train imgs/s ires50-MSML+PartialFC", "value": round(cb["value"], 3), "unit": "imgs/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(cb["ms_per_step"], 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ires50_msml + PartialFC(ArcFace s=64 m=0.5, 93431 classes, sample_rate 1) training step on host CPU "
+                                   "cores, 112x112 (BASELINE config 3 shapes; bounded sample: batch %d per step)" % args.cpu_batch},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": round(cb["value"], 3), "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload == "fusion":
+        torch.cuda.set_device(local_rank)
+        fm = fusion_microbench(iters=max(args.steps, 5))
+        pk = peaks()
+        if rank == 0:
+            print(json.dumps({"metric": "mask-fusion fwd+bwd GB/s (BASELINE config 2)", "value": fm["fwd_bwd_gbs"], "unit": "GB/s",
+                              "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": round(fm["fwd_ms"] + fm["bwd_ms"], 4),
+                              "higher_is_better": True, "dtype": "bf16", "data": "synthetic", "vs_baseline": None, "scaling": "weak",
+                              "config": {"workload": "4-scale mask fusion, batch 512, bf16 NHWC, fwd+bwd, one launch each way"},
+                              "roofline": {"bound": "hbm", "achieved": fm["fwd_bwd_gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                                           "frac": round(fm["fwd_bwd_gbs"] / pk["hbm"], 4), "traffic": None}, "detail": fm}))
+        return 0
+
+    res = run_head(args, rank, local_rank, world) if args.workload == "head" else run_train(args, rank, local_rank, world)
+    if rank == 0 and args.workload == "train":
+        res["fusion_microbench"] = fusion_microbench()
+        if world == 1 and not args.no_cpu_baseline:
+            cb = run_cpu(args.cpu_batch, 6, 1)
+            res["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(res))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

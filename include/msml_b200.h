@@ -40,6 +40,11 @@ const char* msml_last_error(void);
 /* Number of kernel launches this library enqueued (process-wide) since the last reset. */
 int64_t msml_launch_count(void);
 void msml_launch_count_reset(void);
+/* Optional per-launch timing with CUDA events recorded on the launching stream.  collect()
+ * synchronises and writes "name launches total_ms total_algorithmic_work\n" per kernel family
+ * (work = bytes for HBM-bound kernels, flops for the tcgen05 contractions). */
+void msml_profile_enable(int on);
+int64_t msml_profile_collect(char* buf_host, int64_t capacity);
 
 /* ------------------------------------------------------------------------------------------
  * K-A  mask fusion: FMCnn elementwise tail.           ref backbones/fm/fmoperator.py:288,304-310

@@ -32,6 +32,8 @@ SIGNATURES = {
     "msml_last_error": (ctypes.c_char_p, []),
     "msml_launch_count": (c_i64, []),
     "msml_launch_count_reset": (None, []),
+    "msml_profile_enable": (None, [c_int]),
+    "msml_profile_collect": (c_i64, [ctypes.c_char_p, c_i64]),
     "msml_fm_gate_fwd": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_int, c_int, c_int, c_p]),
     "msml_fm_gate_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_int, c_int, c_int, c_p]),
     "msml_fm_gate_fwd_multi": (c_int, [c_int, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p]),

@@ -1,5 +1,10 @@
 // C-ABI plumbing: error string, launch counter, device queries.
 #include <atomic>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -33,7 +38,62 @@ int num_sms() {
   return cached;
 }
 
+// ---- profiling -------------------------------------------------------------------------------
+struct ProfRec { const char* name; double work; cudaEvent_t a, b; };
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(const char* name, double work, cudaStream_t stream) : slot(-1), st(stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r{name, work, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, st);
+}
+
 }  // namespace msml
+
+extern "C" void msml_profile_enable(int on) { msml::g_prof_on.store(on != 0); }
+
+// Synchronises, then writes one line per kernel family: "name launches total_ms total_work\n".
+// Returns the number of bytes written (excluding the terminator) and clears the records.
+extern "C" int64_t msml_profile_collect(char* buf, int64_t cap) {
+  using namespace msml;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<int64_t, std::pair<double, double>>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1; e.second.first += ms; e.second.second += r.work;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s %lld %.6f %.6e\n", kv.first.c_str(), (long long)kv.second.first,
+             kv.second.second.first, kv.second.second.second);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const size_t n = out.size() < (size_t)cap - 1 ? out.size() : (size_t)cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+    return (int64_t)n;
+  }
+  return 0;
+}
 
 extern "C" int msml_abi_version(void) { return MSML_B200_ABI_VERSION; }
 extern "C" const char* msml_last_error(void) { return msml::err_buf(); }

@@ -39,6 +39,16 @@ void count_launch(int n = 1);
                                cudaGetErrorString(_e), __FILE__, __LINE__);               \
   } while (0)
 
+// ---- optional per-launch timing (CUDA events on the launching stream; msml_profile_*) ----------
+// `work` is the ALGORITHMIC work of the launch: bytes for HBM-bound kernels, flops for GEMMs.
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(const char* name, double work, cudaStream_t stream);
+  ~ProfScope();
+};
+#define MSML_PROF(name, work, stream) ::msml::ProfScope _prof_scope((name), (double)(work), (stream))
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int num_sms();

@@ -76,6 +76,7 @@ extern "C" int msml_dap_fwd(const void* x, void* y, int64_t* mask, int64_t B, in
   if (int e = dap_check(x, y, B, G, kk, H, W)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = dap_grid(B * H * W);
+  MSML_PROF("dap_fwd", (double)B * H * W * (G * kk + G) * (dtype == MSML_F32 ? 4 : 2), st);
   MSML_DISPATCH_DTYPE(dtype, T, {
     const T* xi = static_cast<const T*>(x);
     T* yo = static_cast<T*>(y);
@@ -96,6 +97,7 @@ extern "C" int msml_dap_bwd(const void* dy, void* dx, int64_t B, int64_t G, int6
   if (int e = dap_check(dy, dx, B, G, kk, H, W)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = dap_grid(B * H * W);
+  MSML_PROF("dap_bwd", (double)B * H * W * (G * kk + G) * (dtype == MSML_F32 ? 4 : 2), st);
   MSML_DISPATCH_DTYPE(dtype, T, {
     if (channels_last) dap_bwd_kernel<T, true><<<grid, 256, 0, st>>>(static_cast<const T*>(dy), static_cast<T*>(dx), B, (int)G, (int)kk, H * W);
     else dap_bwd_kernel<T, false><<<grid, 256, 0, st>>>(static_cast<const T*>(dy), static_cast<T*>(dx), B, (int)G, (int)kk, H * W);

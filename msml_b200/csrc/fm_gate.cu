@@ -219,6 +219,9 @@ static int deal_blocks(int nseg, const int64_t* n, int vn, int unroll, int ctas_
 template <typename T, int ACT, int ARITH>
 static int launch_fwd(const FwdSegs& s, bool has_fout, cudaStream_t st) {
   const int grid = s.block_end[MSML_MAX_SEGMENTS - 1];
+  double bytes = 0;
+  for (int i = 0; i < s.nseg; ++i) bytes += (double)s.n[i] * sizeof(T) * (has_fout ? 4 : 3);
+  MSML_PROF("fm_gate_fwd", bytes, st);
   if (has_fout) fm_gate_fwd_kernel<T, ACT, ARITH, true><<<grid, kThreads, 0, st>>>(s);
   else fm_gate_fwd_kernel<T, ACT, ARITH, false><<<grid, kThreads, 0, st>>>(s);
   MSML_LAUNCH_CHECK();
@@ -227,6 +230,9 @@ static int launch_fwd(const FwdSegs& s, bool has_fout, cudaStream_t st) {
 template <typename T, int ACT, int ARITH>
 static int launch_bwd(const BwdSegs& s, cudaStream_t st) {
   const int grid = s.block_end[MSML_MAX_SEGMENTS - 1];
+  double bytes = 0;
+  for (int i = 0; i < s.nseg; ++i) bytes += (double)s.n[i] * sizeof(T) * 5;
+  MSML_PROF("fm_gate_bwd", bytes, st);
   fm_gate_bwd_kernel<T, ACT, ARITH><<<grid, kThreads, 0, st>>>(s);
   MSML_LAUNCH_CHECK();
   return 0;

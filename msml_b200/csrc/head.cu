@@ -432,7 +432,7 @@ extern "C" int msml_gemm_bf16_tn(const void* a, int64_t lda, const void* b, int6
   if (int e = encode_tmap_bf16_kmajor(&ma, a, M, K, lda, kBlockM)) return e;
   if (int e = encode_tmap_bf16_kmajor(&mb, b, N, K, ldb, 256)) return e;
   EpiStore epi{c, ldc, (int)M, (int)N, 256};
-  return launch_gemm<256, 2, 4>(ma, mb, make_shape(M, N, K, 256), epi, (cudaStream_t)stream);
+  return launch_gemm<256, 2, 4>("gemm_bf16_tn", ma, mb, make_shape(M, N, K, 256), epi, (cudaStream_t)stream);
 }
 
 extern "C" int msml_wnorm_cast(const float* w, void* wn, void* wn_t, int64_t ld_t, float* inv_norm, int64_t n, int64_t D,
@@ -440,11 +440,15 @@ extern "C" int msml_wnorm_cast(const float* w, void* wn, void* wn_t, int64_t ld_
   MSML_REQUIRE(w && wn && n > 0 && D > 0 && D % 8 == 0, MSML_EINVAL, "bad wnorm arguments (D %% 8 must be 0)");
   MSML_REQUIRE(aligned16(w) && aligned16(wn), MSML_EALIGN, "wnorm buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  wnorm_cast_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(wn), inv_norm, n, (int)D, true);
+  {
+    MSML_PROF("wnorm_cast", (double)n * D * 6, st);
+    wnorm_cast_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(wn), inv_norm, n, (int)D, true);
+  }
   MSML_LAUNCH_CHECK();
   if (wn_t) {
     MSML_REQUIRE(ld_t >= n, MSML_EINVAL, "ld_t %lld < n %lld", (long long)ld_t, (long long)n);
     dim3 grid((unsigned)((n + 63) / 64), (unsigned)((D + 63) / 64));
+    MSML_PROF("transpose_bf16", (double)n * D * 4, st);
     transpose_bf16_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(wn), static_cast<__nv_bfloat16*>(wn_t), n, (int)D, ld_t);
     MSML_LAUNCH_CHECK();
   }
@@ -503,7 +507,7 @@ extern "C" int msml_head_fwd(const void* x, const void* wn, const int64_t* tl, i
   if (int e = encode_tmap_bf16_kmajor(&ma, x, B_tot, D, D, kBlockM)) return e;
   if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, 256)) return e;
   EpiFwdStats epi{tl, mg, (int)B_tot, (int)n_s, kFwdBlockN, h.part_max, h.part_sum, h.tgt};
-  if (int e = launch_gemm<kFwdBlockN, 2, 4>(ma, mb, make_shape(B_tot, n_s, D, kFwdBlockN), epi, st)) return e;
+  if (int e = launch_gemm<kFwdBlockN, 2, 4>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, kFwdBlockN), epi, st)) return e;
   head_local_stats_kernel<<<(unsigned)((B_tot + 127) / 128), 128, 0, st>>>(h.part_max, h.part_sum, h.tgt, tl, h.n_blocks, (int)B_tot, stats);
   MSML_LAUNCH_CHECK();
   return 0;
@@ -536,7 +540,7 @@ extern "C" int msml_head_bwd(const void* x, const void* x_t, int64_t ld_xt, cons
     const float eps = 0.1f;   // ref partial_fc.py:154
     EpiBwdDcos epi{tl, mg, (int)B_tot, (int)n_s, kFwdBlockN, gstats, gstats + B_tot, h.dcos, h.ld_dc, h.dcos_t, h.ld_t,
                    1.0f - eps, eps / (float)(n_s - 1), 1.0f / (float)B_tot};
-    if (int e = launch_gemm<kFwdBlockN, 2, 4>(ma, mb, make_shape(B_tot, n_s, D, kFwdBlockN), epi, st)) return e;
+    if (int e = launch_gemm<kFwdBlockN, 2, 4>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, kFwdBlockN), epi, st)) return e;
   }
   // 2. dX_full = dcos (B_tot x n_s) * Wn (n_s x D): A = dcos, B = Wn^T (D x n_s), K = n_s, split-K
   {
@@ -547,7 +551,7 @@ extern "C" int msml_head_bwd(const void* x, const void* x_t, int64_t ld_xt, cons
     const int tiles = (int)((B_tot + kBlockM - 1) / kBlockM) * (int)((D + 255) / 256);
     int splits = (num_sms() + tiles - 1) / tiles;
     EpiDxAccum epi{dx_full, (int)B_tot, (int)D, 256};
-    if (int e = launch_gemm<256, 2, 4>(ma, mb, make_shape(B_tot, D, n_s, 256, splits), epi, st)) return e;
+    if (int e = launch_gemm<256, 2, 4>("head_bwd_dx_gemm", ma, mb, make_shape(B_tot, D, n_s, 256, splits), epi, st)) return e;
   }
   // 3. dW = normalize_bwd(dcos^T (n_s x B_tot) * X (B_tot x D)): A = dcos^T, B = X^T (D x B_tot), K = B_tot
   {
@@ -555,7 +559,7 @@ extern "C" int msml_head_bwd(const void* x, const void* x_t, int64_t ld_xt, cons
     if (int e = encode_tmap_bf16_kmajor(&ma, h.dcos_t, n_s, B_tot, h.ld_t, kBlockM)) return e;
     if (int e = encode_tmap_bf16_kmajor(&mb, x_t, D, B_tot, ld_xt, 256)) return e;
     EpiDwNormBwd epi{static_cast<const __nv_bfloat16*>(wn), inv_norm, dw, (int)n_s, (int)D};
-    if (int e = launch_gemm<512, 1, 2>(ma, mb, make_shape(n_s, 512, B_tot, 512), epi, st)) return e;
+    if (int e = launch_gemm<512, 1, 2>("head_bwd_dw_gemm", ma, mb, make_shape(n_s, D, B_tot, 512), epi, st)) return e;
   }
   return 0;
 }

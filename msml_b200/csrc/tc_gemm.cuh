@@ -278,7 +278,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 int encode_tmap_bf16_kmajor(CUtensorMap* out, const void* base, int64_t rows, int64_t k, int64_t ld_elems, int box_rows);
 
 template <int BLOCK_N, int ACC_STAGES, int STAGES, class Epi>
-int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& shape, const Epi& epi, cudaStream_t st) {
+int launch_gemm(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& shape, const Epi& epi,
+                cudaStream_t st) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   auto kern = gemm_kernel<BLOCK_N, ACC_STAGES, STAGES, Epi>;
   static thread_local bool configured = false;   // per template instantiation
@@ -290,6 +291,7 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& s
   int grid = num_sms();
   if (units < grid) grid = units;
   if (grid < 1) grid = 1;
+  MSML_PROF(name, 2.0 * shape.M * shape.N * shape.K, st);
   kern<<<grid, kThreads, L::kTotal, st>>>(ma, mb, shape, epi);
   MSML_LAUNCH_CHECK();
   return 0;

@@ -103,3 +103,29 @@ def test_sample_overflow_uses_positive_set():
     tl, index = partial_fc.sample(g["r0.s0.label"], g["r0.s0.perm"], 0, 40, 4, 0.1)
     assert np.array_equal(index, np.unique(g["r0.s0.label"]))
     assert np.array_equal(index, g["r0.s0.index"])
+
+
+def test_model_cpu_matches_reference():
+    """oracle.model_cpu (functional torch-CPU restatement) vs the reference MSML's own outputs."""
+    import torch
+    from oracle import model_cpu
+    from oracle.detfill import det_labels, det_tensor, fill_state_dict_
+    from msml_b200.backbones import MSML
+    g = load_golden("model_iresnet18")
+    net = MSML("iresnet18", "unet", (1, 1, 1, 1), 97, header_type="AMArcFace", fm_params=(3, 2, "sigmoid", "mul"))
+    fill_state_dict_(net)           # same keys/shapes as the reference => same deterministic weights
+    sd = model_cpu.trainable_state(net)
+    x = det_tensor("model.x", (2, 3, 112, 112))
+    with torch.no_grad():
+        feat, seg = model_cpu.msml_forward(sd, x, "iresnet18", training=False)
+    close(feat, g["eval_feature"], 1e-4, 1e-4)
+    close(seg, g["eval_seg"], 1e-4, 1e-4)
+    label = det_labels("model.l", 2, 97)
+    feat, seg = model_cpu.msml_forward(sd, x, "iresnet18", training=True)
+    cls = model_cpu.am_head(sd["classification.weight"], feat, label, "arc", 64.0, 0.5)
+    close(cls.detach(), g["train_cls"], 1e-3, 1e-3)
+    loss = torch.nn.functional.cross_entropy(cls, label) + seg.mean()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    loss.backward()
+    for key in ("frb.conv1.weight", "frb.layer4.1.bn3.weight", "osb.deconv5.weight"):
+        close(sd[key].grad, g["grad." + key], 2e-3, 2e-3 * float(np.abs(g["grad." + key]).max()))
