@@ -143,8 +143,8 @@ def collect_profile(lib):
     lib.msml_profile_collect(buf, len(buf))
     out = {}
     for line in buf.value.decode().splitlines():
-        name, n, ms, work = line.split()
-        out[name] = dict(launches=int(n), total_ms=float(ms), work=float(work))
+        name, n, ms, work, nbytes = line.split()
+        out[name] = dict(launches=int(n), total_ms=float(ms), work=float(work), min_bytes=float(nbytes))
     return out
 
 
@@ -154,6 +154,14 @@ def roofline_entry(name, rec, pk, sustained=True):
     if name.endswith("_gemm"):
         peak = pk["tf_sustained"] if sustained else pk["tf_burst"]
         ach = per_launch / avg_s / 1e12
+        bytes_pl = rec.get("min_bytes", 0.0) / rec["launches"]
+        t_tensor, t_hbm = per_launch / (peak * 1e12), bytes_pl / (pk["hbm"] * 1e9)
+        if t_hbm > t_tensor:   # short-M contraction: the class-centre stream binds, not the tensor pipe
+            gbs = bytes_pl / avg_s / 1e9
+            return dict(kernel=name, bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
+                        traffic=None, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=bytes_pl,
+                        tflops=round(ach, 2), note="HBM-bound at this M: min bytes = operands + outputs streamed once",
+                        peak_source=pk["source"])
         return dict(kernel=name, bound="tensor", achieved=round(ach, 2), peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4),
                     traffic=None, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
                     peak_source=pk["source"] + (", sustained" if sustained else ", burst"))

@@ -149,9 +149,9 @@ int msml_head_merge_stats(const float* gathered, int64_t W, int64_t B_tot, float
                           void* stream);
 /* :144-169  recompute the logits tile by tile, form grad = (softmax - smoothed one-hot) / B_tot,
  * chain through the margin, and contract: dX_full = dcos Wn (B_tot, D) fp32 (this rank's partial,
- * to be reduce-scattered), dW = normalize_bwd(dcos^T X) (n_s, D) fp32. */
-int msml_head_bwd(const void* x_bf16, const void* x_t_bf16, int64_t ld_xt, const void* wn_bf16,
-                  const void* wn_t_bf16, int64_t ld_wt, const float* inv_norm, const int64_t* tl,
+ * to be reduce-scattered), dW = normalize_bwd(dcos^T X) (n_s, D) fp32.  dcos, Wn and X are read in
+ * place by MN-major UMMA operands: no transposed copies. */
+int msml_head_bwd(const void* x_bf16, const void* wn_bf16, const float* inv_norm, const int64_t* tl,
                   int64_t B_tot, int64_t n_s, int64_t D, const msml_margin_params* margin_host,
                   const float* gstats, float* dx_full, float* dw,
                   void* workspace, size_t workspace_bytes, void* stream);
@@ -168,6 +168,10 @@ int msml_margin_bwd(float* dlogits_inout, const float* cos, const int64_t* label
  * C (M, N) fp32 = A (M, K) bf16 * B (N, K)^T bf16, K-major operands, lda/ldb in elements (%8). */
 int msml_gemm_bf16_tn(const void* a, int64_t lda, const void* b, int64_t ldb, float* c, int64_t ldc,
                       int64_t M, int64_t N, int64_t K, void* stream);
+/* Same contraction with per-operand storage: a_mn != 0 => A stored (K, M) row-major (M contiguous),
+ * b_mn != 0 => B stored (K, N) row-major.  block_n in {256, 512} selects the accumulator tile. */
+int msml_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, float* c,
+                   int64_t ldc, int64_t M, int64_t N, int64_t K, int block_n, void* stream);
 
 #ifdef __cplusplus
 }

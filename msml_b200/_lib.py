@@ -55,10 +55,11 @@ SIGNATURES = {
     "msml_head_workspace": (c_size, [c_i64, c_i64, c_i64]),
     "msml_head_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p, c_p, c_size, c_p]),
     "msml_head_merge_stats": (c_int, [c_p, c_i64, c_i64, c_p, c_p, c_p]),
-    "msml_head_bwd": (c_int, [c_p, c_p, c_i64, c_p, c_p, c_i64, c_p, c_p, c_i64, c_i64, c_i64,
+    "msml_head_bwd": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64,
                               ctypes.POINTER(MarginParams), c_p, c_p, c_p, c_p, c_size, c_p]),
     "msml_margin_fwd": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p]),
     "msml_margin_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p]),
+    "msml_gemm_bf16": (c_int, [c_p, c_i64, c_int, c_p, c_i64, c_int, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
     "msml_gemm_bf16_tn": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_i64, c_p]),
 }
 

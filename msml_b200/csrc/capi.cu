@@ -39,14 +39,14 @@ int num_sms() {
 }
 
 // ---- profiling -------------------------------------------------------------------------------
-struct ProfRec { const char* name; double work; cudaEvent_t a, b; };
+struct ProfRec { const char* name; double work, bytes; cudaEvent_t a, b; };
 static std::atomic<bool> g_prof_on{false};
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
 
-ProfScope::ProfScope(const char* name, double work, cudaStream_t stream) : slot(-1), st(stream) {
+ProfScope::ProfScope(const char* name, double work, cudaStream_t stream, double bytes) : slot(-1), st(stream) {
   if (!g_prof_on.load(std::memory_order_relaxed)) return;
-  ProfRec r{name, work, nullptr, nullptr};
+  ProfRec r{name, work, bytes, nullptr, nullptr};
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
   cudaEventRecord(r.a, st);
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -63,17 +63,18 @@ ProfScope::~ProfScope() {
 
 extern "C" void msml_profile_enable(int on) { msml::g_prof_on.store(on != 0); }
 
-// Synchronises, then writes one line per kernel family: "name launches total_ms total_work\n".
+// Synchronises, then writes one line per kernel family: "name launches total_ms total_work total_min_bytes\n".
 // Returns the number of bytes written (excluding the terminator) and clears the records.
 extern "C" int64_t msml_profile_collect(char* buf, int64_t cap) {
   using namespace msml;
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  std::map<std::string, std::pair<int64_t, std::pair<double, double>>> agg;
+  struct Agg { int64_t n = 0; double ms = 0, work = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
   for (auto& r : g_prof) {
     float ms = 0.f;
     if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
       auto& e = agg[r.name];
-      e.first += 1; e.second.first += ms; e.second.second += r.work;
+      e.n += 1; e.ms += ms; e.work += r.work; e.bytes += r.bytes;
     }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -82,8 +83,8 @@ extern "C" int64_t msml_profile_collect(char* buf, int64_t cap) {
   std::string out;
   char line[256];
   for (auto& kv : agg) {
-    snprintf(line, sizeof(line), "%s %lld %.6f %.6e\n", kv.first.c_str(), (long long)kv.second.first,
-             kv.second.second.first, kv.second.second.second);
+    snprintf(line, sizeof(line), "%s %lld %.6f %.6e %.6e\n", kv.first.c_str(), (long long)kv.second.n, kv.second.ms,
+             kv.second.work, kv.second.bytes);
     out += line;
   }
   if (buf && cap > 0) {

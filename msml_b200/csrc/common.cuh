@@ -41,13 +41,16 @@ void count_launch(int n = 1);
 
 // ---- optional per-launch timing (CUDA events on the launching stream; msml_profile_*) ----------
 // `work` is the ALGORITHMIC work of the launch: bytes for HBM-bound kernels, flops for GEMMs.
+// `bytes` (optional) is the minimum HBM traffic of a contraction, so that short-M GEMMs can be
+// reported against the roofline that actually binds them.
 struct ProfScope {
   int slot;
   cudaStream_t st;
-  ProfScope(const char* name, double work, cudaStream_t stream);
+  ProfScope(const char* name, double work, cudaStream_t stream, double bytes = 0.0);
   ~ProfScope();
 };
 #define MSML_PROF(name, work, stream) ::msml::ProfScope _prof_scope((name), (double)(work), (stream))
+#define MSML_PROF2(name, work, bytes, stream) ::msml::ProfScope _prof_scope((name), (double)(work), (stream), (double)(bytes))
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

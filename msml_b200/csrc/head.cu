@@ -36,20 +36,24 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_bf16_kmajor(CUtensorMap* out, const void* base, int64_t rows, int64_t k, int64_t ld_elems, int box_rows) {
+int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, int64_t inner, int64_t outer, int64_t ld_elems,
+                   int box_inner, int box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   MSML_REQUIRE(fn != nullptr, MSML_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  MSML_REQUIRE(elem_bytes == 2 || elem_bytes == 4, MSML_EINVAL, "tensor map element size %d", elem_bytes);
   MSML_REQUIRE(aligned16(base), MSML_EALIGN, "TMA operand base must be 16-byte aligned");
-  MSML_REQUIRE(ld_elems % 8 == 0 && ld_elems >= k, MSML_EALIGN, "TMA operand pitch %lld must be a multiple of 8 elements and >= k=%lld",
-               (long long)ld_elems, (long long)k);
-  MSML_REQUIRE(rows > 0 && k > 0 && box_rows > 0 && box_rows <= 256, MSML_EINVAL, "bad TMA operand shape");
-  const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  const cuuint64_t gstr[1] = {(cuuint64_t)ld_elems * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  MSML_REQUIRE((ld_elems * elem_bytes) % 16 == 0 && ld_elems >= inner, MSML_EALIGN,
+               "TMA operand pitch %lld elements must be 16-byte aligned and >= inner extent %lld", (long long)ld_elems,
+               (long long)inner);
+  MSML_REQUIRE(inner > 0 && outer > 0 && box_inner * elem_bytes == 128 && box_outer > 0 && box_outer <= 256, MSML_EINVAL,
+               "bad TMA operand shape");
+  const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld_elems * elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MSML_REQUIRE(r == CUDA_SUCCESS, MSML_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
@@ -81,12 +85,35 @@ __device__ __forceinline__ float margin_target_grad(const Margin& mg, float c) {
 }
 
 // ------------------------------------------------------------------------------- epilogues
+// Shared structure: a thread owns accumulator row (quarter*32 + lane); the 32-column TMEM chunks are
+// double-buffered in registers (the tcgen05.ld of chunk c+1 is in flight while chunk c is processed).
+// Tile outputs leave through a per-warp swizzled smem staging buffer and a TMA store (fully coalesced
+// 128-byte rows, out-of-range rows/columns clipped by the tensor map) — never through per-thread
+// scattered global stores.
+
+// pick / replace element `idx` (0..31, warp-divergent allowed) without dynamic register indexing
+__device__ __forceinline__ float pick32(const float* v, int idx) {
+  float r = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) r = (j == idx) ? v[j] : r;
+  return r;
+}
+__device__ __forceinline__ void put32(float* v, int idx, float x) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = (j == idx) ? x : v[j];
+}
+
+struct NoScratch {
+  static constexpr int kSmemBytes = 0;
+  __device__ void finish(int, int) const {}
+};
+
 // plain store (tests / in-model heads): C[row, col] = acc
-struct EpiStore {
+struct EpiStore : NoScratch {
   float* c;
   int64_t ldc;
   int M, N, block_n;
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*) const {
     const int row = m_blk * kBlockM + quarter * 32 + lane;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
     for (int c0 = 0; c0 < block_n; c0 += 32) {
@@ -103,43 +130,56 @@ struct EpiStore {
 };
 
 // forward: margin + scale + online (max, sum exp2) in the log2 domain
-struct EpiFwdStats {
+struct EpiFwdStats : NoScratch {
   const int64_t* tl;
   Margin mg;
   int B_tot, n_s, block_n;
   float* part_max;   // [n_blocks][B_tot]  (log2 domain: logit * log2e)
   float* part_sum;   // [n_blocks][B_tot]
   float* tgt;        // [B_tot] target logit (natural units), written by the tile that owns the column
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*) const {
     const int row = m_blk * kBlockM + quarter * 32 + lane;
     const bool row_ok = row < B_tot;
     const int64_t label = row_ok ? tl[row] : -1;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
     const float s2 = mg.s * kLog2e;
+    const int tile_col0 = n_blk * block_n;
+    int n_chunks = (n_s - tile_col0 + 31) / 32;            // warp-uniform
+    if (n_chunks > block_n / 32) n_chunks = block_n / 32;
     float run_max = -INFINITY, run_sum = 0.f;
-    for (int c0 = 0; c0 < block_n; c0 += 32) {
-      float v[32];
-      tmem_ld32(taddr + c0, v);
-      const int col0 = n_blk * block_n + c0;
-      if (col0 >= n_s) break;   // warp-uniform
-      const int64_t rel = label - col0;
-      if (rel >= 0 && rel < 32) {
+    float buf[2][32];
+    tmem_ld32_issue(taddr, buf[0]);
+    tmem_ld_wait(buf[0]);
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; c += 2) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j == (int)rel) { v[j] = margin_target(mg, v[j]); tgt[row] = v[j] * mg.s; }
+      for (int h = 0; h < 2; ++h) {
+        if (c + h >= n_chunks) break;
+        float* cur = buf[h];
+        if (c + h + 1 < n_chunks) tmem_ld32_issue(taddr + (c + h + 1) * 32, buf[h ^ 1]);
+        float* v = cur;
+        const int col0 = tile_col0 + (c + h) * 32;
+        const int64_t rel = label - col0;
+        if (rel >= 0 && rel < 32) {                       // at most one row-chunk pair per row
+          const float t = margin_target(mg, pick32(v, (int)rel));
+          put32(v, (int)rel, t);
+          tgt[row] = t * mg.s;
+        }
+        const int valid = n_s - col0;                      // >= 1
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = (j < valid) ? v[j] * s2 : -INFINITY;
+          cmax = fmaxf(cmax, v[j]);
+        }
+        const float new_max = fmaxf(run_max, cmax);        // finite: column col0 < n_s exists
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc += fast_exp2(v[j] - new_max);
+        run_sum = run_sum * fast_exp2(run_max - new_max) + acc;
+        run_max = new_max;
+        if (c + h + 1 < n_chunks) tmem_ld_wait(buf[h ^ 1]);
       }
-      float cmax = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = (col0 + j < n_s) ? v[j] * s2 : -INFINITY;
-        cmax = fmaxf(cmax, v[j]);
-      }
-      const float new_max = fmaxf(run_max, cmax);   // finite: column col0 < n_s exists
-      float acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc += fast_exp2(v[j] - new_max);
-      run_sum = run_sum * fast_exp2(run_max - new_max) + acc;
-      run_max = new_max;
     }
     if (row_ok) {
       part_max[(int64_t)n_blk * B_tot + row] = run_max;
@@ -148,70 +188,119 @@ struct EpiFwdStats {
   }
 };
 
-// backward pass 1: recompute logits, emit dcos (bf16) row-major and transposed
+// per-warp staging: 2 buffers of 4 KB (32 rows x 128 B, SWIZZLE_128B) feeding TMA stores
+struct StageOut {
+  static constexpr int kBytesPerWarp = 2 * 4096;
+  // store this thread's 128-byte row `lane` (8 x uint4) into buffer `b`, then TMA-store the 32-row box
+  __device__ static __forceinline__ void put_and_store(uint8_t* warp_scratch, int b, int lane, const uint4* row8,
+                                                       const CUtensorMap* map, int c0, int c1) {
+    uint8_t* buf = warp_scratch + b * 4096;
+    if (lane == 0) bulk_wait_read<1>();    // the store that last used this buffer (2 stores ago) has read it
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(buf + swz128(lane, q)) = row8[q];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(map, buf, c0, c1); bulk_commit(); }
+  }
+  __device__ static __forceinline__ void drain(int lane) {
+    if (lane == 0) bulk_wait<0>();
+    __syncwarp();
+  }
+};
+
+// backward pass 1: recompute logits, emit dcos (bf16, row-major) and rdot[n] = sum_m dcos[m,n] cos[m,n]
 struct EpiBwdDcos {
+  static constexpr int kSmemBytes = 4 * StageOut::kBytesPerWarp;   // 32 KB
+  CUtensorMap map_dcos;        // bf16 (B_tot x n_s), boxes 64 cols x 32 rows
   const int64_t* tl;
   Margin mg;
   int B_tot, n_s, block_n;
   const float* gmax;   // [B_tot] global row max   (natural units)
   const float* gsum;   // [B_tot] global row sum of exp(logit - max)
-  __nv_bfloat16* dcos;     // (B_tot, ld_dc)
-  int64_t ld_dc;
-  __nv_bfloat16* dcos_t;   // (n_s, ld_t)
-  int64_t ld_t;
+  float* rdot;         // [n_s] zero-initialised; <Wn[n], dWn[n]> for the normalise backward
   float smooth_on, smooth_off, inv_btot;
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane) const {
-    const int row = m_blk * kBlockM + quarter * 32 + lane;
+  __device__ void finish(int, int lane) const { StageOut::drain(lane); }
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch) const {
+    const int row0 = m_blk * kBlockM + quarter * 32;
+    const int row = row0 + lane;
     const bool row_ok = row < B_tot;
     const int64_t label = row_ok ? tl[row] : -1;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* wscr = scratch + quarter * StageOut::kBytesPerWarp;
     const float s2 = mg.s * kLog2e;
     // p = exp2(logit*log2e - off),  off = max*log2e + log2(sum)
-    const float off = row_ok ? fmaf(gmax[row], kLog2e, log2f(gsum[row])) : 0.f;
-    const float t_off = label >= 0 ? smooth_off : 0.f;   // rows without a local target: one_hot row absent
-    const float gs = mg.s * inv_btot;
-    for (int c0 = 0; c0 < block_n; c0 += 32) {
-      float v[32];
-      tmem_ld32(taddr + c0, v);
-      const int col0 = n_blk * block_n + c0;
-      if (col0 >= n_s) break;   // warp-uniform
-      const int64_t rel = label - col0;
-      float tgt_mult = 1.f;
-      const bool has_t = rel >= 0 && rel < 32;
-      if (has_t) {
+    const float off = row_ok ? fmaf(gmax[row], kLog2e, log2f(gsum[row])) : INFINITY;   // dead rows: p = 0
+    const float t_off = label >= 0 ? smooth_off : 0.f;   // rows without a local target: no one-hot row (ref :166)
+    const float gs = row_ok ? mg.s * inv_btot : 0.f;
+    const int tile_col0 = n_blk * block_n;
+    int n_chunks = (n_s - tile_col0 + 31) / 32;
+    if (n_chunks > block_n / 32) n_chunks = block_n / 32;
+    float buf[2][32];
+    uint4 packed[8];
+    tmem_ld32_issue(taddr, buf[0]);
+    tmem_ld_wait(buf[0]);
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; c += 2) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j == (int)rel) { tgt_mult = margin_target_grad(mg, v[j]); v[j] = margin_target(mg, v[j]); }
-      }
+      for (int h = 0; h < 2; ++h) {
+        if (c + h < n_chunks) {
+          float* cur = buf[h];
+          if (c + h + 1 < n_chunks) tmem_ld32_issue(taddr + (c + h + 1) * 32, buf[h ^ 1]);
+          float* v = cur;
+          const int col0 = tile_col0 + (c + h) * 32;
+          const int64_t rel = label - col0;
+          const bool has_t = rel >= 0 && rel < 32;
+          float cos_t = 0.f, tgt_mult = 1.f, tgt_logit = 0.f;
+          if (has_t) {
+            cos_t = pick32(v, (int)rel);
+            tgt_mult = margin_target_grad(mg, cos_t);
+            tgt_logit = margin_target(mg, cos_t);
+          }
+          float pr[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float p = fast_exp2(fmaf(v[j], s2, -off));
-        const bool is_t = has_t && j == (int)rel;
-        float g = (p - (is_t ? smooth_on : t_off)) * gs;
-        if (is_t) g *= tgt_mult;
-        v[j] = g;
-      }
-      if (row_ok) {
-        __nv_bfloat16* drow = dcos + (int64_t)row * ld_dc + col0;
-        if (col0 + 32 <= n_s) {
+          for (int j = 0; j < 32; ++j) {
+            const bool is_t = has_t && j == (int)rel;
+            const float logit = is_t ? tgt_logit : v[j];
+            const float p = fast_exp2(fmaf(logit, s2, -off));
+            float g = (p - (is_t ? smooth_on : t_off)) * gs;
+            g = is_t ? g * tgt_mult : g;
+            g = (col0 + j < n_s) ? g : 0.f;
+            pr[j] = g * v[j];            // dcos * raw cosine
+            v[j] = g;
+          }
+          // bf16 pack: 32 values = 64 bytes = 4 x uint4 -> half `h` of the 128-byte staging row
 #pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(drow + q * 8) = Vec<__nv_bfloat16>::pack(v + q * 8);
+          for (int q = 0; q < 4; ++q) packed[h * 4 + q] = Vec<__nv_bfloat16>::pack(v + q * 8);
+          // column sums over the 32 rows of this warp by recursive halving (31 shuffles), then one
+          // red per lane: rdot[col0 + lane] += sum_rows pr[.][lane]
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int i = 0; i < sft; ++i) {
+              const float send = up ? pr[i] : pr[i + sft];
+              const float keep = up ? pr[i + sft] : pr[i];
+              pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            }
+          }
+          if (col0 + lane < n_s) atomicAdd(rdot + col0 + lane, pr[0]);
+          if (c + h + 1 < n_chunks) tmem_ld_wait(buf[h ^ 1]);
         } else {
-          for (int j = 0; j < 32 && col0 + j < n_s; ++j) drow[j] = __float2bfloat16_rn(v[j]);
-        }
 #pragma unroll
-        for (int j = 0; j < 32; ++j)   // lanes = consecutive rows: 64-byte coalesced segments
-          if (col0 + j < n_s) dcos_t[(int64_t)(col0 + j) * ld_t + row] = __float2bfloat16_rn(v[j]);
+          for (int q = 0; q < 4; ++q) packed[h * 4 + q] = make_uint4(0, 0, 0, 0);
+        }
       }
+      StageOut::put_and_store(wscr, (c >> 1) & 1, lane, packed, &map_dcos, tile_col0 + c * 32, row0);
     }
   }
 };
 
 // backward pass 2: dX += partial (split-K over classes)
-struct EpiDxAccum {
+struct EpiDxAccum : NoScratch {
   float* dx;   // (B_tot, D) fp32, zero-initialised
   int B_tot, D, block_n;
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*) const {
     const int row = m_blk * kBlockM + quarter * 32 + lane;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
     for (int c0 = 0; c0 < block_n; c0 += 32) {
@@ -234,44 +323,73 @@ struct EpiDxAccum {
   }
 };
 
-// backward pass 3: dW = (dWn - Wn * <Wn, dWn>) * inv_norm      (ref :115 normalize backward)
+// backward pass 3: dW = (dWn - Wn * rdot) * inv_norm      (ref :115 normalize backward), one pass.
+// Wn tile rows arrive through cp.async (coalesced 128-byte rows -> swizzled smem, 2 boxes in flight),
+// dW leaves through TMA stores.
 struct EpiDwNormBwd {
-  const __nv_bfloat16* wn;   // (n_s, D)
-  const float* inv_norm;     // (n_s)
-  float* dw;                 // (n_s, D) fp32
+  static constexpr int kWnBytesPerWarp = 2 * 4096;                  // 2 boxes of 32 rows x 64 bf16
+  static constexpr int kSmemBytes = 4 * (StageOut::kBytesPerWarp + kWnBytesPerWarp);   // 64 KB
+  CUtensorMap map_dw;          // fp32 (n_s x D), boxes 32 cols x 32 rows
+  const __nv_bfloat16* wn;     // (n_s, D)
+  const float* inv_norm;       // (n_s)
+  const float* rdot;           // (n_s)
   int n_s, D;
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int, int, int quarter, int lane) const {
-    const int row = m_blk * kBlockM + quarter * 32 + lane;   // class index
+  __device__ void finish(int, int lane) const { StageOut::drain(lane); }
+  // warp-cooperative async load of Wn[row0 .. row0+32, col0 .. col0+64) into a swizzled 4 KB box
+  __device__ __forceinline__ void load_wn_box(uint8_t* box, int row0, int col0, int lane) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3), ch = lane & 7;
+      const bool ok = row0 + r < n_s;
+      cp_async16(box + swz128(r, ch), wn + (int64_t)(ok ? row0 + r : 0) * D + col0 + ch * 8, ok);
+    }
+    cp_async_commit();
+  }
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch) const {
+    const int row0 = m_blk * kBlockM + quarter * 32;
+    const int row = row0 + lane;                     // class index
+    const int dcol0 = n_blk * 256;                   // this tile covers D columns [dcol0, dcol0 + 256)
     const bool ok = row < n_s;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    const __nv_bfloat16* wrow = wn + (int64_t)(ok ? row : 0) * D;
-    float dot = 0.f;
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      float v[32], w[32];
-      tmem_ld32(taddr + c0, v);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) Vec<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(wrow + c0 + q * 8), w + q * 8);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dot = fmaf(v[j], w[j], dot);
-    }
+    uint8_t* wout = scratch + quarter * StageOut::kBytesPerWarp;
+    uint8_t* wwn = scratch + 4 * StageOut::kBytesPerWarp + quarter * kWnBytesPerWarp;
     const float inv = ok ? inv_norm[row] : 0.f;
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      float v[32], w[32];
-      tmem_ld32(taddr + c0, v);
+    const float cdot = ok ? rdot[row] * inv : 0.f;   // (acc - w*rdot)*inv = acc*inv - w*cdot
+    int n_boxes = (D - dcol0) / 64;
+    if (n_boxes > 4) n_boxes = 4;
+    float buf[2][32];
+    load_wn_box(wwn, row0, dcol0, lane);
+    tmem_ld32_issue(taddr, buf[0]);
+    tmem_ld_wait(buf[0]);
+#pragma unroll 1
+    for (int bx = 0; bx < n_boxes; ++bx) {
+      if (bx + 1 < n_boxes) { load_wn_box(wwn + ((bx + 1) & 1) * 4096, row0, dcol0 + (bx + 1) * 64, lane); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncwarp();
+      const uint8_t* wbox = wwn + (bx & 1) * 4096;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) Vec<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(wrow + c0 + q * 8), w + q * 8);
-      if (ok) {
-        float* o = dw + (int64_t)row * D + c0;
+      for (int h = 0; h < 2; ++h) {
+        const int c = bx * 2 + h;
+        float* cur = buf[h];
+        if (c + 1 < 2 * n_boxes) tmem_ld32_issue(taddr + (c + 1) * 32, buf[h ^ 1]);
+        const float* v = cur;
+        float w[32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Vec<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(wbox + swz128(lane, h * 4 + q)), w + q * 8);
+        uint4 out[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 r;
-          r.x = (v[q * 4 + 0] - w[q * 4 + 0] * dot) * inv;
-          r.y = (v[q * 4 + 1] - w[q * 4 + 1] * dot) * inv;
-          r.z = (v[q * 4 + 2] - w[q * 4 + 2] * dot) * inv;
-          r.w = (v[q * 4 + 3] - w[q * 4 + 3] * dot) * inv;
-          __stcs(reinterpret_cast<float4*>(o + q * 4), r);
+          r.x = fmaf(v[q * 4 + 0], inv, -w[q * 4 + 0] * cdot);
+          r.y = fmaf(v[q * 4 + 1], inv, -w[q * 4 + 1] * cdot);
+          r.z = fmaf(v[q * 4 + 2], inv, -w[q * 4 + 2] * cdot);
+          r.w = fmaf(v[q * 4 + 3], inv, -w[q * 4 + 3] * cdot);
+          out[q] = make_uint4(__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z), __float_as_uint(r.w));
         }
+        StageOut::put_and_store(wout, c & 1, lane, out, &map_dw, dcol0 + c * 32, row0);
+        if (c + 1 < 2 * n_boxes) tmem_ld_wait(buf[h ^ 1]);
       }
+      __syncwarp();   // every lane is done with this Wn box before it is refilled
     }
   }
 };
@@ -393,13 +511,13 @@ static int to_margin(const msml_margin_params* p, Margin* out) {
 
 // workspace carving
 struct HeadWs {
-  float* part_max; float* part_sum; float* tgt;
-  __nv_bfloat16* dcos; __nv_bfloat16* dcos_t;
-  int64_t ld_dc, ld_t;
+  float* part_max; float* part_sum; float* tgt; float* rdot;
+  __nv_bfloat16* dcos;
+  int64_t ld_dc;
   int n_blocks;
   size_t bytes;
 };
-constexpr int kFwdBlockN = 256;
+constexpr int kFwdBlockN = 128;   // granularity of the per-tile softmax partials (smallest class tile)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -407,14 +525,13 @@ static HeadWs carve(void* ws, int64_t B_tot, int64_t n_s) {
   HeadWs h;
   h.n_blocks = (int)((n_s + kFwdBlockN - 1) / kFwdBlockN);
   h.ld_dc = (n_s + 7) / 8 * 8;
-  h.ld_t = (B_tot + 7) / 8 * 8;
   size_t off = 0;
   char* base = static_cast<char*>(ws);
   h.part_max = reinterpret_cast<float*>(base + off); off = align_up(off + sizeof(float) * h.n_blocks * B_tot, 256);
   h.part_sum = reinterpret_cast<float*>(base + off); off = align_up(off + sizeof(float) * h.n_blocks * B_tot, 256);
   h.tgt = reinterpret_cast<float*>(base + off); off = align_up(off + sizeof(float) * B_tot, 256);
+  h.rdot = reinterpret_cast<float*>(base + off); off = align_up(off + sizeof(float) * n_s, 256);
   h.dcos = reinterpret_cast<__nv_bfloat16*>(base + off); off = align_up(off + 2 * (size_t)B_tot * h.ld_dc, 256);
-  h.dcos_t = reinterpret_cast<__nv_bfloat16*>(base + off); off = align_up(off + 2 * (size_t)n_s * h.ld_t, 256);
   h.bytes = off;
   return h;
 }
@@ -431,8 +548,35 @@ extern "C" int msml_gemm_bf16_tn(const void* a, int64_t lda, const void* b, int6
   CUtensorMap ma, mb;
   if (int e = encode_tmap_bf16_kmajor(&ma, a, M, K, lda, kBlockM)) return e;
   if (int e = encode_tmap_bf16_kmajor(&mb, b, N, K, ldb, 256)) return e;
-  EpiStore epi{c, ldc, (int)M, (int)N, 256};
-  return launch_gemm<256, 2, 4>("gemm_bf16_tn", ma, mb, make_shape(M, N, K, 256), epi, (cudaStream_t)stream);
+  EpiStore epi;
+  epi.c = c; epi.ldc = ldc; epi.M = (int)M; epi.N = (int)N; epi.block_n = 256;
+  return launch_gemm<256, 2, 4, false, false>("gemm_bf16_tn", ma, mb, make_shape(M, N, K, 256), epi, (cudaStream_t)stream);
+}
+
+// Generic layouts for the tests of the MN-major operand paths:  C (M x N) = op(A) * op(B)^T where
+// a_mn != 0 means A is stored (K x M) row-major, b_mn != 0 means B is stored (K x N) row-major.
+extern "C" int msml_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, float* c,
+                              int64_t ldc, int64_t M, int64_t N, int64_t K, int block_n, void* stream) {
+  MSML_REQUIRE(a && b && c && M > 0 && N > 0 && K > 0, MSML_EINVAL, "bad GEMM arguments");
+  MSML_REQUIRE(block_n == 256 || block_n == 512, MSML_EINVAL, "block_n must be 256 or 512");
+  CUtensorMap ma, mb;
+  if (int e = a_mn ? encode_tmap_bf16_mnmajor(&ma, a, M, K, lda) : encode_tmap_bf16_kmajor(&ma, a, M, K, lda, kBlockM)) return e;
+  if (int e = b_mn ? encode_tmap_bf16_mnmajor(&mb, b, N, K, ldb) : encode_tmap_bf16_kmajor(&mb, b, N, K, ldb, 256)) return e;
+  EpiStore epi;
+  epi.c = c; epi.ldc = ldc; epi.M = (int)M; epi.N = (int)N; epi.block_n = block_n;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GemmShape sh = make_shape(M, N, K, block_n);
+  const int sel = (block_n == 512 ? 4 : 0) + (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
+  switch (sel) {
+    case 0: return launch_gemm<256, 2, 4, false, false>("gemm_bf16", ma, mb, sh, epi, st);
+    case 1: return launch_gemm<256, 2, 4, false, true>("gemm_bf16", ma, mb, sh, epi, st);
+    case 2: return launch_gemm<256, 2, 4, true, false>("gemm_bf16", ma, mb, sh, epi, st);
+    case 3: return launch_gemm<256, 2, 4, true, true>("gemm_bf16", ma, mb, sh, epi, st);
+    case 4: return launch_gemm<512, 1, 2, false, false>("gemm_bf16", ma, mb, sh, epi, st);
+    case 5: return launch_gemm<512, 1, 2, false, true>("gemm_bf16", ma, mb, sh, epi, st);
+    case 6: return launch_gemm<512, 1, 2, true, false>("gemm_bf16", ma, mb, sh, epi, st);
+    default: return launch_gemm<512, 1, 2, true, true>("gemm_bf16", ma, mb, sh, epi, st);
+  }
 }
 
 extern "C" int msml_wnorm_cast(const float* w, void* wn, void* wn_t, int64_t ld_t, float* inv_norm, int64_t n, int64_t D,
@@ -485,6 +629,16 @@ extern "C" size_t msml_head_workspace(int64_t B_tot, int64_t n_s, int64_t D) {
   return carve(nullptr, B_tot, n_s).bytes;
 }
 
+// class-tile width for the logits GEMMs: the one that fills the last wave of the persistent grid best
+static int pick_block_n(int64_t B_tot, int64_t n_s) {
+  const int64_t mb = (B_tot + kBlockM - 1) / kBlockM, sms = num_sms();
+  auto eff = [&](int bn) {
+    const int64_t tiles = mb * ((n_s + bn - 1) / bn);
+    return (double)tiles / (double)(((tiles + sms - 1) / sms) * sms);
+  };
+  return eff(256) >= eff(128) - 0.02 ? 256 : 128;
+}
+
 static int head_check(int64_t B_tot, int64_t n_s, int64_t D, void* ws, size_t ws_bytes) {
   MSML_REQUIRE(B_tot > 0 && n_s > 1 && D > 0, MSML_EINVAL, "bad head shape B_tot=%lld n_s=%lld D=%lld", (long long)B_tot,
                (long long)n_s, (long long)D);
@@ -503,12 +657,21 @@ extern "C" int msml_head_fwd(const void* x, const void* wn, const int64_t* tl, i
   if (int e = to_margin(margin, &mg)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   HeadWs h = carve(ws, B_tot, n_s);
+  const int bn = pick_block_n(B_tot, n_s);
   CUtensorMap ma, mb;
   if (int e = encode_tmap_bf16_kmajor(&ma, x, B_tot, D, D, kBlockM)) return e;
-  if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, 256)) return e;
-  EpiFwdStats epi{tl, mg, (int)B_tot, (int)n_s, kFwdBlockN, h.part_max, h.part_sum, h.tgt};
-  if (int e = launch_gemm<kFwdBlockN, 2, 4>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, kFwdBlockN), epi, st)) return e;
-  head_local_stats_kernel<<<(unsigned)((B_tot + 127) / 128), 128, 0, st>>>(h.part_max, h.part_sum, h.tgt, tl, h.n_blocks, (int)B_tot, stats);
+  if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, bn)) return e;     // box rows == UMMA_N of the tile
+  EpiFwdStats epi;
+  epi.tl = tl; epi.mg = mg; epi.B_tot = (int)B_tot; epi.n_s = (int)n_s; epi.block_n = bn;
+  epi.part_max = h.part_max; epi.part_sum = h.part_sum; epi.tgt = h.tgt;
+  const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D;      // stream Wn + X once (bf16)
+  if (bn == 256) {
+    if (int e = launch_gemm<256, 2, 4, false, false>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
+  } else {
+    if (int e = launch_gemm<128, 4, 6, false, false>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
+  }
+  const int n_blocks = (int)((n_s + bn - 1) / bn);
+  head_local_stats_kernel<<<(unsigned)((B_tot + 127) / 128), 128, 0, st>>>(h.part_max, h.part_sum, h.tgt, tl, n_blocks, (int)B_tot, stats);
   MSML_LAUNCH_CHECK();
   return 0;
 }
@@ -520,46 +683,60 @@ extern "C" int msml_head_merge_stats(const float* gathered, int64_t W, int64_t B
   return 0;
 }
 
-extern "C" int msml_head_bwd(const void* x, const void* x_t, int64_t ld_xt, const void* wn, const void* wn_t, int64_t ld_wt,
-                             const float* inv_norm, const int64_t* tl, int64_t B_tot, int64_t n_s, int64_t D,
-                             const msml_margin_params* margin, const float* gstats, float* dx_full, float* dw, void* ws,
-                             size_t ws_bytes, void* stream) {
+extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_norm, const int64_t* tl, int64_t B_tot,
+                             int64_t n_s, int64_t D, const msml_margin_params* margin, const float* gstats, float* dx_full,
+                             float* dw, void* ws, size_t ws_bytes, void* stream) {
   if (int e = head_check(B_tot, n_s, D, ws, ws_bytes)) return e;
-  MSML_REQUIRE(x && x_t && wn && wn_t && inv_norm && tl && gstats && dx_full && dw, MSML_EINVAL, "null pointer");
+  MSML_REQUIRE(x && wn && inv_norm && tl && gstats && dx_full && dw, MSML_EINVAL, "null pointer");
   MSML_REQUIRE(aligned16(dx_full) && aligned16(dw), MSML_EALIGN, "gradient buffers must be 16-byte aligned");
   Margin mg;
   if (int e = to_margin(margin, &mg)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   HeadWs h = carve(ws, B_tot, n_s);
 
-  // 1. recompute logits -> dcos (bf16), row-major and transposed
+  // 1. recompute logits -> dcos (bf16, row-major) + rdot[n] = <Wn[n], dWn[n]>
   {
+    MSML_CUDA(cudaMemsetAsync(h.rdot, 0, sizeof(float) * (size_t)n_s, st));
+    const int bn = pick_block_n(B_tot, n_s);
     CUtensorMap ma, mb;
     if (int e = encode_tmap_bf16_kmajor(&ma, x, B_tot, D, D, kBlockM)) return e;
-    if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, 256)) return e;
+    if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, bn)) return e;   // box rows == UMMA_N of the tile
     const float eps = 0.1f;   // ref partial_fc.py:154
-    EpiBwdDcos epi{tl, mg, (int)B_tot, (int)n_s, kFwdBlockN, gstats, gstats + B_tot, h.dcos, h.ld_dc, h.dcos_t, h.ld_t,
-                   1.0f - eps, eps / (float)(n_s - 1), 1.0f / (float)B_tot};
-    if (int e = launch_gemm<kFwdBlockN, 2, 4>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, kFwdBlockN), epi, st)) return e;
+    EpiBwdDcos epi;
+    if (int e = encode_tmap_2d(&epi.map_dcos, h.dcos, 2, n_s, B_tot, h.ld_dc, 64, 32)) return e;
+    epi.tl = tl; epi.mg = mg; epi.B_tot = (int)B_tot; epi.n_s = (int)n_s; epi.block_n = bn;
+    epi.gmax = gstats; epi.gsum = gstats + B_tot; epi.rdot = h.rdot;
+    epi.smooth_on = 1.0f - eps; epi.smooth_off = eps / (float)(n_s - 1); epi.inv_btot = 1.0f / (float)B_tot;
+    const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D + 2.0 * (double)B_tot * n_s;   // + dcos out
+    if (bn == 256) {
+      if (int e = launch_gemm<256, 2, 3, false, false>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
+    } else {
+      if (int e = launch_gemm<128, 4, 5, false, false>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
+    }
   }
-  // 2. dX_full = dcos (B_tot x n_s) * Wn (n_s x D): A = dcos, B = Wn^T (D x n_s), K = n_s, split-K
+  // 2. dX_full = dcos (B_tot x n_s) * Wn (n_s x D): A = dcos (K-major), B = Wn read in place (MN-major), split-K
   {
     MSML_CUDA(cudaMemsetAsync(dx_full, 0, sizeof(float) * (size_t)B_tot * D, st));
     CUtensorMap ma, mb;
     if (int e = encode_tmap_bf16_kmajor(&ma, h.dcos, B_tot, n_s, h.ld_dc, kBlockM)) return e;
-    if (int e = encode_tmap_bf16_kmajor(&mb, wn_t, D, n_s, ld_wt, 256)) return e;
+    if (int e = encode_tmap_bf16_mnmajor(&mb, wn, D, n_s, D)) return e;
     const int tiles = (int)((B_tot + kBlockM - 1) / kBlockM) * (int)((D + 255) / 256);
     int splits = (num_sms() + tiles - 1) / tiles;
-    EpiDxAccum epi{dx_full, (int)B_tot, (int)D, 256};
-    if (int e = launch_gemm<256, 2, 4>("head_bwd_dx_gemm", ma, mb, make_shape(B_tot, D, n_s, 256, splits), epi, st)) return e;
+    EpiDxAccum epi;
+    epi.dx = dx_full; epi.B_tot = (int)B_tot; epi.D = (int)D; epi.block_n = 256;
+    const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 4.0 * (double)B_tot * D;
+    if (int e = launch_gemm<256, 2, 4, false, true>("head_bwd_dx_gemm", ma, mb, make_shape(B_tot, D, n_s, 256, splits), epi, st, min_bytes)) return e;
   }
-  // 3. dW = normalize_bwd(dcos^T (n_s x B_tot) * X (B_tot x D)): A = dcos^T, B = X^T (D x B_tot), K = B_tot
+  // 3. dW = normalize_bwd(dcos^T X): A = dcos read in place (MN-major over classes), B = X in place (MN-major), K = B_tot
   {
     CUtensorMap ma, mb;
-    if (int e = encode_tmap_bf16_kmajor(&ma, h.dcos_t, n_s, B_tot, h.ld_t, kBlockM)) return e;
-    if (int e = encode_tmap_bf16_kmajor(&mb, x_t, D, B_tot, ld_xt, 256)) return e;
-    EpiDwNormBwd epi{static_cast<const __nv_bfloat16*>(wn), inv_norm, dw, (int)n_s, (int)D};
-    if (int e = launch_gemm<512, 1, 2>("head_bwd_dw_gemm", ma, mb, make_shape(n_s, D, B_tot, 512), epi, st)) return e;
+    if (int e = encode_tmap_bf16_mnmajor(&ma, h.dcos, n_s, B_tot, h.ld_dc)) return e;
+    if (int e = encode_tmap_bf16_mnmajor(&mb, x, D, B_tot, D)) return e;
+    EpiDwNormBwd epi;
+    if (int e = encode_tmap_2d(&epi.map_dw, dw, 4, D, n_s, D, 32, 32)) return e;
+    epi.wn = static_cast<const __nv_bfloat16*>(wn); epi.inv_norm = inv_norm; epi.rdot = h.rdot; epi.n_s = (int)n_s; epi.D = (int)D;
+    const double min_bytes = 4.0 * (double)n_s * D + 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 2.0 * (double)B_tot * D;
+    if (int e = launch_gemm<256, 2, 3, true, true>("head_bwd_dw_gemm", ma, mb, make_shape(n_s, D, B_tot, 256), epi, st, min_bytes)) return e;
   }
   return 0;
 }

@@ -16,6 +16,13 @@
 // UMMA smem descriptors read them as the canonical K-major SW128 layout (8-row x 128 B atoms,
 // SBO = 1024 B).  K-steps inside the 128-byte atom advance the descriptor start address by 32 B.
 // Out-of-bounds rows / k are zero-filled by TMA, so M, N, K need not be tile multiples.
+//
+// Either operand may instead be MN-major (A stored (K x M), B stored (K x N), the MN index
+// contiguous): TMA then fetches 64(mn) x 64(k) boxes (128-byte rows again, SWIZZLE_128B) laid out
+// box after box, and the UMMA descriptor describes the canonical MN-major SW128 layout
+// (LBO = 8 KB between 64-wide MN blocks, SBO = 1 KB between 8-deep K groups; a K-step of 16
+// advances the start address by 2 KB).  This is what lets dX = dcos Wn and dW = dcos^T X read
+// dcos, Wn and X in place, without transposed copies.
 #pragma once
 #include <cuda.h>
 
@@ -115,6 +122,52 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// issue only (no wait): pair with tmem_ld_wait(v) which also pins the data dependency
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+        "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]),
+        "=f"(r[16]), "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]),
+        "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for all outstanding tcgen05.ld of this thread; the registers pass through as in/out operands
+// so no consumer can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(float* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                 "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]),
+                 "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]), "+f"(r[23]),
+                 "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]), "+f"(r[30]), "+f"(r[31])
+               :
+               : "memory");
+}
+
+// ---- epilogue-side async copies ---------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t bytes = pred ? 16u : 0u;   // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// byte offset of 16-byte chunk `c` of row `r` in a 128-byte-row SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
 // K-major, SWIZZLE_128B canonical layout: start>>4 | LBO(16B, ignored)=1 | SBO=1024B | version=1 | layout=2
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -125,9 +178,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                             // [61,64) SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major, SWIZZLE_128B canonical layout: 64(mn) x 64(k) boxes of 8 KB; LBO = 8 KB (next MN block),
+// SBO = 1 KB (next group of 8 k)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, M x N, per-operand major (0 = K, 1 = MN)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------- problem
@@ -138,30 +203,37 @@ struct GemmShape {
   int k_blocks_per_split;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int EPI_BYTES>
 struct SmemLayout {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kEpiOffset = STAGES * kStageBytes;          // 1024-aligned epilogue scratch
+  static constexpr int kBarOffset = kEpiOffset + EPI_BYTES;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + tmem ptr, + slack for 1024-B alignment
+  static_assert(EPI_BYTES % 1024 == 0, "epilogue scratch must keep 1024-byte alignment");
+  static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
 };
 
 // Epilogue concept:
-//   struct Epi { __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int k_split,
-//                                           int quarter, int lane) const; };
+//   struct Epi {
+//     static constexpr int kSmemBytes;     // per-CTA scratch (multiple of 1024), split by the callee per warp
+//     __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int k_split,
+//                                int quarter, int lane, uint8_t* scratch) const;
+//     __device__ void finish(int quarter, int lane) const;   // once per warp after the last tile
+//   };
 // tmem_acc already carries the accumulator-stage column offset; the callee adds
 // ((quarter*32) << 16) + column.  Called by all 128 epilogue threads (warp-convergent).
 
-template <int BLOCK_N, int ACC_STAGES, int STAGES, class Epi>
+template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-            const GemmShape shape, const Epi epi) {
-  static_assert(BLOCK_N % 128 == 0 && BLOCK_N <= 512, "BLOCK_N in {128,256,384,512}");
+            const GemmShape shape, const __grid_constant__ Epi epi) {
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256 || BLOCK_N == 512, "BLOCK_N in {128,256,512}");
   static_assert(BLOCK_N * ACC_STAGES <= kTmemCols, "accumulators exceed TMEM");
   constexpr int UMMA_N = BLOCK_N >= 256 ? 256 : BLOCK_N;
   constexpr int N_SUB = BLOCK_N / UMMA_N;
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, Epi::kSmemBytes>;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -205,10 +277,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+          if (A_MN) {   // 64(m) x 64(k) boxes, one per 64-wide M block
 #pragma unroll
-          for (int j = 0; j < N_SUB; ++j)
-            tma_load_2d(sb + j * UMMA_N * kBlockK * 2, &map_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N + j * UMMA_N);
+            for (int j = 0; j < kBlockM / 64; ++j)
+              tma_load_2d(sa + j * 8192, &map_a, &full_bar[stage], m_blk * kBlockM + j * 64, kb * kBlockK);
+          } else {
+            tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * 8192, &map_b, &full_bar[stage], n_blk * BLOCK_N + j * 64, kb * kBlockK);
+          } else {
+#pragma unroll
+            for (int j = 0; j < N_SUB; ++j)
+              tma_load_2d(sb + j * UMMA_N * kBlockK * 2, &map_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N + j * UMMA_N);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -216,7 +300,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   } else if (warp == 1) {
     if (lane == 0) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc(kBlockM, UMMA_N);
+      constexpr uint32_t idesc = make_idesc(kBlockM, UMMA_N, A_MN, B_MN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -234,10 +318,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const uint32_t sb = sa + L::kABytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * kUmmaK * 2);
+            // K-major: +32 B per K-step inside the 128-byte row; MN-major: +16 k-rows = 2 KB
+            const uint64_t da = A_MN ? make_smem_desc_mn(sa + k * 2048) : make_smem_desc(sa + k * kUmmaK * 2);
 #pragma unroll
             for (int j = 0; j < N_SUB; ++j) {
-              const uint64_t db = make_smem_desc(sb + j * UMMA_N * kBlockK * 2 + k * kUmmaK * 2);
+              const uint64_t db = B_MN ? make_smem_desc_mn(sb + j * (UMMA_N / 64) * 8192 + k * 2048)
+                                       : make_smem_desc(sb + j * UMMA_N * kBlockK * 2 + k * kUmmaK * 2);
               umma_bf16(d_tmem + j * UMMA_N, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
@@ -259,12 +345,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int ks = u / (shape.m_blocks * shape.n_blocks);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane);
+      epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane, smem + L::kEpiOffset);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    epi.finish(quarter, lane);
   }
 
   tc_fence_before();
@@ -275,13 +362,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
 // ------------------------------------------------------------------------------- host side
 // cuTensorMapEncodeTiled is fetched through the runtime (no link-time libcuda dependency).
-int encode_tmap_bf16_kmajor(CUtensorMap* out, const void* base, int64_t rows, int64_t k, int64_t ld_elems, int box_rows);
+// 2-D tensor map over a row-major (outer x inner) array: inner contiguous, row pitch ld_elems, 128-byte
+// swizzled boxes of box_inner x box_outer elements (box_inner * elem_bytes must be 128).
+int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, int64_t inner, int64_t outer, int64_t ld_elems,
+                   int box_inner, int box_outer);
+// K-major bf16 operand (rows x k): boxes of 64(k) x box_rows
+inline int encode_tmap_bf16_kmajor(CUtensorMap* out, const void* base, int64_t rows, int64_t k, int64_t ld_elems, int box_rows) {
+  return encode_tmap_2d(out, base, 2, k, rows, ld_elems, kBlockK, box_rows);
+}
+// MN-major bf16 operand stored (k x mn): boxes of 64(mn) x 64(k)
+inline int encode_tmap_bf16_mnmajor(CUtensorMap* out, const void* base, int64_t mn, int64_t k, int64_t ld_elems) {
+  return encode_tmap_2d(out, base, 2, mn, k, ld_elems, 64, kBlockK);
+}
 
-template <int BLOCK_N, int ACC_STAGES, int STAGES, class Epi>
+template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, class Epi>
 int launch_gemm(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& shape, const Epi& epi,
-                cudaStream_t st) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
-  auto kern = gemm_kernel<BLOCK_N, ACC_STAGES, STAGES, Epi>;
+                cudaStream_t st, double min_bytes = 0.0) {
+  using L = SmemLayout<BLOCK_N, STAGES, Epi::kSmemBytes>;
+  auto kern = gemm_kernel<BLOCK_N, ACC_STAGES, STAGES, A_MN, B_MN, Epi>;
   static thread_local bool configured = false;   // per template instantiation
   if (!configured) {
     MSML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -291,7 +389,7 @@ int launch_gemm(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, 
   int grid = num_sms();
   if (units < grid) grid = units;
   if (grid < 1) grid = 1;
-  MSML_PROF(name, 2.0 * shape.M * shape.N * shape.K, st);
+  MSML_PROF2(name, 2.0 * shape.M * shape.N * shape.K, min_bytes, st);
   kern<<<grid, kThreads, L::kTotal, st>>>(ma, mb, shape, epi);
   MSML_LAUNCH_CHECK();
   return 0;

@@ -8,7 +8,7 @@ but the work is done by libmsml_b200.so:
   sample           msml_pfc_remap / mark_positive / select (radix select + ordered compaction) /
                    searchsorted / gather_rows              (ref :77-94; torch.rand stays in torch so
                    the generator is consumed exactly as in the reference)
-  prepare          msml_wnorm_cast: fp32 master rows -> unit-norm bf16 (+ transposed copy)  (ref :115)
+  prepare          msml_wnorm_cast: fp32 master rows -> unit-norm bf16 + 1/||w||            (ref :115)
   forward_backward msml_head_fwd (tcgen05 GEMM, margin/scale/online-softmax epilogue; logits are
                    never materialised) -> ONE all-gather of per-row (max, sum, target) instead of
                    the reference's three all-reduces (:136,141,162) -> msml_head_merge_stats ->
@@ -183,15 +183,13 @@ class PartialFC(Module):
                                         self.embedding_size, stream_ptr()))
 
     def _normalize_weight(self):
-        """ref :115 -> (wn bf16 (n_s, D), wn^T bf16 (D, ld), inv_norm fp32 (n_s))."""
+        """ref :115 -> (wn bf16 (n_s, D), inv_norm fp32 (n_s))."""
         lib = load()
         n_s, D = self.sub_weight.shape
-        ld = (n_s + 7) // 8 * 8
         wn = self._buf("wn", (n_s, D), torch.bfloat16)
-        wn_t = self._buf("wn_t", (D, ld), torch.bfloat16)
         inv = self._buf("inv_norm", (n_s,), torch.float32)
-        check(lib.msml_wnorm_cast(_ptr(self.sub_weight.data), _ptr(wn), _ptr(wn_t), ld, _ptr(inv), n_s, D, stream_ptr()))
-        return wn, wn_t, ld, inv
+        check(lib.msml_wnorm_cast(_ptr(self.sub_weight.data), _ptr(wn), None, 0, _ptr(inv), n_s, D, stream_ptr()))
+        return wn, inv
 
     def prepare(self, label, optimizer):
         with torch.cuda.stream(self.stream):
@@ -215,7 +213,7 @@ class PartialFC(Module):
         B_tot = B * W
         main = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(main)            # label / weights produced on the main stream
-        total_label, (wn, wn_t, ld_wt, inv_norm) = self.prepare(label, optimizer)
+        total_label, (wn, inv_norm) = self.prepare(label, optimizer)
 
         with torch.no_grad():
             # all-gather the embeddings in bf16 (half the bytes of the reference's fp32 gather, :126)
@@ -224,8 +222,6 @@ class PartialFC(Module):
             check(lib.msml_cast_bf16(_ptr(feat), _ptr(x_local), None, 0, B, D, stream_ptr()))
             x = self._buf("x", (B_tot, D), torch.bfloat16)
             self.comm.all_gather(x, x_local)
-            ld_xt = (B_tot + 7) // 8 * 8
-            x_t = self._buf("x_t", (D, ld_xt), torch.bfloat16)
             main.wait_stream(self.stream)        # ref :97
 
             n_s = wn.shape[0]
@@ -244,14 +240,10 @@ class PartialFC(Module):
             loss_v = torch.empty((), dtype=torch.float32, device=self.device)
             check(lib.msml_head_merge_stats(_ptr(gathered), W, B_tot, _ptr(gstats), _ptr(loss_v), stream_ptr()))
 
-            # transposed embeddings for the dW contraction (bf16, K-major over the batch)
-            check(lib.msml_transpose_bf16(_ptr(x), _ptr(x_t), B_tot, D, ld_xt, stream_ptr()))
-
             dx_full = self._buf("dx_full", (B_tot, D), torch.float32)
             dw = torch.empty((n_s, D), dtype=torch.float32, device=self.device)
-            check(lib.msml_head_bwd(_ptr(x), _ptr(x_t), ld_xt, _ptr(wn), _ptr(wn_t), ld_wt, _ptr(inv_norm),
-                                    _ptr(total_label), B_tot, n_s, D, mp, _ptr(gstats), _ptr(dx_full), _ptr(dw),
-                                    _ptr(ws), ws_bytes, stream_ptr()))
+            check(lib.msml_head_bwd(_ptr(x), _ptr(wn), _ptr(inv_norm), _ptr(total_label), B_tot, n_s, D, mp,
+                                    _ptr(gstats), _ptr(dx_full), _ptr(dw), _ptr(ws), ws_bytes, stream_ptr()))
             self.sub_weight.grad = dw
 
             # feature gradient reduce-scatter, then * world_size (ref :172-175)

@@ -216,6 +216,23 @@ def gemm_tn(a, b):
     return c
 
 
+def gemm(a, b, a_mn=False, b_mn=False, block_n=256):
+    """fp32 (M, N) = op(a) @ op(b)^T; a_mn / b_mn: the operand is stored (K, M) / (K, N) row-major and read in
+    place through MN-major UMMA descriptors (no transposed copy)."""
+    require_cuda(a, b)
+    lib = load()
+    a = a.to(torch.bfloat16).contiguous()
+    b = b.to(torch.bfloat16).contiguous()
+    (K, M) = a.shape if a_mn else a.shape[::-1]
+    (K2, N) = b.shape if b_mn else b.shape[::-1]
+    if K != K2:
+        raise ValueError("gemm: K mismatch %d vs %d" % (K, K2))
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    check(lib.msml_gemm_bf16(_ptr(a), a.shape[1], int(a_mn), _ptr(b), b.shape[1], int(b_mn), _ptr(c), N, M, N, K,
+                             block_n, stream_ptr()))
+    return c
+
+
 class _CosineGemm(torch.autograd.Function):
     """cos = en @ wn^T with both gradients, all three contractions on tcgen05."""
 
@@ -227,8 +244,14 @@ class _CosineGemm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dcos):
         en, wn = ctx.saved_tensors
-        d_en = gemm_tn(dcos, wn.t())          # (B, C) x (D, C)^T
-        d_wn = gemm_tn(dcos.t(), en.t())      # (C, B) x (D, B)^T
+        pad = (-dcos.shape[1]) % 8            # TMA pitch rule: row pitch multiple of 16 bytes
+        d16 = torch.nn.functional.pad(dcos, (0, pad)).to(torch.bfloat16) if pad else dcos.to(torch.bfloat16)
+        wn16 = wn.to(torch.bfloat16)
+        en16 = en.to(torch.bfloat16)
+        if pad:
+            wn16 = torch.nn.functional.pad(wn16, (0, 0, 0, pad))
+        d_en = gemm(d16, wn16, a_mn=False, b_mn=True)                      # dcos (B,C) x Wn (C,D) read in place
+        d_wn = gemm(d16, en16, a_mn=True, b_mn=True)[:wn.shape[0]]        # dcos^T (C,B) x En (B,D), both in place
         return d_en.to(en.dtype), d_wn.to(wn.dtype)
 
 

@@ -39,6 +39,26 @@ def test_gemm_exact_on_small_integers():
     assert torch.equal(c, a @ b.t())
 
 
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("block_n", [256, 512])
+@pytest.mark.parametrize("M,N,K", [(128, 512, 128), (384, 520, 320), (200, 96, 1000), (1000, 512, 136)])
+def test_gemm_operand_layouts_exact(a_mn, b_mn, block_n, M, N, K):
+    """All four operand-major combinations (K-major / MN-major UMMA descriptors + their TMA boxes)
+    and both accumulator tiles, on integer-valued operands: results must be bit-exact."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = torch.randint(-4, 5, (M, K), device="cuda").float()
+    b = torch.randint(-4, 5, (N, K), device="cuda").float()
+    a_store = a.t().contiguous() if a_mn else a
+    b_store = b.t().contiguous() if b_mn else b
+    if (a_store.shape[1] % 8) or (b_store.shape[1] % 8):
+        pytest.skip("pitch must be a multiple of 8 elements")
+    c = ops.gemm(a_store, b_store, a_mn=a_mn, b_mn=b_mn, block_n=block_n)
+    assert torch.equal(c, a @ b.t())
+
+
 # ------------------------------------------------------------------------------- sampling
 def _pfc(rank, W, B, C, sr, D, kind="arc", smak=(64.0, 0.5, 0.0, 0.0), comm=None):
     from msml_b200.headers import MarginSoftmax, PartialFC
