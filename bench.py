@@ -204,6 +204,7 @@ def run_train(args, rank, local_rank, world):
     import torch.distributed as dist
     from msml_b200 import _lib, ops
     from msml_b200.backbones import MSML
+    from msml_b200.engine import TrainStep, broadcast_parameters
     from msml_b200.headers import ArcFace, PartialFC
 
     lib = _lib.load()
@@ -212,33 +213,21 @@ def run_train(args, rank, local_rank, world):
     torch.backends.cudnn.benchmark = True
     pk = peaks()
 
-    torch.manual_seed(1)                                     # same init on every rank (ref train.py:133-134)
+    torch.manual_seed(1)                                     # same init on every rank, then broadcast (ref train.py:133-134)
     net = MSML("iresnet50", "unet", (1, 1, 1, 1), NUM_CLASSES, fp16=True, header_type=None, fm_params=FM_PARAMS).to(dev).train()
-    model = net
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], broadcast_buffers=False,
-                                                          find_unused_parameters=True)
+    broadcast_parameters(net)
     pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), NUM_CLASSES, sample_rate=1.0, embedding_size=512)
     lr = 0.1 * BATCH * world / 512
-    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=lr, momentum=0.9, weight_decay=5e-4)
-    opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4)
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
+    opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
+    step = TrainStep(net, pfc, opt, opt_pfc, (BATCH, 3, 112, 112), world_size=world, max_norm=5.0, use_graph=not args.eager)
 
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     n_buf = 4
-    imgs = [torch.randn(BATCH, 3, 112, 112, device=dev, generator=gen) for _ in range(n_buf)]
+    imgs = [torch.randn(BATCH, 3, 112, 112, device=dev, generator=gen).contiguous(memory_format=torch.channels_last) for _ in range(n_buf)]
     labels = [torch.randint(0, NUM_CLASSES, (BATCH,), device=dev, generator=gen) for _ in range(n_buf)]
     imgs_h = [t.cpu().pin_memory() for t in imgs]
     labels_h = [t.cpu().pin_memory() for t in labels]
-
-    def step(img, label):
-        feat, _seg = model(img)
-        featn = torch.nn.functional.normalize(feat)
-        x_grad, loss = pfc.forward_backward(label, featn, opt_pfc)
-        featn.backward(x_grad)
-        torch.nn.utils.clip_grad_norm_([p for p in net.parameters() if p.grad is not None], 5, foreach=True)
-        opt.step(); opt_pfc.step(); pfc.update()
-        opt.zero_grad(set_to_none=True); opt_pfc.zero_grad(set_to_none=True)
-        return loss
 
     def fence():
         if world > 1:
@@ -252,9 +241,7 @@ def run_train(args, rank, local_rank, world):
         last = 0.0
         for i in range(n):
             if host_fed:
-                img = imgs_h[i % n_buf].to(dev, non_blocking=True)
-                label = labels_h[i % n_buf].to(dev, non_blocking=True)
-                last = step(img, label).item()              # D2H read of the step's loss
+                last = step(imgs_h[i % n_buf], labels_h[i % n_buf]).item()     # H2D of the inputs, D2H read of the loss
             else:
                 last = step(imgs[i % n_buf], labels[i % n_buf])
         b.record()
@@ -266,40 +253,57 @@ def run_train(args, rank, local_rank, world):
             ms = float(t.item())
         return ms, float(last)
 
-    for i in range(args.warmup):
+    for i in range(args.warmup):                             # includes the 3 eager steps + graph capture
         step(imgs[i % n_buf], labels[i % n_buf])
     fence()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ops.launch_count_reset()
-    lib.msml_profile_enable(1)
     ms, loss = timed(args.steps, host_fed=False)
-    lib.msml_profile_enable(0)
-    launches = ops.launch_count()
-    prof = collect_profile(lib)
     ms_e2e, loss_e2e = timed(args.steps, host_fed=True)
     clocks = sampler.stop() if sampler else None
+
+    # per-kernel roofline pass: the SAME step run eagerly (a CUDA graph cannot be bracketed kernel by
+    # kernel), every launch of this library between two CUDA events on its own stream
+    prof_steps = 3
+    eager = step if args.eager else TrainStep(net, pfc, opt, opt_pfc, (BATCH, 3, 112, 112), world_size=world, max_norm=5.0, use_graph=False)
+    if not args.eager:
+        eager.flat, eager._used = step.flat, step._used
+    eager(imgs[0], labels[0])
+    fence()
+    ops.launch_count_reset()
+    lib.msml_profile_enable(1)
+    for i in range(prof_steps):
+        eager(imgs[i % n_buf], labels[i % n_buf])
+    torch.cuda.synchronize()
+    lib.msml_profile_enable(0)
+    launches_per_step = ops.launch_count() // prof_steps
+    prof = collect_profile(lib)
+    fence()
 
     if rank != 0:
         return None
     value = args.steps * BATCH * world / (ms * 1e-3)
     rl = sorted((roofline_entry(k, v, pk) for k, v in prof.items()), key=lambda r: -r["avg_us"] * r["launches"])
-    mine_ms = sum(v["total_ms"] for v in prof.values()) / args.steps
+    mine_ms = sum(v["total_ms"] for v in prof.values()) / prof_steps
     res = {
         "metric": "train imgs/s ires50-MSML+PartialFC", "value": round(value, 1), "unit": "imgs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "ires50_msml + PartialFC(ArcFace s=64 m=0.5, 93431 classes, sample_rate 1) bf16 training step, "
                                "112x112, batch 128/GPU (BASELINE config 3)",
-                   "global_batch": BATCH * world, "parallelism": "dp%d backbone (DDP) + class-sharded head" % world,
+                   "global_batch": BATCH * world,
+                   "parallelism": "dp%d backbone (flat-gradient NCCL all-reduce) + class-sharded head" % world,
+                   "execution": "eager" if args.eager else "whole step captured in one CUDA graph (msml_b200.engine.TrainStep)",
                    "l2": "per-step working set (activations, GBs) >> 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(args.steps * BATCH * world / (ms_e2e * 1e-3), 1), "unit": "imgs/s",
                 "h2d_bytes_per_step": imgs_h[0].numel() * 4 + labels_h[0].numel() * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_per_step": int(launches_per_step),
         "own_kernel_ms_per_step": round(mine_ms, 4),
         "roofline": rl[0] if rl else None,
         "rooflines": rl,
+        "roofline_pass": "%d eager replays of the same step after the timed region, CUDA events around every launch" % prof_steps,
         "clocks": clocks,
         "loss": round(loss, 4),
     }
@@ -365,6 +369,7 @@ def main():
     ap.add_argument("--sample-rate", type=float, default=1.0)
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -80,6 +80,28 @@ int msml_fm_mask_bwd(const void* dout, const void* yf, const void* m, void* dyf,
                      int dtype, int act, int arith, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K-N  fused BatchNorm (+ residual add) (+ PReLU) over an NHWC tensor viewed as (P = N*H*W, C):
+ *        y = prelu( (x - mean) * invstd * gamma + beta [+ res] )
+ *   ref backbones/frb/iresnet.py:56-67, backbones/osb/unet.py:80-91, backbones/fm/fmoperator.py:52-68
+ *   (torch.nn.BatchNorm2d + torch.nn.PReLU + `out += identity`).
+ * training != 0: batch statistics (biased variance), running stats updated with `momentum`
+ * (unbiased variance), num_batches_tracked += 1 (nullable).  training == 0: running statistics.
+ * res / prelu are nullable.  save_mean / save_invstd (C) are outputs of fwd and inputs of bwd.
+ * bwd: dres is written only when BOTH res and prelu are fused (otherwise d res == dy);
+ *      dgamma / dbeta / dprelu are fp32 (C).  C must be a multiple of the 16-byte vector width
+ *      with (C / width) dividing 256.
+ * ------------------------------------------------------------------------------------------ */
+size_t msml_bn_workspace(int64_t P, int64_t C);
+int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
+                float* running_mean, float* running_var, int64_t* num_batches_tracked, float* save_mean,
+                float* save_invstd, int64_t P, int64_t C, int dtype, int training, float momentum, float eps,
+                void* workspace, size_t workspace_bytes, void* stream);
+int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* beta,
+                const float* prelu, const float* save_mean, const float* save_invstd, void* dx, void* dres,
+                float* dgamma, float* dbeta, float* dprelu, int64_t P, int64_t C, int dtype, int training,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K-B  DAP head of the segmentation branch + argmax mask.
  *   ref backbones/osb/unet.py:158-161,223 (PixelShuffle(k)+AvgPool2d(k) == mean over k*k channel
  *   groups), train.py:357 / eval/qeval_mxnet.py:347 (final_seg[b].max(0)[1]).

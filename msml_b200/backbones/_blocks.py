@@ -1,7 +1,11 @@
 """Building blocks shared by the FRB trunk and the OSB encoder (both use the same improved-residual
 unit in the reference: ref backbones/frb/iresnet.py:38-67 and backbones/osb/unet.py:62-91).
-Module / parameter names are kept so reference checkpoints load unchanged."""
+Module / parameter names are kept so reference checkpoints load unchanged; the BatchNorm / PReLU /
+residual-add chains between the convolutions run as the fused NHWC kernels of csrc/bn_act.cu
+(ops.bn_act: statistics + normalise + add + activation in two passes), the convolutions on cuDNN."""
 from torch import nn
+
+from .. import ops
 
 
 def conv3x3(cin, cout, stride=1):
@@ -28,9 +32,10 @@ class IBasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = self.bn3(self.conv2(self.prelu(self.bn2(self.conv1(self.bn1(x))))))
-        skip = x if self.downsample is None else self.downsample(x)
-        return out + skip
+        out = self.conv1(ops.bn_act(x, self.bn1))
+        out = self.conv2(ops.bn_act(out, self.bn2, self.prelu))
+        skip = x if self.downsample is None else ops.bn_act(self.downsample[0](x), self.downsample[1])
+        return ops.bn_act(out, self.bn3, None, skip)          # bn3(out) + identity
 
 
 def make_stage(inplanes, planes, blocks, stride):

@@ -37,10 +37,9 @@ class resblock_bottle(nn.Module):
         self.prelu3 = nn.PReLU(out_channels)
 
     def forward(self, x):
-        y = self.prelu1(self.bn1(self.conv1(x)))
-        y = self.prelu2(self.bn2(self.conv2(y)))
-        y = self.bn3(self.conv3(y))
-        return self.prelu3(y + x)
+        y = ops.bn_act(self.conv1(x), self.bn1, self.prelu1)
+        y = ops.bn_act(self.conv2(y), self.bn2, self.prelu2)
+        return ops.bn_act(self.conv3(y), self.bn3, self.prelu3, x)     # prelu3(bn3(.) + identity)
 
 
 def _conv_bn_prelu_x2(c):

@@ -9,6 +9,7 @@ that are not shipped (ref backbones/pretrained/README.md) and are out of scope (
 import torch
 from torch import nn
 
+from ... import ops
 from .._blocks import IBasicBlock, make_stage
 
 __all__ = ['IResNet', 'iresnet18', 'iresnet34', 'iresnet50']
@@ -68,13 +69,13 @@ class IResNet(nn.Module):
                 raise NotImplementedError("peer-guided training needs a pretrained peer network (not shipped with "
                                           "the reference); inject one with IResNet.set_peer()")
             _, ft = self.peer(ori)
-        x = self.prelu(self.bn1(self.conv1(x)))
+        x = ops.bn_act(self.conv1(x), self.bn1, self.prelu)
         kd_terms = []
         for i, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
             x = layer(x)
             x, l = self.fm_ops[i](x, segs[i], ft[i])
             kd_terms.append(l)
-        x = self.bn2(x)
+        x = ops.bn_act(x, self.bn2)
         x = self.dropout(torch.flatten(x, 1))
         x = self.features(self.fc(x.float()))
         kd = sum(kd_terms) if ori is not None and all(t is not None for t in kd_terms) else 0.

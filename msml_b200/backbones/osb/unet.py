@@ -71,11 +71,11 @@ class Unet(nn.Module):
         self.DAP = _DAP(dap_k)
 
     def _decode(self, x):
-        x0 = self.prelu(self.bn1(self.conv1(x)))
+        x0 = ops.bn_act(self.conv1(x), self.bn1, self.prelu)
         x1 = self.layer1(x0)
         x2 = self.layer2(x1)
         x3 = self.layer3(x2)
-        x4 = self.bn2(self.layer4(x3))
+        x4 = ops.bn_act(self.layer4(x3), self.bn2)
         seg0 = self.deconv1(self.gcm1(x4))
         seg1 = self.deconv2(torch.cat((seg0, self.gcm2(x3)), 1))
         seg2 = self.deconv3(torch.cat((seg1, self.gcm3(x2)), 1))

@@ -70,14 +70,21 @@ __device__ __forceinline__ float fast_exp2(float x) {   // MUFU.EX2; -inf -> 0
   return y;
 }
 
+// The reference takes acos of an fp32 cosine of unit vectors (|c| <= 1 up to 1e-7, no clamp).  Here the
+// operands are rounded to bf16, which can push a well-aligned target to |c| ~ 1 + 4e-3; clamping to the open
+// interval restores the reference's domain (and keeps d/dc finite) instead of manufacturing NaNs.
+__device__ __forceinline__ float clamp_cos(float c) { return fminf(fmaxf(c, -1.0f + 1e-6f), 1.0f - 1e-6f); }
+
 // logit / s at the target column (ref margin_losses.py:411-417 arc, :298-299 cos)
 __device__ __forceinline__ float margin_target(const Margin& mg, float c) {
-  const float theta = acosf(c);   // no clamp, as the reference: |c| > 1 -> NaN
+  c = clamp_cos(c);
+  const float theta = acosf(c);
   const float m_eff = mg.m - mg.k * (theta - mg.a);
   return mg.kind == MSML_MARGIN_ARC ? cosf(theta + m_eff) : c - m_eff;
 }
 // d(logit)/d(cos) / s at the target column (the adaptive term carries gradient)
 __device__ __forceinline__ float margin_target_grad(const Margin& mg, float c) {
+  c = clamp_cos(c);
   const float theta = acosf(c);
   const float sin_t = sinf(theta);
   if (mg.kind == MSML_MARGIN_ARC) return (1.0f - mg.k) * sinf((1.0f - mg.k) * theta + mg.m + mg.k * mg.a) / sin_t;

@@ -1,0 +1,148 @@
+"""Training-step engine for the MSML + PartialFC hot path on B200.
+
+The reference's step (train.py:283-300, PartialFC variant) is a few thousand small kernels; on a
+B200 that is launch-bound from Python.  ``TrainStep`` keeps the reference's semantics
+
+    features, _ = backbone(img)
+    x_grad, loss = pfc.forward_backward(label, F.normalize(features), opt_pfc)
+    features.backward(x_grad); clip_grad_norm_(backbone, 5); opt_backbone.step(); opt_pfc.step(); pfc.update()
+
+and runs it the B200 way: gradients of all used backbone parameters live in ONE flat fp32 buffer
+(a single NCCL all-reduce replaces DDP's buckets; clipping is two kernels), and after three eager
+warm-up steps the whole step — cuDNN convolutions, this library's kernels, NCCL collectives and the
+SGD updates — is captured into a CUDA graph and replayed with no Python or launch overhead.
+
+Limits of the captured mode (documented, checked): PartialFC sample_rate must be 1 (sampling needs
+a data-dependent allocation), learning rates are baked in at capture time (call ``recapture()``
+after changing them).  ``use_graph=False`` runs the identical step eagerly.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+class TrainStep:
+    def __init__(self, backbone, pfc, opt_backbone, opt_pfc, batch_shape, world_size=1, max_norm=5.0,
+                 use_graph=True, device=None):
+        self.backbone, self.pfc = backbone, pfc
+        self.opt_backbone, self.opt_pfc = opt_backbone, opt_pfc
+        self.world_size, self.max_norm, self.use_graph = world_size, max_norm, use_graph
+        self.device = device or next(backbone.parameters()).device
+        self.static_img = torch.zeros(batch_shape, device=self.device).contiguous(memory_format=torch.channels_last)
+        self.static_label = torch.zeros(batch_shape[0], dtype=torch.int64, device=self.device)
+        self.static_loss = None
+        self.flat = None
+        self.graph = None
+        self._used = None
+        if use_graph and int(pfc.sample_rate) != 1:
+            raise ValueError("captured TrainStep needs PartialFC sample_rate == 1; use use_graph=False for sampled heads")
+
+    # ------------------------------------------------------------------ one eager step
+    def _discover_used_params(self):
+        """One throw-away forward/backward to find which parameters receive gradients (the OSB
+        branch does not when there is no segmentation loss: its outputs are detached, ref
+        unet.py:227-230) and to build the flat gradient buffer over exactly those."""
+        bn_state = {k: v.clone() for k, v in self.backbone.state_dict().items() if "running_" in k or "num_batches" in k}
+        feat, _ = self.backbone(self.static_img.normal_())
+        feat.sum().backward()
+        self.backbone.load_state_dict(bn_state, strict=False)      # the probe must not touch the BN statistics
+        used = [p for p in self.backbone.parameters() if p.grad is not None]
+        n = sum(p.numel() for p in used)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        off = 0
+        for p in used:      # same strides as the parameter (conv weights are channels-last): no layout conversion per step
+            p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
+            off += p.numel()
+        self._used = used
+        self.static_img.zero_()
+
+    def _step(self, img, label):
+        self.flat.zero_()
+        feat, _seg = self.backbone(img)
+        featn = F.normalize(feat)
+        x_grad, loss = self.pfc.forward_backward(label, featn, self.opt_pfc)
+        featn.backward(x_grad)                      # accumulates into the views of self.flat
+        if self.world_size > 1:
+            dist.all_reduce(self.flat)              # one NCCL all-reduce over NVLink for every gradient
+            self.flat.div_(self.world_size)
+        if self.max_norm is not None:               # == clip_grad_norm_(used params, max_norm)
+            coef = torch.clamp(self.max_norm / (torch.linalg.vector_norm(self.flat) + 1e-6), max=1.0)
+            self.flat.mul_(coef)
+        self.opt_backbone.step()
+        self.opt_pfc.step()
+        self.pfc.update()
+        self.pfc.sub_weight.grad = None
+        return loss
+
+    # ------------------------------------------------------------------ capture / replay
+    def _prepare(self):
+        if self._used is None:
+            self._discover_used_params()
+
+    def _snapshot(self):
+        snap = [t.detach().clone() for t in list(self.backbone.parameters()) + list(self.backbone.buffers())]
+        snap += [self.pfc.weight.clone(), self.pfc.weight_mom.clone()]
+        return snap
+
+    def _restore(self, snap, had_momentum):
+        with torch.no_grad():
+            live = list(self.backbone.parameters()) + list(self.backbone.buffers()) + [self.pfc.weight, self.pfc.weight_mom]
+            for t, s in zip(live, snap):
+                t.copy_(s)                          # in place: the captured graph keeps pointing at the live tensors
+            if not had_momentum:                    # momentum buffers created by the warm-up start from zero again
+                for st in self.opt_backbone.state.values():
+                    if st.get("momentum_buffer") is not None:
+                        st["momentum_buffer"].zero_()
+
+    def recapture(self, preserve_state=True):
+        """Three eager warm-up steps on noise (lazy state: momentum buffers, cuDNN autotuning, workspaces), then the
+        capture.  The warm-up and the capture pass train on noise, so model / optimizer state is snapshotted before
+        and restored afterwards unless preserve_state is False."""
+        self._prepare()
+        self.graph = None
+        had_momentum = any(st.get("momentum_buffer") is not None for st in self.opt_backbone.state.values())
+        snap = self._snapshot() if preserve_state else None
+        mom_snap = ([st["momentum_buffer"].clone() for st in self.opt_backbone.state.values() if st.get("momentum_buffer") is not None]
+                    if preserve_state and had_momentum else None)
+        self.static_img.normal_()
+        self.static_label.random_(0, self.pfc.num_classes)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._step(self.static_img, self.static_label)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.static_loss = self._step(self.static_img, self.static_label)
+        self.graph = g
+        if preserve_state:
+            self._restore(snap, had_momentum)
+            if mom_snap is not None:
+                with torch.no_grad():
+                    bufs = [st["momentum_buffer"] for st in self.opt_backbone.state.values() if st.get("momentum_buffer") is not None]
+                    for b, s in zip(bufs, mom_snap):
+                        b.copy_(s)
+        torch.cuda.synchronize(self.device)
+
+    def __call__(self, img, label):
+        """img (B,3,H,W) and label (B,) may live on the host (pinned) or the device."""
+        self._prepare()
+        if not self.use_graph:
+            return self._step(img.to(self.device, non_blocking=True).contiguous(memory_format=torch.channels_last),
+                              label.to(self.device, non_blocking=True))
+        if self.graph is None:
+            self.recapture()
+        self.static_img.copy_(img, non_blocking=True)
+        self.static_label.copy_(label, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
+
+
+@torch.no_grad()
+def broadcast_parameters(module, src=0):
+    """ref train.py:133-134: every rank starts from rank 0's weights."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src)

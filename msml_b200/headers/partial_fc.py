@@ -19,6 +19,7 @@ Class shards exchange data through torch.distributed (NCCL over NVLink); with wo
 process group is needed.  ``margin_softmax`` must carry (kind, s, m, a, k): a
 ``msml_b200.headers.MarginSoftmax`` (ArcFace()/CosFace()) or an AMArcFace/AMCosFace module.
 """
+import contextlib
 import ctypes
 import logging
 import os
@@ -159,9 +160,10 @@ class PartialFC(Module):
             sub_m = torch.empty_like(sub_w)
             check(lib.msml_gather_rows_f32(_ptr(self.weight), _ptr(index), _ptr(sub_w), rows, self.embedding_size, stream_ptr()))
             check(lib.msml_gather_rows_f32(_ptr(self.weight_mom), _ptr(index), _ptr(sub_m), rows, self.embedding_size, stream_ptr()))
-            main = torch.cuda.default_stream(self.device)
-            for t in (index, sub_w, sub_m):      # produced on the side stream, consumed on the main one
-                t.record_stream(main)
+            if not torch.cuda.is_current_stream_capturing():
+                main = torch.cuda.default_stream(self.device)
+                for t in (index, sub_w, sub_m):  # produced on the side stream, consumed on the main one
+                    t.record_stream(main)
             self.sub_weight = Parameter(sub_w)
             self.sub_weight_mom = sub_m
 
@@ -192,7 +194,11 @@ class PartialFC(Module):
         return wn, inv
 
     def prepare(self, label, optimizer):
-        with torch.cuda.stream(self.stream):
+        # side stream as in the reference (:107) — except under CUDA-graph capture, where the whole
+        # step is one stream-ordered graph anyway
+        capturing = torch.cuda.is_current_stream_capturing()
+        ctx = contextlib.nullcontext() if capturing else torch.cuda.stream(self.stream)
+        with ctx:
             total_label = torch.zeros(size=[self.batch_size * self.world_size], device=self.device, dtype=torch.long)
             self.comm.all_gather(total_label, label)
             self.sample(total_label)
@@ -202,7 +208,8 @@ class PartialFC(Module):
                 optimizer.param_groups[-1]['params'][0] = self.sub_weight
                 optimizer.state[self.sub_weight]['momentum_buffer'] = self.sub_weight_mom
             norm_weight = self._normalize_weight()
-            total_label.record_stream(torch.cuda.default_stream(self.device))
+            if not capturing:
+                total_label.record_stream(torch.cuda.current_stream(self.device))
             return total_label, norm_weight
 
     def forward_backward(self, label, features, optimizer):
@@ -212,7 +219,9 @@ class PartialFC(Module):
         W, B, D = self.world_size, self.batch_size, self.embedding_size
         B_tot = B * W
         main = torch.cuda.current_stream(self.device)
-        self.stream.wait_stream(main)            # label / weights produced on the main stream
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.stream.wait_stream(main)        # label / weights produced on the main stream
         total_label, (wn, inv_norm) = self.prepare(label, optimizer)
 
         with torch.no_grad():
@@ -222,7 +231,8 @@ class PartialFC(Module):
             check(lib.msml_cast_bf16(_ptr(feat), _ptr(x_local), None, 0, B, D, stream_ptr()))
             x = self._buf("x", (B_tot, D), torch.bfloat16)
             self.comm.all_gather(x, x_local)
-            main.wait_stream(self.stream)        # ref :97
+            if not capturing:
+                main.wait_stream(self.stream)    # ref :97
 
             n_s = wn.shape[0]
             ws_bytes = lib.msml_head_workspace(B_tot, n_s, D)

@@ -144,6 +144,68 @@ def fm_mask(yf, m, act="sigmoid", arith="mul"):
 
 
 # --------------------------------------------------------------------------------------------
+# K-N  fused BatchNorm (+ residual) (+ PReLU), NHWC            ref backbones/frb/iresnet.py:56-67,
+#                                                               backbones/fm/fmoperator.py:52-68
+# --------------------------------------------------------------------------------------------
+class _BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, prelu, res, running_mean, running_var, nbt, training, momentum, eps):
+        require_cuda(x, gamma, beta, prelu, res)
+        lib = load()
+        B, C, H, W = x.shape
+        P = B * H * W
+        x_d = x.contiguous(memory_format=torch.channels_last)
+        res_d = _dense_like(x_d, res) if res is not None else None
+        y = torch.empty_like(x_d)
+        ws_bytes = lib.msml_bn_workspace(P, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        stats = torch.empty((2, C), dtype=torch.float32, device=x.device)
+        check(lib.msml_bn_fwd(_ptr(x_d), _ptr(res_d), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(prelu), _ptr(running_mean),
+                              _ptr(running_var), _ptr(nbt) if training else None, _ptr(stats[0]), _ptr(stats[1]), P, C,
+                              dtype_code(x_d.dtype), int(training), float(momentum), float(eps), _ptr(ws), ws_bytes, stream_ptr()))
+        ctx.save_for_backward(x_d, res_d if prelu is not None else None, gamma, beta, prelu, stats)
+        ctx.cfg = (training, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, res, gamma, beta, prelu, stats = ctx.saved_tensors
+        training, has_res = ctx.cfg
+        lib = load()
+        B, C, H, W = x.shape
+        P = B * H * W
+        dy_d = _dense_like(x, dy)
+        dx = torch.empty_like(x)
+        both = has_res and prelu is not None
+        dres = torch.empty_like(x) if both else None
+        grads = torch.empty((3, C), dtype=torch.float32, device=x.device)
+        ws_bytes = lib.msml_bn_workspace(P, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        # a residual without PReLU passes its gradient straight through (dres = dy): no extra stream
+        check(lib.msml_bn_bwd(_ptr(dy_d), _ptr(x), _ptr(res) if both else None, _ptr(gamma), _ptr(beta),
+                              _ptr(prelu), _ptr(stats[0]), _ptr(stats[1]), _ptr(dx), _ptr(dres), _ptr(grads[0]), _ptr(grads[1]),
+                              _ptr(grads[2]), P, C, dtype_code(x.dtype), int(training), _ptr(ws), ws_bytes, stream_ptr()))
+        dprelu = grads[2] if prelu is not None else None
+        return dx, grads[0], grads[1], dprelu, (dres if both else (dy_d if has_res else None)), None, None, None, None, None, None
+
+
+def bn_act(x, bn, prelu=None, res=None):
+    """y = prelu(bn(x) [+ res]) with ``bn`` an nn.BatchNorm2d and ``prelu`` an nn.PReLU (or None): statistics,
+    normalisation, residual add and activation in two fused passes (forward) / two (backward)."""
+    if x.dim() != 4:
+        raise ValueError("bn_act expects a 4-D (B, C, H, W) tensor")
+    if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+        raise RuntimeError("bn_act supports affine BatchNorm2d with running statistics and a fixed momentum")
+    a = prelu.weight if prelu is not None else None
+    if a is not None and a.numel() != x.shape[1]:
+        raise ValueError("bn_act: PReLU must have one slope per channel")
+    if res is not None and res.dtype != x.dtype:
+        res = res.to(x.dtype)
+    return _BNAct.apply(x, bn.weight, bn.bias, a, res, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                        bn.training, bn.momentum, bn.eps)
+
+
+# --------------------------------------------------------------------------------------------
 # K-B  DAP + argmax mask                        ref backbones/osb/unet.py:158-161,223; train.py:357
 # --------------------------------------------------------------------------------------------
 class _DAP(torch.autograd.Function):

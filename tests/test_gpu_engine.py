@@ -1,0 +1,85 @@
+"""TrainStep: the CUDA-graph replay must compute the same step as the eager path, and the eager
+path must match the oracle's CPU restatement of the reference step."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import assert_close, host, need_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(seed=3, classes=1000, B=8, fp16=False):
+    from msml_b200.backbones import MSML
+    from msml_b200.headers import ArcFace, PartialFC
+    from oracle.detfill import fill_state_dict_
+    torch.manual_seed(seed)
+    net = MSML("iresnet18", "unet", (1, 1, 1, 1), classes, fp16=fp16, header_type=None, fm_params=(3, 2, "sigmoid", "mul"))
+    fill_state_dict_(net)
+    net = net.cuda().train()
+    pfc = PartialFC(0, 0, 1, B, False, ArcFace(64.0, 0.5), classes)
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4)
+    opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.01, momentum=0.9, weight_decay=5e-4)
+    return net, pfc, opt, opt_pfc
+
+
+def test_graph_replay_matches_eager():
+    need_gpu()
+    from msml_b200.engine import TrainStep
+    B = 8
+    g = torch.Generator(device="cuda").manual_seed(5)
+    imgs = [torch.randn(B, 3, 112, 112, device="cuda", generator=g) for _ in range(3)]
+    labels = [torch.randint(0, 1000, (B,), device="cuda", generator=g) for _ in range(3)]
+    losses, weights = {}, {}
+    for mode in ("eager", "graph"):
+        net, pfc, opt, opt_pfc = _build()
+        step = TrainStep(net, pfc, opt, opt_pfc, (B, 3, 112, 112), use_graph=(mode == "graph"))
+        if mode == "graph":
+            before = copy.deepcopy(net.state_dict())
+            step.recapture()                          # warm-up + capture must leave model / optimizer state untouched
+            for k, v in net.state_dict().items():
+                assert torch.equal(v, before[k]), k
+        losses[mode] = [float(step(i, l)) for i, l in zip(imgs, labels)]
+        weights[mode] = (host(net.frb.conv1.weight), host(net.frb.fm_ops[2].same_conv.weight), host(pfc.weight))
+        assert net.osb.conv1.weight.grad is None       # unused branch keeps grad None => optimizer skips it (ref semantics)
+    for a, b in zip(losses["eager"], losses["graph"]):
+        assert abs(a - b) <= 2e-3 * abs(a), (losses["eager"], losses["graph"])
+    # same kernels, same order; only the fp32 atomics of the head (dX split-K, rdot) reorder between runs, and three
+    # SGD steps at s=64 amplify that slightly: compare in norm
+    for a, b in zip(weights["eager"], weights["graph"]):
+        assert np.linalg.norm(a - b) <= 2e-3 * np.linalg.norm(a), np.linalg.norm(a - b) / np.linalg.norm(a)
+
+
+def test_eager_step_matches_cpu_oracle_step():
+    """One full step (ires18, 1000 classes, fp32 backbone) against oracle.model_cpu + oracle.partial_fc."""
+    need_gpu()
+    from msml_b200.engine import TrainStep
+    from oracle import model_cpu, partial_fc as opfc
+    B = 8
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        net, pfc, opt, opt_pfc = _build()
+        sd = model_cpu.trainable_state(net)
+        w0 = host(pfc.weight)
+        g = torch.Generator().manual_seed(9)
+        img = torch.randn(B, 3, 112, 112, generator=g)
+        label = torch.randint(0, 1000, (B,), generator=g)
+        step = TrainStep(net, pfc, opt, opt_pfc, (B, 3, 112, 112), use_graph=False, max_norm=None)
+        loss = float(step(img.cuda(), label.cuda()))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    feat, _ = model_cpu.msml_forward(sd, img, "iresnet18", training=True)
+    featn = torch.nn.functional.normalize(feat)
+    res = opfc.step([featn.detach().to(torch.bfloat16).double().numpy()], [label.numpy()], [w0], 1000, "arc", 64.0, 0.5)
+    assert abs(loss - res["loss"]) <= 2e-3 * abs(res["loss"]), (loss, res["loss"])
+    featn.backward(torch.from_numpy(res["x_grad"][0]).float())
+    for key in ("frb.conv1.weight", "frb.fm_ops.0.same_conv.weight", "frb.layer3.0.conv1.weight", "frb.fc.weight"):
+        want = sd[key].grad.numpy()
+        got_w = host(dict(net.named_parameters())[key])           # w1 = w0 - lr * (g + wd * w0)
+        w_init = sd[key].detach().numpy()
+        got_grad = (w_init - got_w) / 0.01 - 5e-4 * w_init
+        assert_close(got_grad, want, 5e-2, atol_frac=3e-2, what="grad via SGD update " + key)

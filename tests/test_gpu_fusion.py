@@ -151,3 +151,83 @@ def test_dap_full_size_properties():
     assert_close(host(y), host(base), 1e-6, atol=1e-6, what="dap const groups")
     assert torch.equal(mask, (base[:, 1].float() > base[:, 0].float()).long())
     assert np.array_equal(odap.argmax_mask(host(y)), mask.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------- fused BN / PReLU / residual
+class _BNRef(torch.nn.Module):
+    def __init__(self, C, prelu):
+        super().__init__()
+        self.bn = torch.nn.BatchNorm2d(C, eps=1e-05)
+        self.prelu = torch.nn.PReLU(C) if prelu else None
+
+
+@pytest.mark.parametrize("C,H", [(32, 9), (64, 14), (128, 7), (512, 7), (256, 3)])
+@pytest.mark.parametrize("prelu", [False, True])
+@pytest.mark.parametrize("res", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn_act_train_vs_oracle(C, H, prelu, res, dtype):
+    need_gpu()
+    from msml_b200 import ops
+    from oracle import bn_act as obn
+    torch.manual_seed(C + H)
+    B = 5
+    m = _BNRef(C, prelu).cuda().train()
+    with torch.no_grad():
+        m.bn.weight.uniform_(0.5, 1.5); m.bn.bias.normal_(0, 0.2)
+        m.bn.running_mean.normal_(0, 0.1); m.bn.running_var.uniform_(0.5, 1.5)
+        if prelu:
+            m.prelu.weight.uniform_(0.1, 0.4)
+    rm0, rv0 = host(m.bn.running_mean), host(m.bn.running_var)
+    x = (torch.randn(B, C, H, H, device="cuda") * 1.3 + 0.4).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    r = torch.randn(B, C, H, H, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True) if res else None
+    dy = torch.randn(B, C, H, H, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    y = ops.bn_act(x, m.bn, m.prelu, r)
+    y.backward(dy)
+    flat = lambda t: host(t).transpose(0, 2, 3, 1).reshape(-1, C)
+    g, b = host(m.bn.weight), host(m.bn.bias)
+    a = host(m.prelu.weight) if prelu else None
+    want, st = obn.bn_act_fwd(flat(x), g, b, a, flat(r) if res else None, True, rm0, rv0)
+    wb = obn.bn_act_bwd(flat(dy), flat(x), g, b, a, flat(r) if res else None)
+    lo = dtype == torch.bfloat16
+    assert_close(flat(y), want, 2e-2 if lo else 2e-5, atol=2e-2 if lo else 2e-5, what="bn y")
+    assert_close(host(m.bn.running_mean), st["running_mean"], 1e-5, atol=1e-6, what="running_mean")
+    assert_close(host(m.bn.running_var), st["running_var"], 1e-4, atol=1e-6, what="running_var")
+    assert int(m.bn.num_batches_tracked) == 1
+    assert_close(flat(x.grad), wb["dx"], 2e-2 if lo else 1e-4, atol_frac=1e-2 if lo else 1e-5, what="bn dx")
+    assert_close(host(m.bn.weight.grad), wb["dgamma"], 2e-2 if lo else 1e-4, atol_frac=1e-2 if lo else 1e-5, what="dgamma")
+    assert_close(host(m.bn.bias.grad), wb["dbeta"], 2e-2 if lo else 1e-4, atol_frac=1e-2 if lo else 1e-5, what="dbeta")
+    if prelu:
+        assert_close(host(m.prelu.weight.grad), wb["dprelu"], 2e-2 if lo else 1e-4, atol_frac=1e-2 if lo else 1e-5, what="dprelu")
+    if res:
+        assert_close(flat(r.grad), wb["dres"], 2e-2 if lo else 1e-5, atol_frac=1e-2 if lo else 1e-6, what="dres")
+
+
+def test_bn_act_eval_uses_running_stats():
+    need_gpu()
+    from msml_b200 import ops
+    from oracle import bn_act as obn
+    torch.manual_seed(3)
+    C = 64
+    m = _BNRef(C, True).cuda().eval()
+    with torch.no_grad():
+        m.bn.running_mean.normal_(0, 0.3); m.bn.running_var.uniform_(0.5, 2.0); m.bn.weight.uniform_(0.5, 1.5)
+    x = torch.randn(3, C, 6, 5, device="cuda").contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y = ops.bn_act(x, m.bn, m.prelu)
+    flat = lambda t: host(t).transpose(0, 2, 3, 1).reshape(-1, C)
+    want, _ = obn.bn_act_fwd(flat(x), host(m.bn.weight), host(m.bn.bias), host(m.prelu.weight), None, False,
+                             host(m.bn.running_mean), host(m.bn.running_var))
+    assert_close(flat(y), want, 2e-5, atol=2e-5, what="bn eval")
+    assert int(m.bn.num_batches_tracked) == 0
+
+
+def test_bn_act_full_size_statistics():
+    """Stage-1 shape at batch 128 (64 x 56 x 56, bf16): the output is normalised per channel."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(4)
+    m = _BNRef(64, False).cuda().train()
+    x = (torch.randn(128, 64, 56, 56, device="cuda") * 3 + 5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = ops.bn_act(x, m.bn).float()
+    assert y.mean((0, 2, 3)).abs().max().item() < 5e-3
+    assert (y.var((0, 2, 3), unbiased=False) - 1).abs().max().item() < 1e-2

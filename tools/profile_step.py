@@ -28,14 +28,12 @@ img = torch.randn(args.batch, 3, 112, 112, device="cuda")
 label = torch.randint(0, args.classes, (args.batch,), device="cuda")
 
 
+from msml_b200.engine import TrainStep  # noqa: E402
+_ts = TrainStep(net, pfc, opt, opt_pfc, (args.batch, 3, 112, 112), use_graph=False)
+
+
 def step():
-    feat, _ = net(img)
-    featn = torch.nn.functional.normalize(feat)
-    x_grad, loss = pfc.forward_backward(label, featn, opt_pfc)
-    featn.backward(x_grad)
-    torch.nn.utils.clip_grad_norm_([p for p in net.parameters() if p.grad is not None], 5)
-    opt.step(); opt_pfc.step(); pfc.update()
-    opt.zero_grad(set_to_none=True); opt_pfc.zero_grad(set_to_none=True)
+    _ts(img, label)
 
 
 for _ in range(4):
