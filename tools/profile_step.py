@@ -16,20 +16,21 @@ ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--frb", default="iresnet50")
 ap.add_argument("--classes", type=int, default=93431)
 ap.add_argument("--rows", type=int, default=45)
+ap.add_argument("--graph", action="store_true", help="profile CUDA-graph replays instead of eager steps")
 args = ap.parse_args()
 
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(1)
 net = MSML(args.frb, "unet", (1, 1, 1, 1), args.classes, fp16=True, header_type=None, fm_params=(3, 2, "sigmoid", "mul")).cuda().train()
 pfc = PartialFC(0, 0, 1, args.batch, False, ArcFace(), args.classes)
-opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.02, momentum=0.9, weight_decay=5e-4)
-opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.02, momentum=0.9, weight_decay=5e-4)
+opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.02, momentum=0.9, weight_decay=5e-4, fused=True)
+opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.02, momentum=0.9, weight_decay=5e-4, fused=True)
 img = torch.randn(args.batch, 3, 112, 112, device="cuda")
 label = torch.randint(0, args.classes, (args.batch,), device="cuda")
 
 
 from msml_b200.engine import TrainStep  # noqa: E402
-_ts = TrainStep(net, pfc, opt, opt_pfc, (args.batch, 3, 112, 112), use_graph=False)
+_ts = TrainStep(net, pfc, opt, opt_pfc, (args.batch, 3, 112, 112), use_graph=args.graph)
 
 
 def step():
