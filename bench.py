@@ -325,6 +325,7 @@ def run_head(args, rank, local_rank, world):
     torch.cuda.set_device(dev)
     pk = peaks()
     torch.manual_seed(1)
+    BATCH = args.batch                                       # per-rank batch (shadows the module constant on purpose)
     pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), args.classes, sample_rate=args.sample_rate, embedding_size=512)
     opt = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.1, momentum=0.9, weight_decay=5e-4)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -382,6 +383,8 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "fusion", "head"])
     ap.add_argument("--classes", type=int, default=1_000_000)
     ap.add_argument("--sample-rate", type=float, default=1.0)
+    ap.add_argument("--batch", type=int, default=BATCH, help="head workload only: per-rank batch (1024 on one GPU reproduces the "
+                    "per-rank GEMM shapes of the 8-GPU config-4 run: B_tot=1024 rows against a 125,000-class shard)")
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")

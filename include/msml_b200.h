@@ -88,8 +88,12 @@ int msml_fm_mask_bwd(const void* dout, const void* yf, const void* m, void* dyf,
  * (unbiased variance), num_batches_tracked += 1 (nullable).  training == 0: running statistics.
  * res / prelu are nullable.  save_mean / save_invstd (C) are outputs of fwd and inputs of bwd.
  * bwd: dres is written only when BOTH res and prelu are fused (otherwise d res == dy);
- *      dgamma / dbeta / dprelu are fp32 (C).  C must be a multiple of the 16-byte vector width
- *      with (C / width) dividing 256.
+ *      dgamma / dbeta / dprelu are fp32 (C), overwritten, or added to when accumulate_param_grads != 0
+ *      (the caller passes the parameters' .grad storage: what torch's AccumulateGrad would do in a
+ *      separate kernel per parameter).  C must be a multiple of the 16-byte vector width with
+ *      (C / width) dividing 256.
+ * Training-mode fwd and bwd are ONE cooperative launch each (slab statistics -> grid barrier -> finalize ->
+ * grid barrier -> apply); the device must support cooperative launches (every sm_100 part does).
  * ------------------------------------------------------------------------------------------ */
 size_t msml_bn_workspace(int64_t P, int64_t C);
 int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
@@ -99,7 +103,7 @@ int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, con
 int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* beta,
                 const float* prelu, const float* save_mean, const float* save_invstd, void* dx, void* dres,
                 float* dgamma, float* dbeta, float* dprelu, int64_t P, int64_t C, int dtype, int training,
-                void* workspace, size_t workspace_bytes, void* stream);
+                int accumulate_param_grads, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K-B  DAP head of the segmentation branch + argmax mask.

@@ -4,17 +4,30 @@
 //   (ref backbones/fm/fmoperator.py:52-68):      y = prelu( bn(x) [+ res] )
 //
 // In the reference these are 3-6 separate ATen kernels per layer (batch_norm statistics, transform,
-// prelu, add; and five more in backward) and make up ~60 % of the training step on B200.  Here:
-//   forward   stats  : one read of x   -> per-CTA (mean, M2) partials -> finalize (Chan merge in fp64,
-//                                         running stats, scale/shift)             [training only]
-//             apply  : read x [, res], write y = prelu(x*scale + shift [+ res])
-//   backward  reduce : read dy, x [, res] -> per-CTA partials of (sum du, sum du*xhat, sum dy*u*[u<=0])
-//                      -> finalize (dgamma, dbeta, dprelu, per-channel coefficients)
-//             apply  : read dy, x [, res], write dx [, dres = du]
-// All passes are HBM-bound streams over a (P = N*H*W) x C matrix with C contiguous: a thread owns
-// one 16-byte channel vector for its whole life (grid strides are multiples of the row), so the
-// per-channel coefficients live in registers; loads are 128-bit, several rows in flight per thread.
+// prelu, add; and five more in backward) and make up ~60 % of the training step on B200.  A layer's
+// tensors are 6-50 MB, i.e. 1-8 us of HBM time, so as separate launches the chain is bound by
+// launch / drain latency, not bandwidth.  Here each direction is ONE cooperative (grid-synchronised) kernel:
+//   forward   phase 1  read x -> per-CTA (mean, M2) slab statistics
+//             phase 2  Chan merge of the slabs (one CTA per channel), running stats, scale / shift
+//             phase 3  re-read the SAME slab newest-first (an activation of <= 51 MB is still in the
+//                      126 MB L2) [+ res], write y = prelu(x*scale + shift [+ res])
+//   backward  phase 1  read dy, x [, res] -> per-CTA partials of (sum du, sum du*xhat, sum dy*u*[u<=0])
+//             phase 2  dgamma, dbeta, dprelu and the coefficients of dx
+//             phase 3  re-read the slab, write dx [, dres = du]
+// (A variant with fp64 atomics into per-channel accumulators and a single barrier was measured and was
+// slower: same-address atomics from 300-600 CTAs cost more than the second barrier.)
+// Minimum HBM traffic is one read of each input + one write of each output.
+// All phases stream a (P = N*H*W) x C matrix with C contiguous: a thread owns one 16-byte channel
+// vector for its whole life, so per-channel coefficients live in registers; loads are 128-bit, several
+// rows in flight per thread.  Eval mode (running statistics) keeps the two-kernel path.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <map>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace msml {
 
@@ -26,66 +39,52 @@ struct BnGeom {
   int C;           // channels (contiguous)
   int vpr;         // 16-byte vectors per row
   int rows_per_pass;   // kBnThreads / vpr
-  int grid;
+  int skip;            // debug (MSML_BN_SKIP_PHASES bitmask: 1, 2, 4 skip the work of phase 1, 2, 3; 8 = timestamps)
 };
 
-// ------------------------------------------------------------------------------------------- forward
-template <typename T>
-__global__ void __launch_bounds__(kBnThreads)
-bn_stats_partial_kernel(const T* __restrict__ x, BnGeom g, float* __restrict__ part /* [grid][2][C]: mean, M2 */,
-                        float* __restrict__ part_n /* [grid] */) {
-  constexpr int VN = Vec<T>::N;
-  __shared__ float red[2][kBnThreads * 8 / 8 * 8];   // [2][rows_per_pass * C] <= [2][256*8]
-  const int cv = threadIdx.x % g.vpr, rl = threadIdx.x / g.vpr;
-  const int64_t rows_per_cta = (g.P + g.grid - 1) / g.grid;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-  int64_t r1 = r0 + rows_per_cta;
-  if (r1 > g.P) r1 = g.P;
-  float s[VN], q[VN];
+// VN consecutive per-channel values as 16-byte loads (a strided scalar load per element costs one 32-byte sector each)
+template <int VN>
+__device__ __forceinline__ void ld_coef(const float* p, float* out) {
 #pragma unroll
-  for (int i = 0; i < VN; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
-  int64_t r = r0 + rl;
-  // 4 rows in flight per thread
-  for (; r + 3 * g.rows_per_pass < r1; r += 4 * g.rows_per_pass) {
-    uint4 v[4];
+  for (int i = 0; i < VN; i += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p + i);
+    out[i] = v.x; out[i + 1] = v.y; out[i + 2] = v.z; out[i + 3] = v.w;
+  }
+}
+template <int VN>
+__device__ __forceinline__ void st_coef(float* p, const float* v, bool accumulate) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld_stream(xv + (r + (int64_t)u * g.rows_per_pass) * g.vpr);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float f[VN];
-      Vec<T>::unpack(v[u], f);
-#pragma unroll
-      for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+  for (int i = 0; i < VN; i += 4) {
+    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    if (accumulate) {
+      const float4 old = *reinterpret_cast<const float4*>(p + i);
+      o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
     }
+    *reinterpret_cast<float4*>(p + i) = o;
   }
-  for (; r < r1; r += g.rows_per_pass) {
-    float f[VN];
-    Vec<T>::unpack(ld_stream(xv + r * g.vpr), f);
-#pragma unroll
-    for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
-  }
-  // reduce over the row lanes of the CTA
-#pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    red[0][rl * g.C + cv * VN + i] = s[i];
-    red[1][rl * g.C + cv * VN + i] = q[i];
-  }
-  __syncthreads();
-  const float n = (float)(r1 > r0 ? r1 - r0 : 0);
-  for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
-    float ss = 0.f, qq = 0.f;
-    for (int k = 0; k < g.rows_per_pass; ++k) { ss += red[0][k * g.C + c]; qq += red[1][k * g.C + c]; }
-    const float mean = n > 0.f ? ss / n : 0.f;
-    part[((int64_t)blockIdx.x * 2 + 0) * g.C + c] = mean;
-    part[((int64_t)blockIdx.x * 2 + 1) * g.C + c] = fmaxf(qq - ss * mean, 0.f);   // M2 of this slab
-  }
-  if (threadIdx.x == 0) part_n[blockIdx.x] = n;
 }
 
-// Chan et al. parallel merge of the slab statistics; running stats; per-channel scale/shift.
-// One warp per channel: lanes stride over the slabs, then a 5-step shuffle merge (all fp32: the merge of
-// (n, mean, M2) triples is well conditioned).
+// Lanes of a warp that own the same channel vector (vpr < 32) are folded with shuffles.
+template <int VN>
+__device__ __forceinline__ void fold_lanes(float* v, int vpr) {
+  for (int o = vpr; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < VN; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+}
+// After fold_lanes, a CTA holds `nslots` partial vectors per channel: one per warp (vpr < 32) or one per row lane.
+struct FoldSlots {
+  int slot, nslots;
+  bool writer;
+};
+__device__ __forceinline__ FoldSlots fold_slots(int vpr, int rl) {
+  FoldSlots f;
+  if (vpr < 32) { f.slot = threadIdx.x >> 5; f.nslots = kBnThreads / 32; f.writer = (int)(threadIdx.x & 31) < vpr; }
+  else { f.slot = rl; f.nslots = kBnThreads / vpr; f.writer = true; }
+  return f;
+}
+
+// Chan et al. parallel merge of (n, mean, M2) triples (fp32: the merge is well conditioned).
 __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb, float m2b) {
   if (nb <= 0.f) return;
   const float tot = n + nb, delta = mb - mean;
@@ -94,34 +93,199 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
   m2 += m2b + delta * delta * n * f;
   n = tot;
 }
+// CTAs without phase-2 work would otherwise spin on the barrier's L2 line while the few busy CTAs read their
+// partials through the same L2: let them sleep first.
+__device__ __forceinline__ void idle_before_barrier(bool idle) {
+  if (idle) __nanosleep(1500);
+}
 
-__global__ void __launch_bounds__(256)
-bn_stats_finalize_kernel(const float* __restrict__ part, const float* __restrict__ part_n, int grid, int C, float P,
-                         const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
-                         float* __restrict__ running_var, long long* __restrict__ nbt, float momentum, float eps,
-                         float* __restrict__ save_mean, float* __restrict__ save_invstd, float* __restrict__ coef /* [2][C] */) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
-  if (c >= C) return;
-  float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int b = lane; b < grid; b += 32)
-    chan_merge(n, mean, m2, part_n[b], part[((int64_t)b * 2 + 0) * C + c], part[((int64_t)b * 2 + 1) * C + c]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
-                m2b = __shfl_xor_sync(0xffffffffu, m2, o);
-    chan_merge(n, mean, m2, nb, mb, m2b);
+// debug attribution (MSML_BN_SKIP_PHASES & 8): CTA 0 stamps %globaltimer at the pass boundaries into the state tail
+__device__ __forceinline__ void dbg_stamp(const int skip, float* coef, int C, int idx) {
+  if ((skip & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(coef + 3 * C)[idx] = t;
   }
-  if (lane != 0) return;
-  const float var = m2 / P;                       // biased: normalisation
-  const float invstd = rsqrtf(var + eps);
-  save_mean[c] = mean;
-  save_invstd[c] = invstd;
-  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-  if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (P > 1.f ? m2 / (P - 1.f) : var);
-  const float sc = (gamma ? gamma[c] : 1.f) * invstd;
-  coef[c] = sc;
-  coef[C + c] = (beta ? beta[c] : 0.f) - mean * sc;
+}
+
+// rows [r0, r1) of this CTA; thread-local row index k maps to row r0 + rl + k * rows_per_pass
+struct Slab {
+  int64_t r0, r1;
+  int n_it;        // rows owned by this thread
+};
+__device__ __forceinline__ Slab slab_of(const BnGeom& g, int rl) {
+  Slab s;
+  const int64_t rows_per_cta = (g.P + gridDim.x - 1) / gridDim.x;
+  s.r0 = (int64_t)blockIdx.x * rows_per_cta;
+  s.r1 = s.r0 + rows_per_cta;
+  if (s.r1 > g.P) s.r1 = g.P;
+  const int64_t span = s.r1 - s.r0 - rl;
+  s.n_it = span > 0 ? (int)((span + g.rows_per_pass - 1) / g.rows_per_pass) : 0;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------- forward (training)
+// part layout: [k][C][grid] (channel-major so that phase 2 reads the slabs of a channel coalesced)
+template <typename T, bool RES, bool PRELU>
+__global__ void __launch_bounds__(kBnThreads)
+bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ prelu, float* __restrict__ running_mean,
+                    float* __restrict__ running_var, long long* __restrict__ nbt, float momentum, float eps,
+                    float* __restrict__ save_mean, float* __restrict__ save_invstd, float* part, float* part_n, float* coef,
+                    BnGeom g) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ float red[2][kBnThreads * 8];   // [2][nslots * C] <= [2][256*8]
+  cg::grid_group grid = cg::this_grid();
+  const int G = gridDim.x;
+  const int cv = threadIdx.x % g.vpr, rl = threadIdx.x / g.vpr;
+  const Slab sl = slab_of(g, rl);
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
+  const int64_t row0 = sl.r0 + rl;
+  dbg_stamp(g.skip, coef, g.C, 0);
+
+  // ---- phase 1: slab statistics
+  if (!(g.skip & 1)) {
+    float s[VN], q[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    int k = 0;
+    for (; k + 4 <= sl.n_it; k += 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld_stream(xv + (row0 + (int64_t)(k + u) * g.rows_per_pass) * g.vpr);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[VN];
+        Vec<T>::unpack(v[u], f);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    }
+    for (; k < sl.n_it; ++k) {
+      float f[VN];
+      Vec<T>::unpack(ld_stream(xv + (row0 + (int64_t)k * g.rows_per_pass) * g.vpr), f);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+    fold_lanes<VN>(s, g.vpr);
+    fold_lanes<VN>(q, g.vpr);
+    const FoldSlots fs = fold_slots(g.vpr, rl);
+    if (fs.writer) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        red[0][fs.slot * g.C + cv * VN + i] = s[i];
+        red[1][fs.slot * g.C + cv * VN + i] = q[i];
+      }
+    }
+    __syncthreads();
+    const float n = (float)(sl.r1 > sl.r0 ? sl.r1 - sl.r0 : 0);
+    for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
+      float ss = 0.f, qq = 0.f;
+      for (int r = 0; r < fs.nslots; ++r) { ss += red[0][r * g.C + c]; qq += red[1][r * g.C + c]; }
+      const float mean = n > 0.f ? ss / n : 0.f;
+      part[(size_t)c * G + blockIdx.x] = mean;
+      part[(size_t)(g.C + c) * G + blockIdx.x] = fmaxf(qq - ss * mean, 0.f);   // M2 of this slab
+    }
+    if (threadIdx.x == 0) part_n[blockIdx.x] = n;
+  }
+  dbg_stamp(g.skip, coef, g.C, 1);
+  grid.sync();
+  dbg_stamp(g.skip, coef, g.C, 2);
+
+  // ---- phase 2: merge the slabs, one CTA per channel (all loads issued up front, then a shuffle / smem tree)
+  if (!(g.skip & 2)) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+    const float Pf = (float)g.P;
+    constexpr int NL = (kBnMaxCtas + kBnThreads - 1) / kBnThreads;
+    for (int c = blockIdx.x; c < g.C; c += G) {
+      // thread 0 issues its (cold, HBM) parameter loads first so that their latency overlaps the merge
+      float p_g = 1.f, p_b = 0.f, p_rm = 0.f, p_rv = 0.f;
+      if (threadIdx.x == 0) {
+        if (gamma) p_g = gamma[c];
+        if (beta) p_b = beta[c];
+        if (running_mean) p_rm = running_mean[c];
+        if (running_var) p_rv = running_var[c];
+      }
+      const float* pm = part + (size_t)c * G;
+      const float* pq = part + (size_t)(g.C + c) * G;
+      float ln[NL], lm[NL], lq[NL];
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const int b = threadIdx.x + j * kBnThreads;
+        ln[j] = b < G ? part_n[b] : 0.f;
+        lm[j] = b < G ? pm[b] : 0.f;
+        lq[j] = b < G ? pq[b] : 0.f;
+      }
+      float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NL; ++j) chan_merge(n, mean, m2, ln[j], lm[j], lq[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                    m2b = __shfl_xor_sync(0xffffffffu, m2, o);
+        chan_merge(n, mean, m2, nb, mb, m2b);
+      }
+      __syncthreads();                      // red[] is free (phase 1 / previous channel done)
+      if (lane == 0) { red[0][warp * 3] = n; red[0][warp * 3 + 1] = mean; red[0][warp * 3 + 2] = m2; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        n = 0.f; mean = 0.f; m2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBnThreads / 32; ++w) chan_merge(n, mean, m2, red[0][w * 3], red[0][w * 3 + 1], red[0][w * 3 + 2]);
+        const float var = m2 / Pf;                       // biased: normalisation
+        const float invstd = rsqrtf(var + eps);
+        save_mean[c] = mean;
+        save_invstd[c] = invstd;
+        if (running_mean) running_mean[c] = (1.f - momentum) * p_rm + momentum * mean;
+        if (running_var) running_var[c] = (1.f - momentum) * p_rv + momentum * (Pf > 1.f ? m2 / (Pf - 1.f) : var);
+        const float sc = p_g * invstd;
+        coef[c] = sc;
+        coef[g.C + c] = p_b - mean * sc;
+      }
+    }
+    idle_before_barrier(blockIdx.x >= g.C);
+  }
+  dbg_stamp(g.skip, coef, g.C, 3);
+  grid.sync();
+  dbg_stamp(g.skip, coef, g.C, 4);
+
+  // ---- phase 3: apply over the same slab, newest rows first (they are the likeliest L2 hits)
+  if (!(g.skip & 4)) {
+    float sc[VN], sh[VN], pa[VN];
+    ld_coef<VN>(coef + cv * VN, sc);
+    ld_coef<VN>(coef + g.C + cv * VN, sh);
+    if (PRELU) ld_coef<VN>(prelu + cv * VN, pa);
+    constexpr int U = RES ? 2 : 4;
+    const uint4* rv = reinterpret_cast<const uint4*>(res) + cv;
+    uint4* yv = reinterpret_cast<uint4*>(y) + cv;
+    for (int k = sl.n_it - 1; k >= 0; k -= U) {
+      uint4 a[U], b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k - u >= 0) {
+          const int64_t v = (row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr;
+          a[u] = ld_stream(xv + v);
+          if (RES) b[u] = ld_stream(rv + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k - u < 0) break;
+        float f[VN], r[VN], o[VN];
+        Vec<T>::unpack(a[u], f);
+        if (RES) Vec<T>::unpack(b[u], r);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          float t = fmaf(f[i], sc[i], sh[i]);
+          if (RES) t += r[i];
+          o[i] = PRELU ? (t > 0.f ? t : t * pa[i]) : t;
+        }
+        yv[(row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr] = Vec<T>::pack(o);   // re-read by the next conv: default policy
+      }
+    }
+  }
+  dbg_stamp(g.skip, coef, g.C, 5);
 }
 
 // eval mode: coefficients from the running statistics
@@ -184,165 +348,203 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
 }
 
 // ------------------------------------------------------------------------------------------- backward
-// u = xhat*gamma + beta [+ res];  du = dy * (u > 0 ? 1 : a);  partial sums per slab:
-//   [0] sum du   [1] sum du * xhat   [2] sum dy * u * [u <= 0]
+// u = x*sc + sh [+ res] (sc = gamma*invstd, sh = beta - mean*sc);  du = dy * (u > 0 ? 1 : a);  xhat = x*invstd - mean*invstd
+// accumulators [3][C]:  [0] sum du   [1] sum du * xhat   [2] sum dy * u * [u <= 0]
+// dx = A*du - A*B - xhat * A*G   with A = gamma*invstd, B = sum du / P, G = sum du*xhat / P  (B = G = 0 in eval mode)
 template <typename T, bool RES, bool PRELU>
 __global__ void __launch_bounds__(kBnThreads)
-bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
-                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, const float* __restrict__ prelu, BnGeom g,
-                     float* __restrict__ part /* [grid][3][C] */) {
-  constexpr int VN = Vec<T>::N;
-  __shared__ float red[3][kBnThreads * 8];
-  const int cv = threadIdx.x % g.vpr, rl = threadIdx.x / g.vpr;
-  float mu[VN], is[VN], ga[VN], be[VN], pa[VN], s0[VN], s1[VN], s2[VN];
-#pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    const int c = cv * VN + i;
-    mu[i] = mean[c]; is[i] = invstd[c];
-    ga[i] = gamma ? gamma[c] : 1.f; be[i] = beta ? beta[c] : 0.f;
-    pa[i] = PRELU ? prelu[c] : 1.f;
-    s0[i] = s1[i] = s2[i] = 0.f;
-  }
-  const int64_t rows_per_cta = (g.P + g.grid - 1) / g.grid;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
-  int64_t r1 = r0 + rows_per_cta;
-  if (r1 > g.P) r1 = g.P;
-  constexpr int U = 2;
-  for (int64_t r = r0 + rl; r < r1; r += (int64_t)U * g.rows_per_pass) {
-    uint4 a[U], b[U], c4[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t rr = r + (int64_t)u * g.rows_per_pass;
-      if (rr < r1) {
-        const int64_t v = rr * g.vpr + cv;
-        a[u] = ld_stream(reinterpret_cast<const uint4*>(dy) + v);
-        b[u] = ld_stream(reinterpret_cast<const uint4*>(x) + v);
-        if (RES && PRELU) c4[u] = ld_stream(reinterpret_cast<const uint4*>(res) + v);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t rr = r + (int64_t)u * g.rows_per_pass;
-      if (rr >= r1) break;
-      float d[VN], f[VN], rs[VN];
-      Vec<T>::unpack(a[u], d);
-      Vec<T>::unpack(b[u], f);
-      if (RES && PRELU) Vec<T>::unpack(c4[u], rs);
-#pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        const float xh = (f[i] - mu[i]) * is[i];
-        float du = d[i];
-        if (PRELU) {
-          float uu = fmaf(xh, ga[i], be[i]);
-          if (RES) uu += rs[i];
-          const bool neg = !(uu > 0.f);
-          if (neg) { s2[i] = fmaf(d[i], uu, s2[i]); du *= pa[i]; }
-        }
-        s0[i] += du;
-        s1[i] = fmaf(du, xh, s1[i]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    red[0][rl * g.C + cv * VN + i] = s0[i];
-    red[1][rl * g.C + cv * VN + i] = s1[i];
-    red[2][rl * g.C + cv * VN + i] = s2[i];
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-    for (int k = 0; k < g.rows_per_pass; ++k) { t0 += red[0][k * g.C + c]; t1 += red[1][k * g.C + c]; t2 += red[2][k * g.C + c]; }
-    part[((int64_t)blockIdx.x * 3 + 0) * g.C + c] = t0;
-    part[((int64_t)blockIdx.x * 3 + 1) * g.C + c] = t1;
-    part[((int64_t)blockIdx.x * 3 + 2) * g.C + c] = t2;
-  }
-}
-
-// dgamma, dbeta, dprelu and the coefficients of  dx = A * (du - B - xhat * G); one warp per channel
-__global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ part, int grid, int C, float P, const float* __restrict__ gamma,
-                       const float* __restrict__ invstd, int training, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                       float* __restrict__ dprelu, float* __restrict__ coef /* [3][C]: A, B, G */) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (c >= C) return;
-  float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-  for (int b = lane; b < grid; b += 32) {
-    t0 += part[((int64_t)b * 3 + 0) * C + c];
-    t1 += part[((int64_t)b * 3 + 1) * C + c];
-    t2 += part[((int64_t)b * 3 + 2) * C + c];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-  }
-  if (lane != 0) return;
-  if (dbeta) dbeta[c] = t0;
-  if (dgamma) dgamma[c] = t1;
-  if (dprelu) dprelu[c] = t2;
-  coef[c] = (gamma ? gamma[c] : 1.f) * invstd[c];
-  coef[C + c] = training ? t0 / P : 0.f;      // eval: statistics are constants
-  coef[2 * C + c] = training ? t1 / P : 0.f;
-}
-
-template <typename T, bool RES, bool PRELU>
-__global__ void __launch_bounds__(kBnThreads)
-bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
+bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, const float* __restrict__ prelu, const float* __restrict__ coef,
-                    T* __restrict__ dx, T* __restrict__ dres, BnGeom g) {
+                    const float* __restrict__ beta, const float* __restrict__ prelu, T* __restrict__ dx, T* __restrict__ dres,
+                    float* dgamma, float* dbeta, float* dprelu, int training, int accumulate, float* part, float* coef, BnGeom g) {
   constexpr int VN = Vec<T>::N;
-  const int cv = threadIdx.x % g.vpr;
-  float mu[VN], is[VN], ga[VN], be[VN], pa[VN], A[VN], B[VN], G[VN];
+  constexpr bool R3 = RES && PRELU;          // the residual is only needed to recover the sign of u
+  constexpr int NA = PRELU ? 3 : 2;
+  __shared__ float red[NA][kBnThreads * 8];
+  cg::grid_group grid = cg::this_grid();
+  const int G = gridDim.x;
+  const int cv = threadIdx.x % g.vpr, rl = threadIdx.x / g.vpr;
+  const Slab sl = slab_of(g, rl);
+  const int64_t row0 = sl.r0 + rl;
+  const uint4* dyv = reinterpret_cast<const uint4*>(dy) + cv;
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
+  const uint4* rv = reinterpret_cast<const uint4*>(res) + cv;
+
+  float is[VN], nmis[VN], sc[VN], sh[VN], pa[VN];
+  {
+    float mu[VN], ga[VN], be[VN];
+    ld_coef<VN>(invstd + cv * VN, is);
+    ld_coef<VN>(mean + cv * VN, mu);
+    if (gamma) ld_coef<VN>(gamma + cv * VN, ga);
+    if (beta) ld_coef<VN>(beta + cv * VN, be);
+    if (PRELU) ld_coef<VN>(prelu + cv * VN, pa);
 #pragma unroll
-  for (int i = 0; i < VN; ++i) {
-    const int c = cv * VN + i;
-    mu[i] = mean[c]; is[i] = invstd[c];
-    ga[i] = gamma ? gamma[c] : 1.f; be[i] = beta ? beta[c] : 0.f;
-    pa[i] = PRELU ? prelu[c] : 1.f;
-    A[i] = coef[c]; B[i] = coef[g.C + c]; G[i] = coef[2 * g.C + c];
+    for (int i = 0; i < VN; ++i) {
+      nmis[i] = -mu[i] * is[i];
+      sc[i] = (gamma ? ga[i] : 1.f) * is[i];
+      sh[i] = (beta ? be[i] : 0.f) - mu[i] * sc[i];
+      if (!PRELU) pa[i] = 1.f;
+    }
   }
-  const int64_t total = g.P * g.vpr;
-  const int64_t stride = (int64_t)gridDim.x * kBnThreads;
-  constexpr int U = 2;
-  for (int64_t base = (int64_t)blockIdx.x * kBnThreads + threadIdx.x; base < total; base += stride * U) {
-    uint4 a[U], b[U], c4[U];
+  dbg_stamp(g.skip, coef, g.C, 0);
+
+  // ---- phase 1: slab reductions
+  if (!(g.skip & 1)) {
+    float s0[VN], s1[VN], s2[VN];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t v = base + u * stride;
-      if (v < total) {
-        a[u] = ld_stream(reinterpret_cast<const uint4*>(dy) + v);
-        b[u] = ld_stream(reinterpret_cast<const uint4*>(x) + v);
-        if (RES && PRELU) c4[u] = ld_stream(reinterpret_cast<const uint4*>(res) + v);
+    for (int i = 0; i < VN; ++i) s0[i] = s1[i] = s2[i] = 0.f;
+    constexpr int U = 2;
+    for (int k = 0; k < sl.n_it; k += U) {
+      uint4 a[U], b[U], c4[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k + u < sl.n_it) {
+          const int64_t v = (row0 + (int64_t)(k + u) * g.rows_per_pass) * g.vpr;
+          a[u] = ld_stream(dyv + v);
+          b[u] = ld_stream(xv + v);
+          if (R3) c4[u] = ld_stream(rv + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k + u >= sl.n_it) break;
+        float d[VN], f[VN], rs[VN];
+        Vec<T>::unpack(a[u], d);
+        Vec<T>::unpack(b[u], f);
+        if (R3) Vec<T>::unpack(c4[u], rs);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          const float xh = fmaf(f[i], is[i], nmis[i]);
+          float du = d[i];
+          if (PRELU) {
+            float uu = fmaf(f[i], sc[i], sh[i]);
+            if (RES) uu += rs[i];
+            if (!(uu > 0.f)) { s2[i] = fmaf(d[i], uu, s2[i]); du *= pa[i]; }
+          }
+          s0[i] += du;
+          s1[i] = fmaf(du, xh, s1[i]);
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t v = base + u * stride;
-      if (v >= total) break;
-      float d[VN], f[VN], rs[VN], o[VN], dr[VN];
-      Vec<T>::unpack(a[u], d);
-      Vec<T>::unpack(b[u], f);
-      if (RES && PRELU) Vec<T>::unpack(c4[u], rs);
+    fold_lanes<VN>(s0, g.vpr);
+    fold_lanes<VN>(s1, g.vpr);
+    if (PRELU) fold_lanes<VN>(s2, g.vpr);
+    const FoldSlots fs = fold_slots(g.vpr, rl);
+    if (fs.writer) {
 #pragma unroll
       for (int i = 0; i < VN; ++i) {
-        const float xh = (f[i] - mu[i]) * is[i];
-        float du = d[i];
-        if (PRELU) {
-          float uu = fmaf(xh, ga[i], be[i]);
-          if (RES) uu += rs[i];
-          if (!(uu > 0.f)) du *= pa[i];
-        }
-        dr[i] = du;
-        o[i] = A[i] * (du - B[i] - xh * G[i]);
+        red[0][fs.slot * g.C + cv * VN + i] = s0[i];
+        red[1][fs.slot * g.C + cv * VN + i] = s1[i];
+        if (PRELU) red[NA - 1][fs.slot * g.C + cv * VN + i] = s2[i];
       }
-      *(reinterpret_cast<uint4*>(dx) + v) = Vec<T>::pack(o);
-      if (RES && PRELU) *(reinterpret_cast<uint4*>(dres) + v) = Vec<T>::pack(dr);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      for (int r = 0; r < fs.nslots; ++r) {
+        t0 += red[0][r * g.C + c]; t1 += red[1][r * g.C + c];
+        if (PRELU) t2 += red[NA - 1][r * g.C + c];
+      }
+      part[(size_t)c * G + blockIdx.x] = t0;
+      part[(size_t)(g.C + c) * G + blockIdx.x] = t1;
+      if (PRELU) part[(size_t)(2 * g.C + c) * G + blockIdx.x] = t2;
     }
   }
+  dbg_stamp(g.skip, coef, g.C, 1);
+  grid.sync();
+  dbg_stamp(g.skip, coef, g.C, 2);
+
+  // ---- phase 2: dgamma, dbeta, dprelu, coefficients; one CTA per channel
+  if (!(g.skip & 2)) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float Pf = (float)g.P;
+    for (int c = blockIdx.x; c < g.C; c += G) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      for (int b = threadIdx.x; b < G; b += kBnThreads) {
+        t0 += part[(size_t)c * G + b];
+        t1 += part[(size_t)(g.C + c) * G + b];
+        if (PRELU) t2 += part[(size_t)(2 * g.C + c) * G + b];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+      }
+      __syncthreads();
+      if (lane == 0) { red[0][warp * 3] = t0; red[0][warp * 3 + 1] = t1; red[0][warp * 3 + 2] = t2; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        t0 = t1 = t2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBnThreads / 32; ++w) { t0 += red[0][w * 3]; t1 += red[0][w * 3 + 1]; t2 += red[0][w * 3 + 2]; }
+        if (accumulate) {       // write straight into the parameters' .grad (flat gradient buffer)
+          if (dbeta) dbeta[c] += t0;
+          if (dgamma) dgamma[c] += t1;
+          if (PRELU && dprelu) dprelu[c] += t2;
+        } else {
+          if (dbeta) dbeta[c] = t0;
+          if (dgamma) dgamma[c] = t1;
+          if (PRELU && dprelu) dprelu[c] = t2;
+        }
+        const float A = (gamma ? gamma[c] : 1.f) * invstd[c];
+        coef[c] = A;
+        coef[g.C + c] = training ? A * t0 / Pf : 0.f;      // eval: statistics are constants
+        coef[2 * g.C + c] = training ? A * t1 / Pf : 0.f;
+      }
+    }
+    idle_before_barrier(blockIdx.x >= g.C);
+  }
+  dbg_stamp(g.skip, coef, g.C, 3);
+  grid.sync();
+  dbg_stamp(g.skip, coef, g.C, 4);
+
+  // ---- phase 3: dx [, dres] over the same slab, newest rows first
+  if (!(g.skip & 4)) {
+    float A[VN], AB[VN], AG[VN];
+    ld_coef<VN>(coef + cv * VN, A);
+    ld_coef<VN>(coef + g.C + cv * VN, AB);
+    ld_coef<VN>(coef + 2 * g.C + cv * VN, AG);
+    uint4* dxv = reinterpret_cast<uint4*>(dx) + cv;
+    uint4* drv = reinterpret_cast<uint4*>(dres) + cv;
+    constexpr int U = 2;
+    for (int k = sl.n_it - 1; k >= 0; k -= U) {
+      uint4 a[U], b[U], c4[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k - u >= 0) {
+          const int64_t v = (row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr;
+          a[u] = ld_stream(dyv + v);
+          b[u] = ld_stream(xv + v);
+          if (R3) c4[u] = ld_stream(rv + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k - u < 0) break;
+        const int64_t v = (row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr;
+        float d[VN], f[VN], rs[VN], o[VN], dr[VN];
+        Vec<T>::unpack(a[u], d);
+        Vec<T>::unpack(b[u], f);
+        if (R3) Vec<T>::unpack(c4[u], rs);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) {
+          const float xh = fmaf(f[i], is[i], nmis[i]);
+          float du = d[i];
+          if (PRELU) {
+            float uu = fmaf(f[i], sc[i], sh[i]);
+            if (RES) uu += rs[i];
+            if (!(uu > 0.f)) du *= pa[i];
+          }
+          dr[i] = du;
+          o[i] = fmaf(-xh, AG[i], fmaf(A[i], du, -AB[i]));
+        }
+        dxv[v] = Vec<T>::pack(o);
+        if (R3) drv[v] = Vec<T>::pack(dr);
+      }
+    }
+  }
+  dbg_stamp(g.skip, coef, g.C, 5);
 }
 
 static int bn_geom(int64_t P, int64_t C, int dtype, BnGeom* g) {
@@ -354,20 +556,43 @@ static int bn_geom(int64_t P, int64_t C, int dtype, BnGeom* g) {
   MSML_REQUIRE(vpr <= kBnThreads && kBnThreads % vpr == 0, MSML_EUNSUPPORTED,
                "C=%lld: vectors per row (%d) must divide %d", (long long)C, vpr, kBnThreads);
   g->P = P; g->C = (int)C; g->vpr = vpr; g->rows_per_pass = kBnThreads / vpr;
-  // slabs of >= 8 passes per CTA, at most kBnMaxCtas CTAs
-  int64_t want = (P + (int64_t)g->rows_per_pass * 8 - 1) / ((int64_t)g->rows_per_pass * 8);
-  const int64_t cap = (int64_t)num_sms() * 4 < kBnMaxCtas ? (int64_t)num_sms() * 4 : kBnMaxCtas;
-  if (want > cap) want = cap;
-  if (want < 1) want = 1;
-  g->grid = (int)want;
+  static const int skip = getenv("MSML_BN_SKIP_PHASES") ? atoi(getenv("MSML_BN_SKIP_PHASES")) : 0;
+  g->skip = skip;
   return 0;
 }
 
-static size_t bn_ws_floats(int C) { return (size_t)kBnMaxCtas * 3 * C + kBnMaxCtas + 3 * (size_t)C; }
+// Every CTA must be co-resident (grid barrier), so the grid is capped by the occupancy of the
+// instantiation; slabs of >= 2 passes per CTA.
+template <typename K>
+static int coop_grid(K kernel, const BnGeom& g, int* out) {
+  static thread_local std::map<const void*, int> cache;     // max co-resident CTAs per kernel instantiation
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = cache.find(key);
+  int cap;
+  if (it == cache.end()) {
+    int per_sm = 0;
+    MSML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBnThreads, 0));
+    MSML_REQUIRE(per_sm > 0, MSML_EUNSUPPORTED, "BN kernel cannot be resident");
+    cap = per_sm * num_sms();
+    cache[key] = cap;
+  } else {
+    cap = it->second;
+  }
+  if (cap > kBnMaxCtas) cap = kBnMaxCtas;
+  static const int env_cap = getenv("MSML_BN_MAX_CTAS") ? atoi(getenv("MSML_BN_MAX_CTAS")) : 0;   // debug
+  if (env_cap > 0 && cap > env_cap) cap = env_cap;
+  int64_t want = (g.P + (int64_t)g.rows_per_pass * 2 - 1) / ((int64_t)g.rows_per_pass * 2);
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  *out = (int)want;
+  return 0;
+}
 
 }  // namespace msml
 
 using namespace msml;
+
+static size_t bn_ws_floats(int C) { return (size_t)kBnMaxCtas * 3 * C + kBnMaxCtas + 3 * (size_t)C + 16; }
 
 extern "C" size_t msml_bn_workspace(int64_t P, int64_t C) {
   (void)P;
@@ -382,38 +607,75 @@ extern "C" size_t msml_bn_workspace(int64_t P, int64_t C) {
            else { constexpr bool RES = false, PRELU = false; __VA_ARGS__; } }                   \
   })
 
+static int launch_grid_synced(const void* kern, int grid, void** args, cudaStream_t st) {
+  MSML_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kBnThreads), args, 0, st));
+  count_launch();
+  return 0;
+}
+
+template <typename T, bool RES, bool PRELU>
+static int launch_bn_fwd_fused(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
+                               float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps, float* save_mean,
+                               float* save_invstd, float* part, float* part_n, float* coef, BnGeom g, cudaStream_t st) {
+  auto kern = bn_fwd_fused_kernel<T, RES, PRELU>;
+  int grid = 0;
+  if (int e = coop_grid(kern, g, &grid)) return e;
+  const T* xp = static_cast<const T*>(x);
+  const T* rp = static_cast<const T*>(res);
+  T* yp = static_cast<T*>(y);
+  long long* nb = reinterpret_cast<long long*>(nbt);
+  void* args[] = {&xp, &rp, &yp, &gamma, &beta, &prelu, &running_mean, &running_var, &nb, &momentum, &eps,
+                  &save_mean, &save_invstd, &part, &part_n, &coef, &g};
+  return launch_grid_synced(reinterpret_cast<const void*>(kern), grid, args, st);
+}
+
+template <typename T, bool RES, bool PRELU>
+static int launch_bn_bwd_fused(const void* dy, const void* x, const void* res, const float* mean, const float* invstd,
+                               const float* gamma, const float* beta, const float* prelu, void* dx, void* dres, float* dgamma,
+                               float* dbeta, float* dprelu, int training, int accumulate, float* part, float* coef, BnGeom g,
+                               cudaStream_t st) {
+  auto kern = bn_bwd_fused_kernel<T, RES, PRELU>;
+  int grid = 0;
+  if (int e = coop_grid(kern, g, &grid)) return e;
+  const T* dyp = static_cast<const T*>(dy);
+  const T* xp = static_cast<const T*>(x);
+  const T* rp = static_cast<const T*>(res);
+  T* dxp = static_cast<T*>(dx);
+  T* drp = static_cast<T*>(dres);
+  void* args[] = {&dyp, &xp, &rp, &mean, &invstd, &gamma, &beta, &prelu, &dxp, &drp, &dgamma, &dbeta, &dprelu,
+                  &training, &accumulate, &part, &coef, &g};
+  return launch_grid_synced(reinterpret_cast<const void*>(kern), grid, args, st);
+}
+
 extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
                            float* running_mean, float* running_var, int64_t* num_batches_tracked, float* save_mean,
                            float* save_invstd, int64_t P, int64_t C, int dtype, int training, float momentum, float eps,
                            void* ws, size_t ws_bytes, void* stream) {
   BnGeom g;
   if (int e = bn_geom(P, C, dtype, &g)) return e;
-  MSML_REQUIRE(x && y && save_mean && save_invstd && ws, MSML_EINVAL, "null pointer");
+  MSML_REQUIRE(x && y && save_mean && save_invstd, MSML_EINVAL, "null pointer");
   MSML_REQUIRE(training || (running_mean && running_var), MSML_EINVAL, "eval mode needs running statistics");
-  MSML_REQUIRE(aligned16(x) && aligned16(y) && aligned16(res) && aligned16(ws), MSML_EALIGN, "pointers must be 16-byte aligned");
-  MSML_REQUIRE(ws_bytes >= msml_bn_workspace(P, C), MSML_EWORKSPACE, "BN workspace too small");
+  MSML_REQUIRE(aligned16(x) && aligned16(y) && aligned16(res) && aligned16(ws) && aligned16(gamma) && aligned16(beta) &&
+                   aligned16(prelu),
+               MSML_EALIGN, "pointers must be 16-byte aligned");
+  MSML_REQUIRE(ws && ws_bytes >= msml_bn_workspace(P, C), MSML_EWORKSPACE, "BN workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   float* part = static_cast<float*>(ws);
   float* part_n = part + (size_t)kBnMaxCtas * 3 * C;
   float* coef = part_n + kBnMaxCtas;
   const double elem = dtype == MSML_F32 ? 4.0 : 2.0;
   if (training) {
-    {
-      MSML_PROF("bn_stats", (double)P * C * elem, st);
-      MSML_DISPATCH_DTYPE(dtype, T, (bn_stats_partial_kernel<T><<<g.grid, kBnThreads, 0, st>>>(static_cast<const T*>(x), g, part, part_n)));
-      MSML_LAUNCH_CHECK();
-    }
-    MSML_PROF("bn_stats_finalize", (double)g.grid * 2 * C * 4, st);
-    bn_stats_finalize_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(part, part_n, g.grid, (int)C, (float)P, gamma, beta,
-                                                                        running_mean, running_var,
-                                                                        reinterpret_cast<long long*>(num_batches_tracked),
-                                                                        momentum, eps, save_mean, save_invstd, coef);
-    MSML_LAUNCH_CHECK();
-  } else {
-    bn_eval_coef_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>((int)C, gamma, beta, running_mean, running_var, eps, save_mean,
-                                                                   save_invstd, coef);
-    MSML_LAUNCH_CHECK();
+    MSML_PROF("bn_fwd_fused", (double)P * C * elem * (res ? 3 : 2), st);
+    int rc = 0;
+    MSML_BN_DISPATCH(dtype, res != nullptr, prelu != nullptr,
+                     (rc = launch_bn_fwd_fused<T, RES, PRELU>(x, res, y, gamma, beta, prelu, running_mean, running_var,
+                                                              num_batches_tracked, momentum, eps, save_mean, save_invstd,
+                                                              part, part_n, coef, g, st)));
+    return rc;
   }
+  bn_eval_coef_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>((int)C, gamma, beta, running_mean, running_var, eps, save_mean,
+                                                                 save_invstd, coef);
+  MSML_LAUNCH_CHECK();
   const int64_t total = P * g.vpr;
   int64_t blocks = (total + (int64_t)kBnThreads * 4 - 1) / ((int64_t)kBnThreads * 4);
   const int64_t cap = (int64_t)num_sms() * 4;
@@ -430,46 +692,26 @@ extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float*
 
 extern "C" int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* beta,
                            const float* prelu, const float* save_mean, const float* save_invstd, void* dx, void* dres,
-                           float* dgamma, float* dbeta, float* dprelu, int64_t P, int64_t C, int dtype, int training, void* ws,
-                           size_t ws_bytes, void* stream) {
+                           float* dgamma, float* dbeta, float* dprelu, int64_t P, int64_t C, int dtype, int training,
+                           int accumulate_param_grads, void* ws, size_t ws_bytes, void* stream) {
   BnGeom g;
   if (int e = bn_geom(P, C, dtype, &g)) return e;
-  MSML_REQUIRE(dy && x && dx && save_mean && save_invstd && ws, MSML_EINVAL, "null pointer");
+  MSML_REQUIRE(dy && x && dx && save_mean && save_invstd, MSML_EINVAL, "null pointer");
   const bool has_prelu = prelu != nullptr, has_res = res != nullptr;
   MSML_REQUIRE(!(has_prelu && has_res) || dres, MSML_EINVAL, "dres is required when both a residual and PReLU are fused");
-  MSML_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(res) && aligned16(dx) && aligned16(dres) && aligned16(ws), MSML_EALIGN,
-               "pointers must be 16-byte aligned");
-  MSML_REQUIRE(ws_bytes >= msml_bn_workspace(P, C), MSML_EWORKSPACE, "BN workspace too small");
+  MSML_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(res) && aligned16(dx) && aligned16(dres) && aligned16(ws) &&
+                   aligned16(gamma) && aligned16(beta) && aligned16(prelu) && aligned16(save_mean) && aligned16(save_invstd),
+               MSML_EALIGN, "pointers must be 16-byte aligned");
+  MSML_REQUIRE(ws && ws_bytes >= msml_bn_workspace(P, C), MSML_EWORKSPACE, "BN workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   float* part = static_cast<float*>(ws);
   float* coef = part + (size_t)kBnMaxCtas * 3 * C + kBnMaxCtas;
   const double elem = dtype == MSML_F32 ? 4.0 : 2.0;
-  const int streams_in = 2 + (has_prelu && has_res ? 1 : 0);
-  {
-    MSML_PROF("bn_bwd_reduce", (double)P * C * elem * streams_in, st);
-    MSML_BN_DISPATCH(dtype, has_res, has_prelu,
-                     (bn_bwd_reduce_kernel<T, RES, PRELU><<<g.grid, kBnThreads, 0, st>>>(
-                         static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(res), save_mean, save_invstd, gamma,
-                         beta, prelu, g, part)));
-    MSML_LAUNCH_CHECK();
-  }
-  {
-    MSML_PROF("bn_bwd_finalize", (double)g.grid * 3 * C * 4, st);
-    bn_bwd_finalize_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(part, g.grid, (int)C, (float)P, gamma, save_invstd, training,
-                                                                  dgamma, dbeta, has_prelu ? dprelu : nullptr, coef);
-    MSML_LAUNCH_CHECK();
-  }
-  const int64_t total = P * g.vpr;
-  int64_t blocks = (total + (int64_t)kBnThreads * 2 - 1) / ((int64_t)kBnThreads * 2);
-  const int64_t cap = (int64_t)num_sms() * 4;
-  const int grid = (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
-  {
-    MSML_PROF("bn_bwd_apply", (double)P * C * elem * (streams_in + 1 + (has_prelu && has_res ? 1 : 0)), st);
-    MSML_BN_DISPATCH(dtype, has_res, has_prelu,
-                     (bn_bwd_apply_kernel<T, RES, PRELU><<<grid, kBnThreads, 0, st>>>(
-                         static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<const T*>(res), save_mean, save_invstd, gamma,
-                         beta, prelu, coef, static_cast<T*>(dx), static_cast<T*>(dres), g)));
-    MSML_LAUNCH_CHECK();
-  }
-  return 0;
+  const int both = has_prelu && has_res ? 1 : 0;
+  MSML_PROF("bn_bwd_fused", (double)P * C * elem * (3 + 2 * both), st);
+  int rc = 0;
+  MSML_BN_DISPATCH(dtype, has_res, has_prelu,
+                   (rc = launch_bn_bwd_fused<T, RES, PRELU>(dy, x, res, save_mean, save_invstd, gamma, beta, prelu, dx, dres, dgamma,
+                                                            dbeta, dprelu, training, accumulate_param_grads, part, coef, g, st)));
+  return rc;
 }

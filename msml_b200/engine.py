@@ -47,12 +47,14 @@ class TrainStep:
         feat.sum().backward()
         self.backbone.load_state_dict(bn_state, strict=False)      # the probe must not touch the BN statistics
         used = [p for p in self.backbone.parameters() if p.grad is not None]
-        n = sum(p.numel() for p in used)
+        pad4 = lambda k: (k + 3) // 4 * 4     # every gradient starts on a 16-byte boundary (vector accesses in the kernels)
+        n = sum(pad4(p.numel()) for p in used)
         self.flat = torch.zeros(n, dtype=torch.float32, device=self.device)
         off = 0
         for p in used:      # same strides as the parameter (conv weights are channels-last): no layout conversion per step
             p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
-            off += p.numel()
+            p._msml_direct_grad = True          # fused kernels may add their parameter gradients into p.grad themselves
+            off += pad4(p.numel())
         self._used = used
         self.static_img.zero_()
 

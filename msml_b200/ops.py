@@ -157,14 +157,15 @@ class _BNAct(torch.autograd.Function):
         x_d = x.contiguous(memory_format=torch.channels_last)
         res_d = _dense_like(x_d, res) if res is not None else None
         y = torch.empty_like(x_d)
+        stats = torch.empty((2, C), dtype=torch.float32, device=x.device)
         ws_bytes = lib.msml_bn_workspace(P, C)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        stats = torch.empty((2, C), dtype=torch.float32, device=x.device)
         check(lib.msml_bn_fwd(_ptr(x_d), _ptr(res_d), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(prelu), _ptr(running_mean),
                               _ptr(running_var), _ptr(nbt) if training else None, _ptr(stats[0]), _ptr(stats[1]), P, C,
                               dtype_code(x_d.dtype), int(training), float(momentum), float(eps), _ptr(ws), ws_bytes, stream_ptr()))
         ctx.save_for_backward(x_d, res_d if prelu is not None else None, gamma, beta, prelu, stats)
         ctx.cfg = (training, res is not None)
+        ctx.params = (gamma, beta, prelu)          # the Parameter objects themselves (for the direct-gradient path)
         return y
 
     @staticmethod
@@ -178,15 +179,33 @@ class _BNAct(torch.autograd.Function):
         dx = torch.empty_like(x)
         both = has_res and prelu is not None
         dres = torch.empty_like(x) if both else None
-        grads = torch.empty((3, C), dtype=torch.float32, device=x.device)
         ws_bytes = lib.msml_bn_workspace(P, C)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        # Direct-gradient path (engine.TrainStep): the parameters' .grad are views of one flat fp32 buffer and the
+        # kernel adds dgamma / dbeta / dprelu into them itself: what AccumulateGrad would do in one more kernel each.
+        params = [p for p in ctx.params if p is not None]
+        direct = all(_direct_grad(p) for p in params)
+        if direct:
+            g_ptrs = [_ptr(p.grad) if p is not None else None for p in ctx.params]
+            grads = None
+        else:
+            grads = torch.empty((3, C), dtype=torch.float32, device=x.device)
+            g_ptrs = [_ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])]
         # a residual without PReLU passes its gradient straight through (dres = dy): no extra stream
         check(lib.msml_bn_bwd(_ptr(dy_d), _ptr(x), _ptr(res) if both else None, _ptr(gamma), _ptr(beta),
-                              _ptr(prelu), _ptr(stats[0]), _ptr(stats[1]), _ptr(dx), _ptr(dres), _ptr(grads[0]), _ptr(grads[1]),
-                              _ptr(grads[2]), P, C, dtype_code(x.dtype), int(training), _ptr(ws), ws_bytes, stream_ptr()))
+                              _ptr(prelu), _ptr(stats[0]), _ptr(stats[1]), _ptr(dx), _ptr(dres), g_ptrs[0], g_ptrs[1],
+                              g_ptrs[2], P, C, dtype_code(x.dtype), int(training), int(direct), _ptr(ws), ws_bytes, stream_ptr()))
+        d_res = dres if both else (dy_d if has_res else None)
+        if direct:
+            return dx, None, None, None, d_res, None, None, None, None, None, None
         dprelu = grads[2] if prelu is not None else None
-        return dx, grads[0], grads[1], dprelu, (dres if both else (dy_d if has_res else None)), None, None, None, None, None, None
+        return dx, grads[0], grads[1], dprelu, d_res, None, None, None, None, None, None
+
+
+def _direct_grad(p):
+    """True when the engine has marked ``p`` as living in its flat gradient buffer (see engine.TrainStep)."""
+    return (getattr(p, "_msml_direct_grad", False) and p.grad is not None and p.grad.dtype == torch.float32
+            and p.grad.is_contiguous() and p.grad.data_ptr() % 16 == 0)
 
 
 def bn_act(x, bn, prelu=None, res=None):
