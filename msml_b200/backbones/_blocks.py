@@ -32,9 +32,9 @@ class IBasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = self.conv1(ops.bn_act(x, self.bn1))
-        out = self.conv2(ops.bn_act(out, self.bn2, self.prelu))
-        skip = x if self.downsample is None else ops.bn_act(self.downsample[0](x), self.downsample[1])
+        out = ops.conv2d(ops.bn_act(x, self.bn1), self.conv1)
+        out = ops.conv2d(ops.bn_act(out, self.bn2, self.prelu), self.conv2)
+        skip = x if self.downsample is None else ops.bn_act(ops.conv2d(x, self.downsample[0]), self.downsample[1])
         return ops.bn_act(out, self.bn3, None, skip)          # bn3(out) + identity
 
 

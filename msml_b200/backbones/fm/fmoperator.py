@@ -37,9 +37,9 @@ class resblock_bottle(nn.Module):
         self.prelu3 = nn.PReLU(out_channels)
 
     def forward(self, x):
-        y = ops.bn_act(self.conv1(x), self.bn1, self.prelu1)
-        y = ops.bn_act(self.conv2(y), self.bn2, self.prelu2)
-        return ops.bn_act(self.conv3(y), self.bn3, self.prelu3, x)     # prelu3(bn3(.) + identity)
+        y = ops.bn_act(ops.conv2d(x, self.conv1), self.bn1, self.prelu1)
+        y = ops.bn_act(ops.conv2d(y, self.conv2), self.bn2, self.prelu2)
+        return ops.bn_act(ops.conv2d(y, self.conv3), self.bn3, self.prelu3, x)     # prelu3(bn3(.) + identity)
 
 
 def _conv_bn_prelu_x2(c):
@@ -126,7 +126,8 @@ class FMCnn(nn.Module):
     def forward(self, yf, yo, yt=None):
         """yf (B,C,H,W) face features, yo (B,18,H,W) occlusion maps, yt peer features (train only)
         -> (Z_f with the shape of yf, l2 distillation loss or None)."""
-        z = self.res_block(self.same_conv(torch.cat((yf, yo.to(yf.dtype)), dim=1)))
+        x, pad = ops.cat_channels_padded((yf, yo.to(yf.dtype)))        # C+18 channels, zero-padded to a multiple of 8
+        z = self.res_block(ops.conv2d_padded_in(x, self.same_conv, pad))
         f_out, l2 = None, None
         if self.use_ori or self.en_save:
             gate = self.mask_norm(z)

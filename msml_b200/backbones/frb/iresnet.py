@@ -69,7 +69,7 @@ class IResNet(nn.Module):
                 raise NotImplementedError("peer-guided training needs a pretrained peer network (not shipped with "
                                           "the reference); inject one with IResNet.set_peer()")
             _, ft = self.peer(ori)
-        x = ops.bn_act(self.conv1(x), self.bn1, self.prelu)
+        x = ops.bn_act(ops.conv2d_padded_in(x, self.conv1, x.shape[1] - self.conv1.in_channels), self.bn1, self.prelu)
         kd_terms = []
         for i, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
             x = layer(x)
@@ -77,7 +77,7 @@ class IResNet(nn.Module):
             kd_terms.append(l)
         x = ops.bn_act(x, self.bn2)
         x = self.dropout(torch.flatten(x, 1))
-        x = self.features(self.fc(x.float()))
+        x = self.features(ops.linear(x.float(), self.fc))
         kd = sum(kd_terms) if ori is not None and all(t is not None for t in kd_terms) else 0.
         return x, kd * 1.0
 

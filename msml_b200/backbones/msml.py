@@ -15,6 +15,8 @@ coalesced channel vectors; ``fp16=True`` selects bf16 autocast for OSB + FRB (fp
 bf16 needs no loss scaling), the 512-d feature is returned in fp32 as in the reference (ref :169).
 """
 import torch
+
+from .. import ops
 import torch.nn as nn
 
 from .fm import FMCnn, FMNone
@@ -104,6 +106,10 @@ class MSML(nn.Module):
     def forward(self, x, label=None, ori=None):
         x = x.contiguous(memory_format=torch.channels_last)
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bool(self.fp16)):
+            if self.fp16 and x.is_cuda:
+                # one bf16 copy of the image with the channels zero-padded 3 -> 8: both stem convolutions (OSB, FRB) then run
+                # cuDNN's tensor-core kernels instead of the 3-channel generic ones (their weights get zero input channels)
+                x, _ = ops.cat_channels_padded((x.to(torch.bfloat16),))
             if self.use_osb:
                 seg_list = self.osb(x)              # [seg0, seg1, seg2, seg3, seg5] small to big
                 final_seg = seg_list[4]

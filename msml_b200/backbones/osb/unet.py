@@ -28,7 +28,18 @@ class _GlobalConvModule(nn.Module):
         self.conv_r2 = nn.Conv2d(out_dim, out_dim, (kh, 1), padding=(ph, 0))
 
     def forward(self, x):
-        return self.conv_l2(self.conv_l1(x)) + self.conv_r2(self.conv_r1(x))
+        return (ops.conv2d(ops.conv2d(x, self.conv_l1), self.conv_l2) +
+                ops.conv2d(ops.conv2d(x, self.conv_r1), self.conv_r2))
+
+    def forward_padded(self, x, po):
+        """Same module with ``po`` zero output channels appended (they stay exactly zero): 18-channel maps become
+        24-channel ones so that cuDNN's tensor-core kernels apply (C % 8 == 0)."""
+        F = torch.nn.functional
+
+        def conv(t, m, pad_in):
+            w, b = ops.padded_params(m, pad_in, po)
+            return F.conv2d(t, w, b, m.stride, m.padding)
+        return conv(conv(x, self.conv_l1, 0), self.conv_l2, po) + conv(conv(x, self.conv_r1, 0), self.conv_r2, po)
 
 
 class _DAP(nn.Module):
@@ -70,17 +81,43 @@ class Unet(nn.Module):
             setattr(self, 'deconv%d' % i, nn.ConvTranspose2d(2 * seg, seg, kernel_size=4, stride=2, padding=1, bias=False))
         self.DAP = _DAP(dap_k)
 
+    def _decode_padded(self, x4, x3, x2, x1, x0):
+        """The decoder on channel counts padded to multiples of 8 (bf16 autocast path).  Padding channels carry zero
+        weights and zero biases, so the first ``seg`` channels are bit-identical in exact arithmetic; the results are
+        sliced back to the reference's shapes."""
+        F = torch.nn.functional
+        seg = self.deconv2.weight.shape[1]
+        po = (-seg) % 8
+        w, b = ops.padded_params(self.deconv1, (-self.deconv1.weight.shape[0]) % 8, po, transposed=True)
+        g1 = self.gcm1.forward_padded(x4, (-self.deconv1.weight.shape[0]) % 8)
+        d = self.deconv1
+        s = F.conv_transpose2d(g1, w, b, d.stride, d.padding, d.output_padding)
+        outs = [s]
+        for i, xi in zip((2, 3, 4, 5), (x3, x2, x1, x0)):
+            d = getattr(self, 'deconv%d' % i)
+            g = getattr(self, 'gcm%d' % i).forward_padded(xi, po)
+            wd = ops._weight_of(d)                                       # (2*seg, seg, 4, 4): rows [prev seg | gcm]
+            z = wd.new_zeros((po,) + tuple(wd.shape[1:])) if po else None
+            wp = torch.cat((wd[:seg], z, wd[seg:], z), 0) if po else wd
+            wp = F.pad(wp, (0, 0, 0, 0, 0, po)) if po else wp
+            s = F.conv_transpose2d(torch.cat((s, g), 1), wp, None, d.stride, d.padding, d.output_padding)
+            outs.append(s)
+        return [o[:, :seg] for o in outs]
+
     def _decode(self, x):
-        x0 = ops.bn_act(self.conv1(x), self.bn1, self.prelu)
+        x0 = ops.bn_act(ops.conv2d_padded_in(x, self.conv1, x.shape[1] - self.conv1.in_channels), self.bn1, self.prelu)
         x1 = self.layer1(x0)
         x2 = self.layer2(x1)
         x3 = self.layer3(x2)
         x4 = ops.bn_act(self.layer4(x3), self.bn2)
-        seg0 = self.deconv1(self.gcm1(x4))
-        seg1 = self.deconv2(torch.cat((seg0, self.gcm2(x3)), 1))
-        seg2 = self.deconv3(torch.cat((seg1, self.gcm3(x2)), 1))
-        seg3 = self.deconv4(torch.cat((seg2, self.gcm4(x1)), 1))
-        seg5_ = self.deconv5(torch.cat((seg3, self.gcm5(x0)), 1))
+        if x4.is_cuda and x4.dtype != torch.float32:
+            seg0, seg1, seg2, seg3, seg5_ = self._decode_padded(x4, x3, x2, x1, x0)
+            return [seg0.detach(), seg1.detach(), seg2.detach(), seg3.detach()], seg5_
+        seg0 = ops.conv_transpose2d(self.gcm1(x4), self.deconv1)
+        seg1 = ops.conv_transpose2d(torch.cat((seg0, self.gcm2(x3)), 1), self.deconv2)
+        seg2 = ops.conv_transpose2d(torch.cat((seg1, self.gcm3(x2)), 1), self.deconv3)
+        seg3 = ops.conv_transpose2d(torch.cat((seg2, self.gcm4(x1)), 1), self.deconv4)
+        seg5_ = ops.conv_transpose2d(torch.cat((seg3, self.gcm5(x0)), 1), self.deconv5)
         return [seg0.detach(), seg1.detach(), seg2.detach(), seg3.detach()], seg5_   # detach link, ref :227-230
 
     def forward(self, x):

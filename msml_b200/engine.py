@@ -28,12 +28,15 @@ class TrainStep:
         self.opt_backbone, self.opt_pfc = opt_backbone, opt_pfc
         self.world_size, self.max_norm, self.use_graph = world_size, max_norm, use_graph
         self.device = device or next(backbone.parameters()).device
+        # NHWC everywhere: channels-last weights spare cuDNN a weight-layout conversion per convolution, forward and wgrad
+        self.backbone.to(memory_format=torch.channels_last)
         self.static_img = torch.zeros(batch_shape, device=self.device).contiguous(memory_format=torch.channels_last)
         self.static_label = torch.zeros(batch_shape[0], dtype=torch.int64, device=self.device)
         self.static_loss = None
         self.flat = None
         self.graph = None
         self._used = None
+        self._shadow_src, self._shadow_dst = [], []
         if use_graph and int(pfc.sample_rate) != 1:
             raise ValueError("captured TrainStep needs PartialFC sample_rate == 1; use use_graph=False for sampled heads")
 
@@ -57,9 +60,25 @@ class TrainStep:
             off += pad4(p.numel())
         self._used = used
         self.static_img.zero_()
+        self._install_shadows()
+
+    def _install_shadows(self):
+        """bf16 shadow of every conv / linear weight that runs under autocast (ops._ShadowWeight): refreshed by ONE
+        multi-tensor copy per step instead of one cast kernel per layer, and gradients flow into the flat buffer."""
+        self._shadow_src, self._shadow_dst = [], []
+        if not getattr(self.backbone, "fp16", False):
+            return
+        for m in self.backbone.modules():
+            if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d, torch.nn.Linear)):
+                w = m.weight
+                w._msml_shadow = torch.empty_like(w, dtype=torch.bfloat16)      # preserves strides (channels-last weights)
+                self._shadow_src.append(w.detach())
+                self._shadow_dst.append(w._msml_shadow)
 
     def _step(self, img, label):
         self.flat.zero_()
+        if self._shadow_dst:
+            torch._foreach_copy_(self._shadow_dst, self._shadow_src)
         feat, _seg = self.backbone(img)
         featn = F.normalize(feat)
         x_grad, loss = self.pfc.forward_backward(label, featn, self.opt_pfc)

@@ -370,6 +370,102 @@ def margin_logits(cos, label, kind, s, m, a=0.0, k=0.0):
     return _Margin.apply(cos.float(), label, kind, s, m, a, k)
 
 
+# --------------------------------------------------------------------------------------------
+# Convolution plumbing (cuDNN does the math): bf16 shadow weights + direct weight-gradient accumulation.
+# Under autocast every convolution casts its fp32 weight to bf16 (one kernel), casts the bf16 weight gradient
+# back (another) and AccumulateGrad adds it into .grad (a third).  engine.TrainStep keeps ONE bf16 shadow per
+# weight, refreshed for all weights by a single multi-tensor copy per step; the shadow enters the graph through
+# _ShadowWeight, whose backward adds the bf16 gradient straight into the fp32 flat-gradient view.
+# Without an engine (no ``_msml_shadow`` attribute) these helpers are exactly ``module(x)``.
+# --------------------------------------------------------------------------------------------
+class _ShadowWeight(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w):
+        ctx.param = w
+        return w._msml_shadow.view_as(w._msml_shadow)
+
+    @staticmethod
+    def backward(ctx, g):
+        p = ctx.param
+        if _direct_grad(p):
+            p.grad.add_(g)                      # bf16 -> fp32 accumulate, one kernel
+            return None
+        return g.to(p.dtype)
+
+
+def _weight_of(m):
+    w = m.weight
+    sh = getattr(w, "_msml_shadow", None)
+    # training steps only: the engine refreshes the shadows at the start of each step, so they would be one update
+    # behind for an evaluation pass run between two steps
+    if (sh is not None and m.training and torch.is_grad_enabled() and w.requires_grad and torch.is_autocast_enabled()
+            and torch.get_autocast_dtype("cuda") == sh.dtype):
+        return _ShadowWeight.apply(w)
+    return w
+
+
+def conv2d(x, m):
+    """``m(x)`` for an nn.Conv2d, through the bf16 shadow weight when the engine installed one."""
+    w = _weight_of(m)
+    if w is m.weight:
+        return m(x)
+    return torch.nn.functional.conv2d(x, w, m.bias, m.stride, m.padding, m.dilation, m.groups)
+
+
+def conv_transpose2d(x, m):
+    w = _weight_of(m)
+    if w is m.weight:
+        return m(x)
+    return torch.nn.functional.conv_transpose2d(x, w, m.bias, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
+
+
+def linear(x, m):
+    w = _weight_of(m)
+    if w is m.weight:
+        return m(x)
+    return torch.nn.functional.linear(x, w, m.bias)
+
+
+_ZERO_PAD = {}
+
+
+def cat_channels_padded(parts, multiple=8):
+    """cat(parts, dim=1) with zero channels appended up to a multiple of ``multiple`` (cuDNN's bf16 tensor-core
+    kernels need C % 8 == 0; otherwise it pads the activation itself, in a separate kernel, in forward, dgrad and
+    wgrad).  Returns (tensor, number of padding channels)."""
+    c = sum(t.shape[1] for t in parts)
+    pad = (-c) % multiple
+    if pad and parts[0].is_cuda:
+        B, _, H, W = parts[0].shape
+        key = (B, pad, H, W, parts[0].dtype, parts[0].device)
+        z = _ZERO_PAD.get(key)
+        if z is None:
+            z = torch.zeros((B, pad, H, W), dtype=parts[0].dtype, device=parts[0].device).contiguous(memory_format=torch.channels_last)
+            _ZERO_PAD[key] = z
+        return torch.cat(list(parts) + [z], dim=1), pad
+    return torch.cat(list(parts), dim=1), 0
+
+
+def padded_params(m, pad_in=0, pad_out=0, transposed=False):
+    """(weight, bias) of a conv module with zero input / output channels appended (weight through the bf16 shadow when
+    there is one).  ConvTranspose2d stores its weight as (in, out, kh, kw)."""
+    w = _weight_of(m)
+    if pad_in or pad_out:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad_out, 0, pad_in) if transposed else (0, 0, 0, 0, 0, pad_in, 0, pad_out))
+    b = m.bias
+    if b is not None and pad_out:
+        b = torch.nn.functional.pad(b, (0, pad_out))
+    return w, b
+
+
+def conv2d_padded_in(x, m, pad):
+    """conv2d whose input carries ``pad`` extra zero channels: the weight gets matching zero input channels."""
+    if not pad:
+        return conv2d(x, m)
+    w = torch.nn.functional.pad(_weight_of(m), (0, 0, 0, 0, 0, pad))
+    return torch.nn.functional.conv2d(x, w, m.bias, m.stride, m.padding, m.dilation, m.groups)
+
+
 def launch_count():
     return load().msml_launch_count()
 
