@@ -120,10 +120,10 @@ struct EpiStore : NoScratch {
   float* c;
   int64_t ldc;
   int M, N, block_n;
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*, int half, int nh) const {
     const int row = m_blk * kBlockM + quarter * 32 + lane;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = 0; c0 < block_n; c0 += 32) {
+    for (int c0 = half * (block_n / nh); c0 < (half + 1) * (block_n / nh); c0 += 32) {
       float v[32];
       tmem_ld32(taddr + c0, v);
       const int col0 = n_blk * block_n + c0;
@@ -144,53 +144,56 @@ struct EpiFwdStats : NoScratch {
   float* part_max;   // [n_blocks][B_tot]  (log2 domain: logit * log2e)
   float* part_sum;   // [n_blocks][B_tot]
   float* tgt;        // [B_tot] target logit (natural units), written by the tile that owns the column
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*, int half, int nh) const {
     const int row = m_blk * kBlockM + quarter * 32 + lane;
     const bool row_ok = row < B_tot;
     const int64_t label = row_ok ? tl[row] : -1;
-    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
     const float s2 = mg.s * kLog2e;
-    const int tile_col0 = n_blk * block_n;
-    int n_chunks = (n_s - tile_col0 + 31) / 32;            // warp-uniform
-    if (n_chunks > block_n / 32) n_chunks = block_n / 32;
+    const int cph = block_n / 32 / nh;                     // 32-column chunks per epilogue warp
+    const int tile_col0 = n_blk * block_n + half * cph * 32;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + half * cph * 32;
+    int n_chunks = (n_s - tile_col0 + 31) / 32;            // warp-uniform; <= 0 when this half lies beyond n_s
+    if (n_chunks > cph) n_chunks = cph;
     float run_max = -INFINITY, run_sum = 0.f;
-    float buf[2][32];
-    tmem_ld32_issue(taddr, buf[0]);
-    tmem_ld_wait(buf[0]);
+    if (n_chunks > 0) {
+      float buf[2][32];
+      tmem_ld32_issue(taddr, buf[0]);
+      tmem_ld_wait(buf[0]);
 #pragma unroll 1
-    for (int c = 0; c < n_chunks; c += 2) {
+      for (int c = 0; c < n_chunks; c += 2) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (c + h >= n_chunks) break;
-        float* cur = buf[h];
-        if (c + h + 1 < n_chunks) tmem_ld32_issue(taddr + (c + h + 1) * 32, buf[h ^ 1]);
-        float* v = cur;
-        const int col0 = tile_col0 + (c + h) * 32;
-        const int64_t rel = label - col0;
-        if (rel >= 0 && rel < 32) {                       // at most one row-chunk pair per row
-          const float t = margin_target(mg, pick32(v, (int)rel));
-          put32(v, (int)rel, t);
-          tgt[row] = t * mg.s;
+        for (int h = 0; h < 2; ++h) {
+          if (c + h >= n_chunks) break;
+          float* cur = buf[h];
+          if (c + h + 1 < n_chunks) tmem_ld32_issue(taddr + (c + h + 1) * 32, buf[h ^ 1]);
+          float* v = cur;
+          const int col0 = tile_col0 + (c + h) * 32;
+          const int64_t rel = label - col0;
+          if (rel >= 0 && rel < 32) {                       // at most one row-chunk pair per row
+            const float t = margin_target(mg, pick32(v, (int)rel));
+            put32(v, (int)rel, t);
+            tgt[row] = t * mg.s;
+          }
+          const int valid = n_s - col0;                      // >= 1
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = (j < valid) ? v[j] * s2 : -INFINITY;
+            cmax = fmaxf(cmax, v[j]);
+          }
+          const float new_max = fmaxf(run_max, cmax);        // finite: column col0 < n_s exists
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += fast_exp2(v[j] - new_max);
+          run_sum = run_sum * fast_exp2(run_max - new_max) + acc;
+          run_max = new_max;
+          if (c + h + 1 < n_chunks) tmem_ld_wait(buf[h ^ 1]);
         }
-        const int valid = n_s - col0;                      // >= 1
-        float cmax = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = (j < valid) ? v[j] * s2 : -INFINITY;
-          cmax = fmaxf(cmax, v[j]);
-        }
-        const float new_max = fmaxf(run_max, cmax);        // finite: column col0 < n_s exists
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc += fast_exp2(v[j] - new_max);
-        run_sum = run_sum * fast_exp2(run_max - new_max) + acc;
-        run_max = new_max;
-        if (c + h + 1 < n_chunks) tmem_ld_wait(buf[h ^ 1]);
       }
     }
-    if (row_ok) {
-      part_max[(int64_t)n_blk * B_tot + row] = run_max;
-      part_sum[(int64_t)n_blk * B_tot + row] = run_sum;
+    if (row_ok) {       // one partial per (class tile, half); an empty half contributes (-inf, 0)
+      part_max[(int64_t)(n_blk * nh + half) * B_tot + row] = run_max;
+      part_sum[(int64_t)(n_blk * nh + half) * B_tot + row] = run_sum;
     }
   }
 };
@@ -218,7 +221,7 @@ struct StageOut {
 
 // backward pass 1: recompute logits, emit dcos (bf16, row-major) and rdot[n] = sum_m dcos[m,n] cos[m,n]
 struct EpiBwdDcos {
-  static constexpr int kSmemBytes = 4 * StageOut::kBytesPerWarp;   // 32 KB
+  static constexpr int kSmemBytes = 8 * StageOut::kBytesPerWarp;   // 64 KB (up to 8 epilogue warps)
   CUtensorMap map_dcos;        // bf16 (B_tot x n_s), boxes 64 cols x 32 rows
   const int64_t* tl;
   Margin mg;
@@ -228,21 +231,23 @@ struct EpiBwdDcos {
   float* rdot;         // [n_s] zero-initialised; <Wn[n], dWn[n]> for the normalise backward
   float smooth_on, smooth_off, inv_btot;
   __device__ void finish(int, int lane) const { StageOut::drain(lane); }
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int half, int nh) const {
     const int row0 = m_blk * kBlockM + quarter * 32;
     const int row = row0 + lane;
     const bool row_ok = row < B_tot;
     const int64_t label = row_ok ? tl[row] : -1;
-    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* wscr = scratch + quarter * StageOut::kBytesPerWarp;
+    const int cph = block_n / 32 / nh;                     // 32-column chunks per epilogue warp (even)
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + half * cph * 32;
+    uint8_t* wscr = scratch + (half * 4 + quarter) * StageOut::kBytesPerWarp;
     const float s2 = mg.s * kLog2e;
     // p = exp2(logit*log2e - off),  off = max*log2e + log2(sum)
     const float off = row_ok ? fmaf(gmax[row], kLog2e, log2f(gsum[row])) : INFINITY;   // dead rows: p = 0
     const float t_off = label >= 0 ? smooth_off : 0.f;   // rows without a local target: no one-hot row (ref :166)
     const float gs = row_ok ? mg.s * inv_btot : 0.f;
-    const int tile_col0 = n_blk * block_n;
+    const int tile_col0 = n_blk * block_n + half * cph * 32;
     int n_chunks = (n_s - tile_col0 + 31) / 32;
-    if (n_chunks > block_n / 32) n_chunks = block_n / 32;
+    if (n_chunks > cph) n_chunks = cph;
+    if (n_chunks <= 0) return;
     float buf[2][32];
     uint4 packed[8];
     tmem_ld32_issue(taddr, buf[0]);
@@ -307,10 +312,10 @@ struct EpiBwdDcos {
 struct EpiDxAccum : NoScratch {
   float* dx;   // (B_tot, D) fp32, zero-initialised
   int B_tot, D, block_n;
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t*, int half, int nh) const {
     const int row = m_blk * kBlockM + quarter * 32 + lane;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = 0; c0 < block_n; c0 += 32) {
+    for (int c0 = half * (block_n / nh); c0 < (half + 1) * (block_n / nh); c0 += 32) {
       float v[32];
       tmem_ld32(taddr + c0, v);
       const int col0 = n_blk * block_n + c0;
@@ -352,9 +357,9 @@ struct EpiDwNormBwd {
     }
     cp_async_commit();
   }
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int, int) const {
     const int row0 = m_blk * kBlockM + quarter * 32;
-    const int row = row0 + lane;                     // class index
+    const int row = row0 + lane;                     // class index (4 epilogue warps: each owns all 256 columns)
     const int dcol0 = n_blk * 256;                   // this tile covers D columns [dcol0, dcol0 + 256)
     const bool ok = row < n_s;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
@@ -524,13 +529,13 @@ struct HeadWs {
   int n_blocks;
   size_t bytes;
 };
-constexpr int kFwdBlockN = 128;   // granularity of the per-tile softmax partials (smallest class tile)
+constexpr int kFwdBlockN = 128;   // smallest class tile; each tile yields two softmax partials (one per epilogue half)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static HeadWs carve(void* ws, int64_t B_tot, int64_t n_s) {
   HeadWs h;
-  h.n_blocks = (int)((n_s + kFwdBlockN - 1) / kFwdBlockN);
+  h.n_blocks = 2 * (int)((n_s + kFwdBlockN - 1) / kFwdBlockN);
   h.ld_dc = (n_s + 7) / 8 * 8;
   size_t off = 0;
   char* base = static_cast<char*>(ws);
@@ -673,11 +678,11 @@ extern "C" int msml_head_fwd(const void* x, const void* wn, const int64_t* tl, i
   epi.part_max = h.part_max; epi.part_sum = h.part_sum; epi.tgt = h.tgt;
   const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D;      // stream Wn + X once (bf16)
   if (bn == 256) {
-    if (int e = launch_gemm<256, 2, 4, false, false>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
+    if (int e = launch_gemm<256, 2, 4, false, false, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
   } else {
-    if (int e = launch_gemm<128, 4, 6, false, false>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
+    if (int e = launch_gemm<128, 4, 6, false, false, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
   }
-  const int n_blocks = (int)((n_s + bn - 1) / bn);
+  const int n_blocks = (int)((n_s + bn - 1) / bn) * 2;      // two epilogue halves per class tile
   head_local_stats_kernel<<<(unsigned)((B_tot + 127) / 128), 128, 0, st>>>(h.part_max, h.part_sum, h.tgt, tl, n_blocks, (int)B_tot, stats);
   MSML_LAUNCH_CHECK();
   return 0;
@@ -716,9 +721,9 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
     epi.smooth_on = 1.0f - eps; epi.smooth_off = eps / (float)(n_s - 1); epi.inv_btot = 1.0f / (float)B_tot;
     const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D + 2.0 * (double)B_tot * n_s;   // + dcos out
     if (bn == 256) {
-      if (int e = launch_gemm<256, 2, 3, false, false>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
+      if (int e = launch_gemm<256, 2, 3, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
     } else {
-      if (int e = launch_gemm<128, 4, 5, false, false>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
+      if (int e = launch_gemm<128, 4, 4, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
     }
   }
   // 2. dX_full = dcos (B_tot x n_s) * Wn (n_s x D): A = dcos (K-major), B = Wn read in place (MN-major), split-K
@@ -728,11 +733,14 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
     if (int e = encode_tmap_bf16_kmajor(&ma, h.dcos, B_tot, n_s, h.ld_dc, kBlockM)) return e;
     if (int e = encode_tmap_bf16_mnmajor(&mb, wn, D, n_s, D)) return e;
     const int tiles = (int)((B_tot + kBlockM - 1) / kBlockM) * (int)((D + 255) / 256);
-    int splits = (num_sms() + tiles - 1) / tiles;
+    // as many split-K units as fit in ONE wave of the persistent grid (rounding up would leave a second, almost
+    // empty wave: 16 tiles x 10 splits = 160 units on 148 SMs ran at 54 % occupancy)
+    int splits = num_sms() / tiles;
+    if (splits < 1) splits = 1;
     EpiDxAccum epi;
     epi.dx = dx_full; epi.B_tot = (int)B_tot; epi.D = (int)D; epi.block_n = 256;
     const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 4.0 * (double)B_tot * D;
-    if (int e = launch_gemm<256, 2, 4, false, true>("head_bwd_dx_gemm", ma, mb, make_shape(B_tot, D, n_s, 256, splits), epi, st, min_bytes)) return e;
+    if (int e = launch_gemm<256, 2, 4, false, true, 8>("head_bwd_dx_gemm", ma, mb, make_shape(B_tot, D, n_s, 256, splits), epi, st, min_bytes)) return e;
   }
   // 3. dW = normalize_bwd(dcos^T X): A = dcos read in place (MN-major over classes), B = X in place (MN-major), K = B_tot
   {
@@ -743,7 +751,7 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
     if (int e = encode_tmap_2d(&epi.map_dw, dw, 4, D, n_s, D, 32, 32)) return e;
     epi.wn = static_cast<const __nv_bfloat16*>(wn); epi.inv_norm = inv_norm; epi.rdot = h.rdot; epi.n_s = (int)n_s; epi.D = (int)D;
     const double min_bytes = 4.0 * (double)n_s * D + 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 2.0 * (double)B_tot * D;
-    if (int e = launch_gemm<256, 2, 3, true, true>("head_bwd_dw_gemm", ma, mb, make_shape(n_s, D, B_tot, 256), epi, st, min_bytes)) return e;
+    if (int e = launch_gemm<256, 2, 3, true, true>("head_bwd_dw_gemm", ma, mb, make_shape(n_s, D, B_tot, 256, 1, /*n_fastest=*/true), epi, st, min_bytes)) return e;
   }
   return 0;
 }

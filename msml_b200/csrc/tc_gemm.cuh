@@ -2,11 +2,13 @@
 //
 //   D[m, n] = sum_k A[m, k] * B[n, k]       A (M x K) and B (N x K) bf16, both K-major ("TN")
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 64 + 32*EW threads, warp-specialised:
 //   warp 0  lane 0 : TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem ring (STAGES deep)
 //   warp 1  lane 0 : MMA issuer     tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM
-//   warps 2..5     : epilogue       tcgen05.ld (32x32b): one thread = one accumulator ROW, so row
-//                                   reductions (max / sum-exp / dot) need no shuffles
+//   warps 2..1+EW  : epilogue       tcgen05.ld (32x32b): one thread = one accumulator ROW, so row
+//                                   reductions (max / sum-exp / dot) need no shuffles.  EW = 4, or 8 when the
+//                                   epilogue (exp2 / pack / stores per element) is heavier than the tile's MMAs:
+//                                   the two warps of a TMEM lane quarter then split the tile's columns
 // Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue; ACC_STAGES
 // accumulators of BLOCK_N fp32 columns each so the epilogue of tile i overlaps the MMAs of tile
 // i+1), and the static persistent tile loop (m fastest so that concurrently running CTAs share
@@ -34,7 +36,6 @@ namespace tc {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
 constexpr uint32_t kSpinLimit = 1u << 26;  // bounded waits: trap instead of hanging the GPU
@@ -201,6 +202,7 @@ struct GemmShape {
   int m_blocks, n_blocks;
   int k_splits;          // split-K work units
   int k_blocks_per_split;
+  int n_fastest;         // unit order: 0 = m fastest (CTAs running together share the B tile in L2), 1 = n fastest (share A)
 };
 
 template <int BLOCK_N, int STAGES, int EPI_BYTES>
@@ -219,14 +221,15 @@ struct SmemLayout {
 //   struct Epi {
 //     static constexpr int kSmemBytes;     // per-CTA scratch (multiple of 1024), split by the callee per warp
 //     __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int k_split,
-//                                int quarter, int lane, uint8_t* scratch) const;
+//                                int quarter, int lane, uint8_t* scratch, int half, int n_halves) const;
 //     __device__ void finish(int quarter, int lane) const;   // once per warp after the last tile
 //   };
 // tmem_acc already carries the accumulator-stage column offset; the callee adds
-// ((quarter*32) << 16) + column.  Called by all 128 epilogue threads (warp-convergent).
+// ((quarter*32) << 16) + column.  Called by all epilogue threads (warp-convergent); with 8 epilogue warps
+// (n_halves == 2) warp `half` of a quarter owns columns [half, half+1) * BLOCK_N / 2 of the tile.
 
-template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, class Epi, int EW = 4>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const GemmShape shape, const __grid_constant__ Epi epi) {
   static_assert(BLOCK_N == 128 || BLOCK_N == 256 || BLOCK_N == 512, "BLOCK_N in {128,256,512}");
@@ -251,7 +254,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
@@ -266,8 +269,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        const int m_blk = u % shape.m_blocks;
-        const int n_blk = (u / shape.m_blocks) % shape.n_blocks;
+        const int mn = u % (shape.m_blocks * shape.n_blocks);
+        const int m_blk = shape.n_fastest ? mn / shape.n_blocks : mn % shape.m_blocks;
+        const int n_blk = shape.n_fastest ? mn % shape.n_blocks : mn / shape.m_blocks;
         const int ks = u / (shape.m_blocks * shape.n_blocks);
         const int kb0 = ks * shape.k_blocks_per_split;
         int kb1 = kb0 + shape.k_blocks_per_split;
@@ -337,15 +341,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   } else {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-      const int m_blk = u % shape.m_blocks;
-      const int n_blk = (u / shape.m_blocks) % shape.n_blocks;
+      const int mn = u % (shape.m_blocks * shape.n_blocks);
+      const int m_blk = shape.n_fastest ? mn / shape.n_blocks : mn % shape.m_blocks;
+      const int n_blk = shape.n_fastest ? mn % shape.n_blocks : mn / shape.m_blocks;
       const int ks = u / (shape.m_blocks * shape.n_blocks);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane, smem + L::kEpiOffset);
+      epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane, smem + L::kEpiOffset, half, EW / 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -375,11 +381,11 @@ inline int encode_tmap_bf16_mnmajor(CUtensorMap* out, const void* base, int64_t 
   return encode_tmap_2d(out, base, 2, mn, k, ld_elems, 64, kBlockK);
 }
 
-template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, class Epi>
+template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, int EW = 4, class Epi>
 int launch_gemm(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& shape, const Epi& epi,
                 cudaStream_t st, double min_bytes = 0.0) {
   using L = SmemLayout<BLOCK_N, STAGES, Epi::kSmemBytes>;
-  auto kern = gemm_kernel<BLOCK_N, ACC_STAGES, STAGES, A_MN, B_MN, Epi>;
+  auto kern = gemm_kernel<BLOCK_N, ACC_STAGES, STAGES, A_MN, B_MN, Epi, EW>;
   static thread_local bool configured = false;   // per template instantiation
   if (!configured) {
     MSML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -390,14 +396,15 @@ int launch_gemm(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, 
   if (units < grid) grid = units;
   if (grid < 1) grid = 1;
   MSML_PROF2(name, 2.0 * shape.M * shape.N * shape.K, min_bytes, st);
-  kern<<<grid, kThreads, L::kTotal, st>>>(ma, mb, shape, epi);
+  kern<<<grid, 64 + 32 * EW, L::kTotal, st>>>(ma, mb, shape, epi);
   MSML_LAUNCH_CHECK();
   return 0;
 }
 
-inline GemmShape make_shape(int64_t M, int64_t N, int64_t K, int block_n, int k_splits = 1) {
+inline GemmShape make_shape(int64_t M, int64_t N, int64_t K, int block_n, int k_splits = 1, bool n_fastest = false) {
   GemmShape s;
   s.M = (int)M; s.N = (int)N; s.K = (int)K;
+  s.n_fastest = n_fastest ? 1 : 0;
   s.m_blocks = (int)((M + kBlockM - 1) / kBlockM);
   s.n_blocks = (int)((N + block_n - 1) / block_n);
   const int total_kb = (int)((K + kBlockK - 1) / kBlockK);
