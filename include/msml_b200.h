@@ -106,6 +106,15 @@ int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gam
                 int accumulate_param_grads, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Gradient plumbing of the training step (no reference counterpart: replaces one ATen mixed-dtype add per weight,
+ * i.e. torch's AccumulateGrad after the bf16 -> fp32 cast of ref train.py:283-300 under autocast).
+ * dst[i] (fp32, n[i] elements) += src[i] (bf16, same element order), all segments in one launch per
+ * MSML_ACCUM_MAX_SEGMENTS segments.  Pointers may be unaligned (scalar path), 16-byte alignment is fastest.
+ * ------------------------------------------------------------------------------------------ */
+#define MSML_ACCUM_MAX_SEGMENTS 96
+int msml_accum_bf16_multi(int nseg, float* const* dst, const void* const* src, const int64_t* n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K-B  DAP head of the segmentation branch + argmax mask.
  *   ref backbones/osb/unet.py:158-161,223 (PixelShuffle(k)+AvgPool2d(k) == mean over k*k channel
  *   groups), train.py:357 / eval/qeval_mxnet.py:347 (final_seg[b].max(0)[1]).

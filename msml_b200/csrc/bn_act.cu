@@ -562,7 +562,7 @@ static int bn_geom(int64_t P, int64_t C, int dtype, BnGeom* g) {
 }
 
 // Every CTA must be co-resident (grid barrier), so the grid is capped by the occupancy of the
-// instantiation; slabs of >= 2 passes per CTA.
+// instantiation; slabs of >= 4 passes per CTA.
 template <typename K>
 static int coop_grid(K kernel, const BnGeom& g, int* out) {
   static thread_local std::map<const void*, int> cache;     // max co-resident CTAs per kernel instantiation
@@ -581,7 +581,10 @@ static int coop_grid(K kernel, const BnGeom& g, int* out) {
   if (cap > kBnMaxCtas) cap = kBnMaxCtas;
   static const int env_cap = getenv("MSML_BN_MAX_CTAS") ? atoi(getenv("MSML_BN_MAX_CTAS")) : 0;   // debug
   if (env_cap > 0 && cap > env_cap) cap = env_cap;
-  int64_t want = (g.P + (int64_t)g.rows_per_pass * 2 - 1) / ((int64_t)g.rows_per_pass * 2);
+  static const int env_passes = getenv("MSML_BN_PASSES") ? atoi(getenv("MSML_BN_PASSES")) : 0;   // debug
+  const int passes = env_passes > 0 ? env_passes : 4;      // measured: 2..8 passes per CTA are equivalent, 16+ lose (each pass is a
+                                                           // ~1.5 us memory round trip, so fewer / fatter CTAs serialise latency)
+  int64_t want = (g.P + (int64_t)g.rows_per_pass * passes - 1) / ((int64_t)g.rows_per_pass * passes);
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   *out = (int)want;

@@ -20,6 +20,8 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from . import ops
+
 
 class TrainStep:
     def __init__(self, backbone, pfc, opt_backbone, opt_pfc, batch_shape, world_size=1, max_norm=5.0,
@@ -83,6 +85,7 @@ class TrainStep:
         featn = F.normalize(feat)
         x_grad, loss = self.pfc.forward_backward(label, featn, self.opt_pfc)
         featn.backward(x_grad)                      # accumulates into the views of self.flat
+        ops.flush_weight_grads()                    # the queued bf16 weight gradients, one multi-tensor launch
         if self.world_size > 1:
             dist.all_reduce(self.flat)              # one NCCL all-reduce over NVLink for every gradient
             self.flat.div_(self.world_size)

@@ -388,9 +388,43 @@ class _ShadowWeight(torch.autograd.Function):
     def backward(ctx, g):
         p = ctx.param
         if _direct_grad(p):
-            p.grad.add_(g)                      # bf16 -> fp32 accumulate, one kernel
+            if g.dtype == torch.bfloat16 and g.stride() == p.grad.stride() and _is_dense(g):
+                _PENDING_WGRADS.append((p.grad, g))     # added by ONE multi-tensor kernel in flush_weight_grads()
+            else:
+                p.grad.add_(g)                          # e.g. the slice of a zero-padded weight's gradient
             return None
         return g.to(p.dtype)
+
+
+_PENDING_WGRADS = []
+
+
+def _is_dense(t):
+    """True when t's elements occupy one gap-free block of memory (any permutation of dims)."""
+    expect = 1
+    for size, stride in sorted(zip(t.shape, t.stride()), key=lambda q: q[1]):
+        if size == 1:
+            continue
+        if stride != expect:
+            return False
+        expect *= size
+    return True
+
+
+def flush_weight_grads():
+    """Add every bf16 weight gradient queued by _ShadowWeight.backward into its fp32 flat-gradient view: one launch
+    (msml_accum_bf16_multi) for all of them.  engine.TrainStep calls this right after the backward pass."""
+    if not _PENDING_WGRADS:
+        return
+    lib = load()
+    n = len(_PENDING_WGRADS)
+    dst = (ctypes.c_void_p * n)(*[d.data_ptr() for d, _ in _PENDING_WGRADS])
+    src = (ctypes.c_void_p * n)(*[g.data_ptr() for _, g in _PENDING_WGRADS])
+    cnt = (ctypes.c_int64 * n)(*[g.numel() for _, g in _PENDING_WGRADS])
+    try:
+        check(lib.msml_accum_bf16_multi(n, dst, src, cnt, stream_ptr()))
+    finally:
+        _PENDING_WGRADS.clear()
 
 
 def _weight_of(m):
