@@ -52,6 +52,8 @@ class _DAP(nn.Module):
 
 
 class Unet(nn.Module):
+    pad_channels = True      # 16-bit CUDA path: run the decoder on channel counts padded to multiples of 8
+
     def __init__(self, block, layers, groups=1, num_classes=2, kernel_size=7, dap_k=3, gray=True, input_size=128):
         super().__init__()
         del block, groups
@@ -110,7 +112,7 @@ class Unet(nn.Module):
         x2 = self.layer2(x1)
         x3 = self.layer3(x2)
         x4 = ops.bn_act(self.layer4(x3), self.bn2)
-        if x4.is_cuda and x4.dtype != torch.float32:
+        if self.pad_channels and x4.is_cuda and x4.dtype != torch.float32:
             seg0, seg1, seg2, seg3, seg5_ = self._decode_padded(x4, x3, x2, x1, x0)
             return [seg0.detach(), seg1.detach(), seg2.detach(), seg3.detach()], seg5_
         seg0 = ops.conv_transpose2d(self.gcm1(x4), self.deconv1)

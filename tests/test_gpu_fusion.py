@@ -231,3 +231,51 @@ def test_bn_act_full_size_statistics():
     y = ops.bn_act(x, m.bn).float()
     assert y.mean((0, 2, 3)).abs().max().item() < 5e-3
     assert (y.var((0, 2, 3), unbiased=False) - 1).abs().max().item() < 1e-2
+
+
+def test_accum_bf16_multi_matches_torch():
+    """dst_f32 += src_bf16 over many ragged / unaligned segments in one launch (csrc/optim.cu)."""
+    need_gpu()
+    import ctypes
+    from msml_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sizes = [1, 7, 8, 9, 4096, 8191, 8192, 8193, 100003, 3 * 3 * 64 * 64] + [257 + 13 * i for i in range(110)]   # > one table
+    big_d = torch.randn(sum(sizes) + 8 * len(sizes) + 8, device="cuda", generator=g)
+    big_s = torch.randn(sum(sizes) + 8 * len(sizes) + 8, device="cuda", generator=g).to(torch.bfloat16)
+    want = big_d.clone()
+    dst, src, off = [], [], 0
+    for i, n in enumerate(sizes):
+        o = off + (i % 3)                      # some segments start off a 16-byte boundary
+        dst.append(big_d[o:o + n]); src.append(big_s[o + 1:o + 1 + n] if i % 5 == 0 else big_s[o:o + n])
+        want[o:o + n] += src[-1].float()
+        off = o + n + 5
+    k = len(sizes)
+    d = (ctypes.c_void_p * k)(*[t.data_ptr() for t in dst]); s = (ctypes.c_void_p * k)(*[t.data_ptr() for t in src])
+    n = (ctypes.c_int64 * k)(*sizes)
+    _lib.check(lib.msml_accum_bf16_multi(k, d, s, n, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(big_d, want)
+
+
+def test_padded_channel_paths_match_unpadded(monkeypatch):
+    """Zero-padded channel counts (FM concat, image stems, U-Net decoder) must not change the bf16 forward beyond
+    rounding: same model with the padding helpers disabled."""
+    need_gpu()
+    from msml_b200 import ops
+    from msml_b200.backbones import MSML
+    import importlib
+    unet_mod = importlib.import_module("msml_b200.backbones.osb.unet")
+    from oracle.detfill import det_tensor, fill_state_dict_
+    net = MSML("iresnet18", "unet", (1, 1, 1, 1), 97, fp16=True, header_type=None, fm_params=(3, 2, "sigmoid", "mul"))
+    fill_state_dict_(net)
+    net = net.cuda().eval()
+    x = det_tensor("model.x", (2, 3, 112, 112)).cuda()
+    with torch.no_grad():
+        f1, s1 = net(x)
+        monkeypatch.setattr(ops, "cat_channels_padded", lambda parts, multiple=8: (torch.cat(list(parts), 1), 0))
+        monkeypatch.setattr(unet_mod.Unet, "pad_channels", False)
+        f2, s2 = net(x)
+    cos = torch.nn.functional.cosine_similarity(f1.double(), f2.double())
+    assert (cos > 0.999).all(), cos
+    assert_close(host(s1), host(s2), 3e-2, atol_frac=3e-2, what="seg padded vs unpadded")
