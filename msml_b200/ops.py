@@ -205,7 +205,7 @@ class _BNAct(torch.autograd.Function):
 def _direct_grad(p):
     """True when the engine has marked ``p`` as living in its flat gradient buffer (see engine.TrainStep)."""
     return (getattr(p, "_msml_direct_grad", False) and p.grad is not None and p.grad.dtype == torch.float32
-            and p.grad.is_contiguous() and p.grad.data_ptr() % 16 == 0)
+            and _is_dense(p.grad) and p.grad.data_ptr() % 16 == 0)
 
 
 def bn_act(x, bn, prelu=None, res=None):

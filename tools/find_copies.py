@@ -25,5 +25,5 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     torch.cuda.synchronize()
 rows = [e for e in prof.key_averages(group_by_input_shape=True) if e.self_device_time_total > 0 and e.key.startswith("aten::")]
 rows.sort(key=lambda e: -e.self_device_time_total)
-for e in rows[:45]:
+for e in rows[:70]:
     print("%8.1f us %4d  %-28s %s" % (e.self_device_time_total, e.count, e.key, str(e.input_shapes)[:150]))
