@@ -148,7 +148,21 @@ def collect_profile(lib):
     return out
 
 
-def roofline_entry(name, rec, pk, sustained=True):
+_TRAFFIC = None
+
+
+def ncu_traffic(name, suffix=""):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this kernel
+    (profiles/r01b_traffic.json), or None if that kernel was not captured."""
+    global _TRAFFIC
+    if _TRAFFIC is None:
+        path = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+        _TRAFFIC = json.load(open(path)) if os.path.exists(path) else {}
+    rec = _TRAFFIC.get(name + suffix)
+    return rec["dram_bytes_per_launch"] if rec else None
+
+
+def roofline_entry(name, rec, pk, sustained=True, traffic_suffix=""):
     avg_s = rec["total_ms"] / rec["launches"] * 1e-3
     per_launch = rec["work"] / rec["launches"]
     if name.endswith("_gemm"):
@@ -159,15 +173,15 @@ def roofline_entry(name, rec, pk, sustained=True):
         if t_hbm > t_tensor:   # short-M contraction: the class-centre stream binds, not the tensor pipe
             gbs = bytes_pl / avg_s / 1e9
             return dict(kernel=name, bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
-                        traffic=None, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=bytes_pl,
+                        traffic=ncu_traffic(name, traffic_suffix), launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=bytes_pl,
                         tflops=round(ach, 2), note="HBM-bound at this M: min bytes = operands + outputs streamed once",
                         peak_source=pk["source"])
         return dict(kernel=name, bound="tensor", achieved=round(ach, 2), peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4),
-                    traffic=None, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
+                    traffic=ncu_traffic(name, traffic_suffix), launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
                     peak_source=pk["source"] + (", sustained" if sustained else ", burst"))
     ach = per_launch / avg_s / 1e9
     return dict(kernel=name, bound="hbm", achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4),
-                traffic=None, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
+                traffic=ncu_traffic(name, traffic_suffix), launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
                 peak_source=pk["source"])
 
 
@@ -196,7 +210,45 @@ def fusion_microbench(iters=20, batch=512):
     elems = FEAT_ELEMS_PER_IMG * batch
     return dict(batch=batch, fwd_ms=round(fwd, 4), bwd_ms=round(bwd, 4), fwd_gbs=round(3 * elems * 2 / fwd / 1e6, 1),
                 bwd_gbs=round(5 * elems * 2 / bwd / 1e6, 1), fwd_bwd_gbs=round(8 * elems * 2 / (fwd + bwd) / 1e6, 1),
-                algorithmic_bytes=8 * elems * 2)
+                algorithmic_bytes=8 * elems * 2,
+                ncu_dram_bytes={"fwd": ncu_traffic("fm_gate_fwd", "@config2"), "bwd": ncu_traffic("fm_gate_bwd", "@config2")}
+                if batch == 512 else None)
+
+
+def head_microbench(iters=5, b_tot=1024, n_s=125000):
+    """BASELINE config 4 per-rank shapes on ONE GPU: the 8-GPU run gathers B_tot = 8 x 128 = 1024 embeddings against a
+    125,000-class shard per rank (1M classes / 8); the head kernels see exactly these GEMM shapes, only the collectives
+    are absent.  Every launch is bracketed by CUDA events (msml_profile_*); tensor-bound kernels are quoted against the
+    measured cuBLAS bf16 burst peak."""
+    import torch
+    from msml_b200 import _lib
+    from msml_b200.headers import ArcFace, PartialFC
+    lib = _lib.load()
+    pk = peaks()
+    torch.manual_seed(1)
+    pfc = PartialFC(0, torch.cuda.current_device(), 1, b_tot, False, ArcFace(S, M), n_s, sample_rate=1.0, embedding_size=512)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    feat = torch.nn.functional.normalize(torch.randn(b_tot, 512, device="cuda", generator=g))
+    label = torch.randint(0, n_s, (b_tot,), device="cuda", generator=g)
+    for _ in range(3):
+        pfc.forward_backward(label, feat, None)
+        pfc.sub_weight.grad = None
+    torch.cuda.synchronize()
+    lib.msml_profile_enable(1)
+    for _ in range(iters):
+        pfc.forward_backward(label, feat, None)
+        pfc.sub_weight.grad = None
+    torch.cuda.synchronize()
+    lib.msml_profile_enable(0)
+    prof = collect_profile(lib)
+    rl = sorted((roofline_entry(k, v, pk, sustained=False, traffic_suffix="@config4") for k, v in prof.items()),
+                key=lambda r: -r["avg_us"] * r["launches"])
+    gemm_ms = sum(v["total_ms"] for k, v in prof.items() if k.endswith("_gemm")) / iters
+    del pfc
+    torch.cuda.empty_cache()
+    return dict(b_tot=b_tot, n_s=n_s, algorithmic_flops=6.0 * b_tot * n_s * 512,
+                tflops_over_gemm_time=round(6.0 * b_tot * n_s * 512 / (gemm_ms * 1e-3) / 1e12, 1),
+                frac_of_bf16_burst_peak=round(6.0 * b_tot * n_s * 512 / (gemm_ms * 1e-3) / 1e12 / pk["tf_burst"], 4), rooflines=rl)
 
 
 def run_train(args, rank, local_rank, world):
@@ -435,6 +487,7 @@ def main():
     res = run_head(args, rank, local_rank, world) if args.workload == "head" else run_train(args, rank, local_rank, world)
     if rank == 0 and args.workload == "train":
         res["fusion_microbench"] = fusion_microbench()
+        res["head_microbench"] = head_microbench()
         if world == 1 and not args.no_cpu_baseline:
             cb = run_cpu(args.cpu_batch, 6, 1)
             res["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
