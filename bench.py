@@ -416,6 +416,41 @@ def run_head(args, rank, local_rank, world):
             "rooflines": rl, "roofline": rl[0] if rl else None}
 
 
+def run_infer(args, rank, local_rank, world):
+    """BASELINE config 5: test.py-style occluded-face verification embedding extraction (LFW shape), ires50_msml, batch
+    1024, one B200.  A step = one batch of 1024 uint8 images: H2D, normalise, f(x) + f(flip x), L2-normalise, D2H."""
+    import numpy as np
+    import torch
+    from msml_b200.backbones import MSML
+    from msml_b200.eval import extract_embeddings, random_block_occlusion
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(1)
+    net = MSML("iresnet50", "unet", (1, 1, 1, 1), NUM_CLASSES, fp16=True, header_type=None, fm_params=FM_PARAMS).to(dev)
+    net = net.to(memory_format=torch.channels_last).eval()
+    bs = 1024
+    n = bs * max(1, min(args.steps, 12))                    # LFW: 12,000 images
+    g = torch.Generator(device=dev).manual_seed(1)
+    imgs = torch.randint(0, 256, (n, 3, 112, 112), dtype=torch.uint8, device=dev, generator=g)
+    imgs = random_block_occlusion(imgs, 40, 41, generator=g).cpu().pin_memory()     # RandomBlock(40, 41, 'black')
+    for _ in range(max(args.warmup, 3)):
+        extract_embeddings([imgs[:bs]], net, bs)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    emb, _ = extract_embeddings([imgs], net, bs)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    assert np.isfinite(emb).all() and abs(np.linalg.norm(emb[0]) - 1.0) < 1e-6
+    return {"metric": "occluded verification embedding extraction imgs/s (BASELINE config 5)", "value": round(n / (ms * 1e-3), 1),
+            "unit": "imgs/s", "n_gpus": 1, "steps": n // bs, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / (n // bs), 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "ires50_msml eval, %d uint8 112x112 images with a 40x40 black block, batch 1024, f(x)+f(flip x), "
+                                   "host-fed (pinned uint8) and embeddings read back: end to end" % n}}
+
+
 def main():
     # the contract is ONE JSON line on stdout: native libraries (NCCL's version banner, cuDNN warnings) print to fd 1,
     # so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor
@@ -433,7 +468,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "fusion", "head"])
+    ap.add_argument("--workload", default="train", choices=["train", "fusion", "head", "infer"])
     ap.add_argument("--classes", type=int, default=1_000_000)
     ap.add_argument("--sample-rate", type=float, default=1.0)
     ap.add_argument("--batch", type=int, default=BATCH, help="head workload only: per-rank batch (1024 on one GPU reproduces the "
@@ -484,6 +519,10 @@ def main():
                                            "frac": round(fm["fwd_bwd_gbs"] / pk["hbm"], 4), "traffic": None}, "detail": fm}))
         return 0
 
+    if args.workload == "infer":
+        if rank == 0:
+            emit(run_infer(args, rank, local_rank, world))
+        return 0
     res = run_head(args, rank, local_rank, world) if args.workload == "head" else run_train(args, rank, local_rank, world)
     if rank == 0 and args.workload == "train":
         res["fusion_microbench"] = fusion_microbench()
