@@ -323,8 +323,7 @@ def run_train(args, rank, local_rank, world):
     prof_steps = 3
     eager = step if args.eager else TrainStep(net, pfc, opt, opt_pfc, (BATCH, 3, 112, 112), world_size=world, max_norm=5.0, use_graph=False)
     if not args.eager:
-        eager.flat, eager._used = step.flat, step._used
-        eager._shadow_src, eager._shadow_dst = step._shadow_src, step._shadow_dst
+        eager.share_state_from(step)
     eager(imgs[0], labels[0])
     fence()
     ops.launch_count_reset()

@@ -72,6 +72,7 @@ class IResNet(nn.Module):
         x = ops.bn_act(ops.conv2d_padded_in(x, self.conv1, x.shape[1] - self.conv1.in_channels), self.bn1, self.prelu)
         kd_terms = []
         for i, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
+            x = ops.grad_marker(x, i)       # backward: everything from stage i on has its parameter gradients complete
             x = layer(x)
             x, l = self.fm_ops[i](x, segs[i], ft[i])
             kd_terms.append(l)

@@ -52,6 +52,7 @@ class TrainStep:
         feat.sum().backward()
         self.backbone.load_state_dict(bn_state, strict=False)      # the probe must not touch the BN statistics
         used = [p for p in self.backbone.parameters() if p.grad is not None]
+        used, self._buckets = self._order_for_overlap(used)
         pad4 = lambda k: (k + 3) // 4 * 4     # every gradient starts on a 16-byte boundary (vector accesses in the kernels)
         n = sum(pad4(p.numel()) for p in used)
         self.flat = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -61,8 +62,54 @@ class TrainStep:
             p._msml_direct_grad = True          # fused kernels may add their parameter gradients into p.grad themselves
             off += pad4(p.numel())
         self._used = used
+        # element ranges of the flat buffer per bucket (bucket i is complete when the backward pass crosses marker i)
+        self._bucket_ranges, lo = {}, 0
+        for tag, cnt in self._buckets:
+            hi = lo + sum(pad4(p.numel()) for p in used[self._bucket_start[tag]:self._bucket_start[tag] + cnt])
+            self._bucket_ranges[tag] = (lo, hi)
+            lo = hi
         self.static_img.zero_()
         self._install_shadows()
+
+    def _order_for_overlap(self, used):
+        """Order the parameters so that the ones whose gradients finish first in the backward pass come first in the
+        flat buffer: [stage 3 (layer4, fm_ops.3, bn2, fc, features) | stage 2 | stage 1 | stage 0 | rest (stem, OSB)].
+        Returns (ordered list, [(tag, count)])."""
+        names = {id(p): n for n, p in self.backbone.named_parameters()}
+
+        def stage_of(name):
+            for i in (3, 2, 1, 0):
+                if name.startswith("frb.layer%d." % (i + 1)) or name.startswith("frb.fm_ops.%d." % i):
+                    return i
+            if name.startswith(("frb.bn2.", "frb.fc.", "frb.features.")):
+                return 3
+            return -1                                   # stem and anything outside the FRB stages: reduced last
+        groups = {3: [], 2: [], 1: [], 0: [], -1: []}
+        for p in used:
+            groups[stage_of(names.get(id(p), ""))].append(p)
+        ordered, buckets, self._bucket_start = [], [], {}
+        for tag in (3, 2, 1, 0, -1):
+            self._bucket_start[tag] = len(ordered)
+            buckets.append((tag, len(groups[tag])))
+            ordered += groups[tag]
+        return ordered, buckets
+
+    def _on_marker(self, tag):
+        """Backward crossed marker `tag`: the gradients of bucket `tag` are complete (after the queued bf16 weight
+        gradients are flushed) -> start its all-reduce; NCCL's stream runs it under the rest of the backward pass."""
+        if self.world_size <= 1 or tag in self._reduced:
+            return
+        ops.flush_weight_grads()
+        lo, hi = self._bucket_ranges[tag]
+        if hi > lo:
+            self._works.append(dist.all_reduce(self.flat[lo:hi], async_op=True))
+        self._reduced.add(tag)
+
+    def share_state_from(self, other):
+        """Make this TrainStep operate on `other`'s flat gradient buffer, buckets and shadow weights (bench.py runs an
+        eager twin of the captured step to time individual launches)."""
+        for k in ("flat", "_used", "_buckets", "_bucket_ranges", "_bucket_start", "_shadow_src", "_shadow_dst"):
+            setattr(self, k, getattr(other, k))
 
     def _install_shadows(self):
         """bf16 shadow of every conv / linear weight that runs under autocast (ops._ShadowWeight): refreshed by ONE
@@ -81,13 +128,29 @@ class TrainStep:
         self.flat.zero_()
         if self._shadow_dst:
             torch._foreach_copy_(self._shadow_dst, self._shadow_src)
+        self._works, self._reduced = [], set()
+        ops.set_grad_marker_callback(self._on_marker if self.world_size > 1 else None)   # markers are placed in forward
+        try:
+            return self._step_body(img, label)
+        finally:
+            ops.set_grad_marker_callback(None)
+
+    def _step_body(self, img, label):
         feat, _seg = self.backbone(img)
         featn = F.normalize(feat)
         x_grad, loss = self.pfc.forward_backward(label, featn, self.opt_pfc)
         featn.backward(x_grad)                      # accumulates into the views of self.flat
         ops.flush_weight_grads()                    # the queued bf16 weight gradients, one multi-tensor launch
         if self.world_size > 1:
-            dist.all_reduce(self.flat)              # one NCCL all-reduce over NVLink for every gradient
+            # buckets 3..0 were started by the markers while the backward pass was still running (NCCL over NVLink on its
+            # own stream); what is left is the small tail (stem, stage 0 if its marker did not fire)
+            for tag, _cnt in self._buckets:
+                if tag not in self._reduced:
+                    lo, hi = self._bucket_ranges[tag]
+                    if hi > lo:
+                        self._works.append(dist.all_reduce(self.flat[lo:hi], async_op=True))
+            for w in self._works:
+                w.wait()
             self.flat.div_(self.world_size)
         if self.max_norm is not None:               # == clip_grad_norm_(used params, max_norm)
             coef = torch.clamp(self.max_norm / (torch.linalg.vector_norm(self.flat) + 1e-6), max=1.0)

@@ -500,6 +500,38 @@ def conv2d_padded_in(x, m, pad):
     return torch.nn.functional.conv2d(x, w, m.bias, m.stride, m.padding, m.dilation, m.groups)
 
 
+# --------------------------------------------------------------------------------------------
+# Backward-progress markers: identity in forward; in backward they tell the engine that every parameter used
+# AFTER this point of the forward pass has its gradient complete, so that its slice of the flat gradient buffer
+# can be all-reduced while the rest of the backward pass still runs (engine.TrainStep, world_size > 1).
+# --------------------------------------------------------------------------------------------
+_MARKER_CALLBACK = None
+
+
+def set_grad_marker_callback(fn):
+    global _MARKER_CALLBACK
+    _MARKER_CALLBACK = fn
+
+
+class _GradMarker(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, tag):
+        ctx.tag = tag
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        if _MARKER_CALLBACK is not None:
+            _MARKER_CALLBACK(ctx.tag)
+        return g, None
+
+
+def grad_marker(x, tag):
+    if _MARKER_CALLBACK is None or not x.requires_grad or not torch.is_grad_enabled():
+        return x
+    return _GradMarker.apply(x, tag)
+
+
 def launch_count():
     return load().msml_launch_count()
 
