@@ -112,6 +112,7 @@ __device__ __forceinline__ void put32(float* v, int idx, float x) {
 
 struct NoScratch {
   static constexpr int kSmemBytes = 0;
+  __device__ void prefetch(int, int, int, int, uint8_t*) const {}
   __device__ void finish(int, int) const {}
 };
 
@@ -219,7 +220,10 @@ struct StageOut {
   }
 };
 
-// backward pass 1: recompute logits, emit dcos (bf16, row-major) and rdot[n] = sum_m dcos[m,n] cos[m,n]
+// backward pass 1: recompute logits, emit dcos (bf16, row-major) and rdot[n] = sum_m dcos[m,n] cos[m,n] (= <Wn[n], dWn[n]>
+// for the normalise backward).  The inner loop is the bare softmax gradient (FFMA, EX2, FFMA, FMUL per element): the target
+// column is patched afterwards (rare, one element per row) and ragged tiles take a separate path, so that the epilogue of
+// a tile issues fewer instructions than its MMAs take cycles.
 struct EpiBwdDcos {
   static constexpr int kSmemBytes = 8 * StageOut::kBytesPerWarp;   // 64 KB (up to 8 epilogue warps)
   CUtensorMap map_dcos;        // bf16 (B_tot x n_s), boxes 64 cols x 32 rows
@@ -230,6 +234,7 @@ struct EpiBwdDcos {
   const float* gsum;   // [B_tot] global row sum of exp(logit - max)
   float* rdot;         // [n_s] zero-initialised; <Wn[n], dWn[n]> for the normalise backward
   float smooth_on, smooth_off, inv_btot;
+  __device__ void prefetch(int, int, int, int, uint8_t*) const {}
   __device__ void finish(int, int lane) const { StageOut::drain(lane); }
   __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int half, int nh) const {
     const int row0 = m_blk * kBlockM + quarter * 32;
@@ -240,10 +245,10 @@ struct EpiBwdDcos {
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + half * cph * 32;
     uint8_t* wscr = scratch + (half * 4 + quarter) * StageOut::kBytesPerWarp;
     const float s2 = mg.s * kLog2e;
-    // p = exp2(logit*log2e - off),  off = max*log2e + log2(sum)
-    const float off = row_ok ? fmaf(gmax[row], kLog2e, log2f(gsum[row])) : INFINITY;   // dead rows: p = 0
-    const float t_off = label >= 0 ? smooth_off : 0.f;   // rows without a local target: no one-hot row (ref :166)
+    // p = exp2(logit*log2e - off),  off = max*log2e + log2(sum);  dead rows: p = 0 and gs = 0
+    const float neg_off = row_ok ? -fmaf(gmax[row], kLog2e, log2f(gsum[row])) : -INFINITY;
     const float gs = row_ok ? mg.s * inv_btot : 0.f;
+    const float tg = (label >= 0 ? smooth_off : 0.f) * gs;   // rows without a local target: no one-hot row (ref :166)
     const int tile_col0 = n_blk * block_n + half * cph * 32;
     int n_chunks = (n_s - tile_col0 + 31) / 32;
     if (n_chunks > cph) n_chunks = cph;
@@ -257,35 +262,31 @@ struct EpiBwdDcos {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (c + h < n_chunks) {
-          float* cur = buf[h];
+          float* v = buf[h];
           if (c + h + 1 < n_chunks) tmem_ld32_issue(taddr + (c + h + 1) * 32, buf[h ^ 1]);
-          float* v = cur;
           const int col0 = tile_col0 + (c + h) * 32;
           const int64_t rel = label - col0;
           const bool has_t = rel >= 0 && rel < 32;
-          float cos_t = 0.f, tgt_mult = 1.f, tgt_logit = 0.f;
-          if (has_t) {
-            cos_t = pick32(v, (int)rel);
-            tgt_mult = margin_target_grad(mg, cos_t);
-            tgt_logit = margin_target(mg, cos_t);
-          }
-          float pr[32];
+          float cos_t = 0.f;
+          if (has_t) cos_t = pick32(v, (int)rel);
+          float pr[32];                                      // dcos * raw cosine
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const bool is_t = has_t && j == (int)rel;
-            const float logit = is_t ? tgt_logit : v[j];
-            const float p = fast_exp2(fmaf(logit, s2, -off));
-            float g = (p - (is_t ? smooth_on : t_off)) * gs;
-            g = is_t ? g * tgt_mult : g;
-            g = (col0 + j < n_s) ? g : 0.f;
-            pr[j] = g * v[j];            // dcos * raw cosine
+            const float g = fmaf(fast_exp2(fmaf(v[j], s2, neg_off)), gs, -tg);
+            pr[j] = g * v[j];
             v[j] = g;
           }
-          // bf16 pack: 32 values = 64 bytes = 4 x uint4 -> half `h` of the 128-byte staging row
+          if (has_t) {                                       // the one target element of this row (warp-divergent, rare)
+            const float p = fast_exp2(fmaf(margin_target(mg, cos_t), s2, neg_off));
+            const float g = (p - smooth_on) * gs * margin_target_grad(mg, cos_t);
+            put32(v, (int)rel, g);
+            put32(pr, (int)rel, g * cos_t);
+          }
+          if (col0 + 32 > n_s) {                             // ragged last tile (warp-uniform)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) packed[h * 4 + q] = Vec<__nv_bfloat16>::pack(v + q * 8);
-          // column sums over the 32 rows of this warp by recursive halving (31 shuffles), then one
-          // red per lane: rdot[col0 + lane] += sum_rows pr[.][lane]
+            for (int j = 0; j < 32; ++j) { v[j] = (col0 + j < n_s) ? v[j] : 0.f; pr[j] = (col0 + j < n_s) ? pr[j] : 0.f; }
+          }
+          // column sums over the 32 rows of this warp by recursive halving (31 shuffles), then one red per lane
 #pragma unroll
           for (int sft = 16; sft >= 1; sft >>= 1) {
             const bool up = (lane & sft) != 0;
@@ -297,6 +298,9 @@ struct EpiBwdDcos {
             }
           }
           if (col0 + lane < n_s) atomicAdd(rdot + col0 + lane, pr[0]);
+          // bf16 pack: 32 values = 64 bytes = 4 x uint4 -> half `h` of the 128-byte staging row
+#pragma unroll
+          for (int q = 0; q < 4; ++q) packed[h * 4 + q] = Vec<__nv_bfloat16>::pack(v + q * 8);
           if (c + h + 1 < n_chunks) tmem_ld_wait(buf[h ^ 1]);
         } else {
 #pragma unroll
@@ -336,8 +340,8 @@ struct EpiDxAccum : NoScratch {
 };
 
 // backward pass 3: dW = (dWn - Wn * rdot) * inv_norm      (ref :115 normalize backward), one pass.
-// Wn tile rows arrive through cp.async (coalesced 128-byte rows -> swizzled smem, 2 boxes in flight),
-// dW leaves through TMA stores.
+// Wn tile rows arrive through cp.async (coalesced 128-byte rows -> swizzled smem, 2 boxes in flight; the first two are
+// requested before the tile's MMAs have finished), dW leaves through TMA stores.  rdot = <Wn, dWn> comes from pass 1.
 struct EpiDwNormBwd {
   static constexpr int kWnBytesPerWarp = 2 * 4096;                  // 2 boxes of 32 rows x 64 bf16
   static constexpr int kSmemBytes = 4 * (StageOut::kBytesPerWarp + kWnBytesPerWarp);   // 64 KB
@@ -357,6 +361,12 @@ struct EpiDwNormBwd {
     }
     cp_async_commit();
   }
+  __device__ void prefetch(int m_blk, int n_blk, int quarter, int lane, uint8_t* scratch) const {
+    uint8_t* wwn = scratch + 4 * StageOut::kBytesPerWarp + quarter * kWnBytesPerWarp;
+    const int row0 = m_blk * kBlockM + quarter * 32, dcol0 = n_blk * 256;
+    load_wn_box(wwn, row0, dcol0, lane);
+    if (D - dcol0 > 64) load_wn_box(wwn + 4096, row0, dcol0 + 64, lane);
+  }
   __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int, int) const {
     const int row0 = m_blk * kBlockM + quarter * 32;
     const int row = row0 + lane;                     // class index (4 epilogue warps: each owns all 256 columns)
@@ -370,13 +380,11 @@ struct EpiDwNormBwd {
     int n_boxes = (D - dcol0) / 64;
     if (n_boxes > 4) n_boxes = 4;
     float buf[2][32];
-    load_wn_box(wwn, row0, dcol0, lane);
-    tmem_ld32_issue(taddr, buf[0]);
+    tmem_ld32_issue(taddr, buf[0]);                  // boxes 0 and 1 of Wn are already in flight (prefetch())
     tmem_ld_wait(buf[0]);
 #pragma unroll 1
     for (int bx = 0; bx < n_boxes; ++bx) {
-      if (bx + 1 < n_boxes) { load_wn_box(wwn + ((bx + 1) & 1) * 4096, row0, dcol0 + (bx + 1) * 64, lane); cp_async_wait<1>(); }
-      else cp_async_wait<0>();
+      if (bx + 1 < n_boxes) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncwarp();
       const uint8_t* wbox = wwn + (bx & 1) * 4096;
 #pragma unroll
@@ -402,6 +410,7 @@ struct EpiDwNormBwd {
         if (c + 1 < 2 * n_boxes) tmem_ld_wait(buf[h ^ 1]);
       }
       __syncwarp();   // every lane is done with this Wn box before it is refilled
+      if (bx + 2 < n_boxes) load_wn_box(wwn + (bx & 1) * 4096, row0, dcol0 + (bx + 2) * 64, lane);
     }
   }
 };
