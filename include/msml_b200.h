@@ -91,7 +91,9 @@ int msml_fm_mask_bwd(const void* dout, const void* yf, const void* m, void* dyf,
  *      dgamma / dbeta / dprelu are fp32 (C), overwritten, or added to when accumulate_param_grads != 0
  *      (the caller passes the parameters' .grad storage: what torch's AccumulateGrad would do in a
  *      separate kernel per parameter).  C must be a multiple of the 16-byte vector width with
- *      (C / width) dividing 256.
+ *      (C / width) dividing 256.  dadd (nullable, same layout as x) is added to dx: the gradient that reaches x
+ *      through its OTHER consumer (the skip connection of ref iresnet.py:56-67: `identity = x; out = bn1(x)`),
+ *      which autograd would otherwise add in a separate pass.
  * Training-mode fwd and bwd are ONE cooperative launch each (slab statistics -> grid barrier -> finalize ->
  * grid barrier -> apply); the device must support cooperative launches (every sm_100 part does).
  * ------------------------------------------------------------------------------------------ */
@@ -102,8 +104,9 @@ int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, con
                 void* workspace, size_t workspace_bytes, void* stream);
 int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* beta,
                 const float* prelu, const float* save_mean, const float* save_invstd, void* dx, void* dres,
-                float* dgamma, float* dbeta, float* dprelu, int64_t P, int64_t C, int dtype, int training,
-                int accumulate_param_grads, void* workspace, size_t workspace_bytes, void* stream);
+                const void* dadd /* nullable: dx = bn_bwd(..) + dadd */, float* dgamma, float* dbeta, float* dprelu,
+                int64_t P, int64_t C, int dtype, int training, int accumulate_param_grads, void* workspace,
+                size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Gradient plumbing of the training step (no reference counterpart: replaces one ATen mixed-dtype add per weight,

@@ -32,7 +32,8 @@ class IBasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = ops.conv2d(ops.bn_act(x, self.bn1), self.conv1)
+        y, x = ops.bn_act_fork(x, self.bn1)                    # x feeds bn1 and the skip: one fused gradient sum in backward
+        out = ops.conv2d(y, self.conv1)
         out = ops.conv2d(ops.bn_act(out, self.bn2, self.prelu), self.conv2)
         skip = x if self.downsample is None else ops.bn_act(ops.conv2d(x, self.downsample[0]), self.downsample[1])
         return ops.bn_act(out, self.bn3, None, skip)          # bn3(out) + identity

@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ prelu, T* __restrict__ dx, T* __restrict__ dres,
-                    float* dgamma, float* dbeta, float* dprelu, int training, int accumulate, float* part, float* coef, BnGeom g) {
+                    const T* __restrict__ dadd, float* dgamma, float* dbeta, float* dprelu, int training, int accumulate,
+                    float* part, float* coef, BnGeom g) {
   constexpr int VN = Vec<T>::N;
   constexpr bool R3 = RES && PRELU;          // the residual is only needed to recover the sign of u
   constexpr int NA = PRELU ? 3 : 2;
@@ -507,9 +508,11 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     ld_coef<VN>(coef + 2 * g.C + cv * VN, AG);
     uint4* dxv = reinterpret_cast<uint4*>(dx) + cv;
     uint4* drv = reinterpret_cast<uint4*>(dres) + cv;
+    const uint4* dav = reinterpret_cast<const uint4*>(dadd) + cv;     // gradient of the other consumer of x (skip branch)
+    const bool has_add = dadd != nullptr;
     constexpr int U = 2;
     for (int k = sl.n_it - 1; k >= 0; k -= U) {
-      uint4 a[U], b[U], c4[U];
+      uint4 a[U], b[U], c4[U], e[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (k - u >= 0) {
@@ -517,6 +520,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
           a[u] = ld_stream(dyv + v);
           b[u] = ld_stream(xv + v);
           if (R3) c4[u] = ld_stream(rv + v);
+          if (has_add) e[u] = ld_stream(dav + v);
         }
       }
 #pragma unroll
@@ -538,6 +542,12 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
           }
           dr[i] = du;
           o[i] = fmaf(-xh, AG[i], fmaf(A[i], du, -AB[i]));
+        }
+        if (has_add) {
+          float ad[VN];
+          Vec<T>::unpack(e[u], ad);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) o[i] += ad[i];
         }
         dxv[v] = Vec<T>::pack(o);
         if (R3) drv[v] = Vec<T>::pack(dr);
@@ -634,7 +644,7 @@ static int launch_bn_fwd_fused(const void* x, const void* res, void* y, const fl
 
 template <typename T, bool RES, bool PRELU>
 static int launch_bn_bwd_fused(const void* dy, const void* x, const void* res, const float* mean, const float* invstd,
-                               const float* gamma, const float* beta, const float* prelu, void* dx, void* dres, float* dgamma,
+                               const float* gamma, const float* beta, const float* prelu, void* dx, void* dres, const void* dadd, float* dgamma,
                                float* dbeta, float* dprelu, int training, int accumulate, float* part, float* coef, BnGeom g,
                                cudaStream_t st) {
   auto kern = bn_bwd_fused_kernel<T, RES, PRELU>;
@@ -645,7 +655,8 @@ static int launch_bn_bwd_fused(const void* dy, const void* x, const void* res, c
   const T* rp = static_cast<const T*>(res);
   T* dxp = static_cast<T*>(dx);
   T* drp = static_cast<T*>(dres);
-  void* args[] = {&dyp, &xp, &rp, &mean, &invstd, &gamma, &beta, &prelu, &dxp, &drp, &dgamma, &dbeta, &dprelu,
+  const T* dap = static_cast<const T*>(dadd);
+  void* args[] = {&dyp, &xp, &rp, &mean, &invstd, &gamma, &beta, &prelu, &dxp, &drp, &dap, &dgamma, &dbeta, &dprelu,
                   &training, &accumulate, &part, &coef, &g};
   return launch_grid_synced(reinterpret_cast<const void*>(kern), grid, args, st);
 }
@@ -695,14 +706,14 @@ extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float*
 
 extern "C" int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* beta,
                            const float* prelu, const float* save_mean, const float* save_invstd, void* dx, void* dres,
-                           float* dgamma, float* dbeta, float* dprelu, int64_t P, int64_t C, int dtype, int training,
+                           const void* dadd, float* dgamma, float* dbeta, float* dprelu, int64_t P, int64_t C, int dtype, int training,
                            int accumulate_param_grads, void* ws, size_t ws_bytes, void* stream) {
   BnGeom g;
   if (int e = bn_geom(P, C, dtype, &g)) return e;
   MSML_REQUIRE(dy && x && dx && save_mean && save_invstd, MSML_EINVAL, "null pointer");
   const bool has_prelu = prelu != nullptr, has_res = res != nullptr;
   MSML_REQUIRE(!(has_prelu && has_res) || dres, MSML_EINVAL, "dres is required when both a residual and PReLU are fused");
-  MSML_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(res) && aligned16(dx) && aligned16(dres) && aligned16(ws) &&
+  MSML_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(res) && aligned16(dx) && aligned16(dres) && aligned16(ws) && aligned16(dadd) &&
                    aligned16(gamma) && aligned16(beta) && aligned16(prelu) && aligned16(save_mean) && aligned16(save_invstd),
                MSML_EALIGN, "pointers must be 16-byte aligned");
   MSML_REQUIRE(ws && ws_bytes >= msml_bn_workspace(P, C), MSML_EWORKSPACE, "BN workspace too small");
@@ -711,10 +722,10 @@ extern "C" int msml_bn_bwd(const void* dy, const void* x, const void* res, const
   float* coef = part + (size_t)kBnMaxCtas * 3 * C + kBnMaxCtas;
   const double elem = dtype == MSML_F32 ? 4.0 : 2.0;
   const int both = has_prelu && has_res ? 1 : 0;
-  MSML_PROF("bn_bwd_fused", (double)P * C * elem * (3 + 2 * both), st);
+  MSML_PROF("bn_bwd_fused", (double)P * C * elem * (3 + 2 * both + (dadd ? 1 : 0)), st);
   int rc = 0;
   MSML_BN_DISPATCH(dtype, has_res, has_prelu,
-                   (rc = launch_bn_bwd_fused<T, RES, PRELU>(dy, x, res, save_mean, save_invstd, gamma, beta, prelu, dx, dres, dgamma,
+                   (rc = launch_bn_bwd_fused<T, RES, PRELU>(dy, x, res, save_mean, save_invstd, gamma, beta, prelu, dx, dres, dadd, dgamma,
                                                             dbeta, dprelu, training, accumulate_param_grads, part, coef, g, st)));
   return rc;
 }

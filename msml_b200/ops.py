@@ -149,7 +149,7 @@ def fm_mask(yf, m, act="sigmoid", arith="mul"):
 # --------------------------------------------------------------------------------------------
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, prelu, res, running_mean, running_var, nbt, training, momentum, eps):
+    def forward(ctx, x, gamma, beta, prelu, res, running_mean, running_var, nbt, training, momentum, eps, fork=False):
         require_cuda(x, gamma, beta, prelu, res)
         lib = load()
         B, C, H, W = x.shape
@@ -166,16 +166,23 @@ class _BNAct(torch.autograd.Function):
         ctx.save_for_backward(x_d, res_d if prelu is not None else None, gamma, beta, prelu, stats)
         ctx.cfg = (training, res is not None)
         ctx.params = (gamma, beta, prelu)          # the Parameter objects themselves (for the direct-gradient path)
+        ctx.fork = fork
+        ctx.set_materialize_grads(False)           # an unused output arrives as None in backward, not as a zero tensor
+        if fork:                                   # second output: x itself, for the skip branch (see bn_act_fork)
+            return y, x_d.view_as(x_d)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x, res, gamma, beta, prelu, stats = ctx.saved_tensors
         training, has_res = ctx.cfg
         lib = load()
         B, C, H, W = x.shape
         P = B * H * W
+        if dy is None:                             # only the skip branch carried a gradient (or nothing did)
+            return (dskip,) + (None,) * 11
         dy_d = _dense_like(x, dy)
+        dadd = _dense_like(x, dskip) if dskip is not None else None
         dx = torch.empty_like(x)
         both = has_res and prelu is not None
         dres = torch.empty_like(x) if both else None
@@ -193,19 +200,40 @@ class _BNAct(torch.autograd.Function):
             g_ptrs = [_ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])]
         # a residual without PReLU passes its gradient straight through (dres = dy): no extra stream
         check(lib.msml_bn_bwd(_ptr(dy_d), _ptr(x), _ptr(res) if both else None, _ptr(gamma), _ptr(beta),
-                              _ptr(prelu), _ptr(stats[0]), _ptr(stats[1]), _ptr(dx), _ptr(dres), g_ptrs[0], g_ptrs[1],
+                              _ptr(prelu), _ptr(stats[0]), _ptr(stats[1]), _ptr(dx), _ptr(dres), _ptr(dadd), g_ptrs[0], g_ptrs[1],
                               g_ptrs[2], P, C, dtype_code(x.dtype), int(training), int(direct), _ptr(ws), ws_bytes, stream_ptr()))
         d_res = dres if both else (dy_d if has_res else None)
         if direct:
-            return dx, None, None, None, d_res, None, None, None, None, None, None
+            return dx, None, None, None, d_res, None, None, None, None, None, None, None
         dprelu = grads[2] if prelu is not None else None
-        return dx, grads[0], grads[1], dprelu, d_res, None, None, None, None, None, None
+        return dx, grads[0], grads[1], dprelu, d_res, None, None, None, None, None, None, None
 
 
 def _direct_grad(p):
     """True when the engine has marked ``p`` as living in its flat gradient buffer (see engine.TrainStep)."""
     return (getattr(p, "_msml_direct_grad", False) and p.grad is not None and p.grad.dtype == torch.float32
             and _is_dense(p.grad) and p.grad.data_ptr() % 16 == 0)
+
+
+def bn_act_fork(x, bn, prelu=None):
+    """(prelu(bn(x)), x): for a tensor with TWO consumers, the normalisation and a skip connection (ref iresnet.py:56-67
+    `identity = x; out = self.bn1(x)`).  Use the second output for the skip branch: the backward kernel then adds the
+    skip gradient while it writes dx, instead of autograd summing the two contributions in one more pass."""
+    if not (torch.is_grad_enabled() and x.requires_grad):
+        return bn_act(x, bn, prelu), x
+    _check_bn_args(x, bn, prelu)
+    a = prelu.weight if prelu is not None else None
+    return _BNAct.apply(x, bn.weight, bn.bias, a, None, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                        bn.training, bn.momentum, bn.eps, True)
+
+
+def _check_bn_args(x, bn, prelu):
+    if x.dim() != 4:
+        raise ValueError("bn_act expects a 4-D (B, C, H, W) tensor")
+    if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+        raise RuntimeError("bn_act supports affine BatchNorm2d with running statistics and a fixed momentum")
+    if prelu is not None and prelu.weight.numel() != x.shape[1]:
+        raise ValueError("bn_act: PReLU must have one slope per channel")
 
 
 def bn_act(x, bn, prelu=None, res=None):

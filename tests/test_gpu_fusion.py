@@ -279,3 +279,34 @@ def test_padded_channel_paths_match_unpadded(monkeypatch):
     cos = torch.nn.functional.cosine_similarity(f1.double(), f2.double())
     assert (cos > 0.999).all(), cos
     assert_close(host(s1), host(s2), 3e-2, atol_frac=3e-2, what="seg padded vs unpadded")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn_act_fork_fuses_the_skip_gradient(dtype):
+    """(bn(x), x) with the skip gradient added inside the backward kernel == bn(x) and x used separately."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(4)
+    bn = torch.nn.BatchNorm2d(64).cuda().train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+    x0 = torch.randn(4, 64, 14, 14, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    d1 = torch.randn_like(x0); d2 = torch.randn_like(x0)
+    res = {}
+    for mode in ("plain", "fork"):
+        x = x0.clone().requires_grad_(True)
+        bn.zero_grad(set_to_none=True)
+        if mode == "plain":
+            y, xs = ops.bn_act(x, bn), x
+        else:
+            y, xs = ops.bn_act_fork(x, bn)
+        (y * d1).sum().backward(retain_graph=True) if False else ((y * d1).sum() + (xs * d2).sum()).backward()
+        res[mode] = (host(y), host(x.grad), host(bn.weight.grad), host(bn.bias.grad))
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    for a, b, what in zip(res["fork"], res["plain"], ("y", "dx", "dgamma", "dbeta")):
+        assert_close(a, b, tol, atol_frac=tol, what=what)
+    # only the skip branch used: gradient passes straight through
+    x = x0.clone().requires_grad_(True)
+    _y, xs = ops.bn_act_fork(x, bn)
+    (xs * d2).sum().backward()
+    assert_close(host(x.grad), host(d2), 0.0, atol=0.0, what="skip only")
