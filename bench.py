@@ -291,10 +291,17 @@ def run_train(args, rank, local_rank, world):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         last = 0.0
-        for i in range(n):
-            if host_fed:
-                last = step(imgs_h[i % n_buf], labels_h[i % n_buf]).item()     # H2D of the inputs, D2H read of the loss
-            else:
+        if host_fed:
+            # every step: H2D of that step's inputs from pinned memory (issued through the engine's prefetcher, so it
+            # runs under the previous step, as a data loader's prefetcher would) and a D2H read of that step's loss
+            step.prefetch(imgs_h[0], labels_h[0])
+            for i in range(n):
+                loss_t = step()
+                if i + 1 < n:
+                    step.prefetch(imgs_h[(i + 1) % n_buf], labels_h[(i + 1) % n_buf])
+                last = loss_t.item()
+        else:
+            for i in range(n):
                 last = step(imgs[i % n_buf], labels[i % n_buf])
         b.record()
         fence()

@@ -39,6 +39,7 @@ class TrainStep:
         self.graph = None
         self._used = None
         self._shadow_src, self._shadow_dst = [], []
+        self._copy_stream, self._has_staged = None, False
         if use_graph and int(pfc.sample_rate) != 1:
             raise ValueError("captured TrainStep needs PartialFC sample_rate == 1; use use_graph=False for sampled heads")
 
@@ -213,16 +214,50 @@ class TrainStep:
                         b.copy_(s)
         torch.cuda.synchronize(self.device)
 
-    def __call__(self, img, label):
-        """img (B,3,H,W) and label (B,) may live on the host (pinned) or the device."""
+    def prefetch(self, img, label):
+        """Start the host -> device copy of the NEXT step's inputs (pinned host tensors) on a copy stream, so that it runs
+        under the current step; the following ``step()`` call (no arguments) consumes them.  What a data loader's
+        prefetcher does (ref utils: DataLoaderX / CUDAPrefetcher in datasets/dataloaderx.py)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._staged_img = torch.empty_like(self.static_img)
+            self._staged_label = torch.empty_like(self.static_label)
+            self._staged_free = torch.cuda.Event()
+            self._staged_ready = torch.cuda.Event()
+            self._staged_free.record(torch.cuda.current_stream(self.device))
+        self._copy_stream.wait_event(self._staged_free)          # the previous staged batch has been consumed
+        with torch.cuda.stream(self._copy_stream):
+            self._staged_img.copy_(img, non_blocking=True)
+            self._staged_label.copy_(label, non_blocking=True)
+            self._staged_ready.record(self._copy_stream)
+        self._has_staged = True
+
+    def __call__(self, img=None, label=None):
+        """img (B,3,H,W) and label (B,) may live on the host (pinned) or the device; with no arguments the batch staged by
+        ``prefetch`` is used."""
         self._prepare()
+        if img is None:
+            if not self._has_staged:
+                raise RuntimeError("TrainStep(): no inputs given and nothing staged by prefetch()")
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(self._staged_ready)
+            img, label = self._staged_img, self._staged_label
+            self._has_staged = False
+            staged = True
+        else:
+            staged = False
         if not self.use_graph:
-            return self._step(img.to(self.device, non_blocking=True).contiguous(memory_format=torch.channels_last),
+            loss = self._step(img.to(self.device, non_blocking=True).contiguous(memory_format=torch.channels_last),
                               label.to(self.device, non_blocking=True))
+            if staged:
+                self._staged_free.record(torch.cuda.current_stream(self.device))
+            return loss
         if self.graph is None:
             self.recapture()
         self.static_img.copy_(img, non_blocking=True)
         self.static_label.copy_(label, non_blocking=True)
+        if staged:
+            self._staged_free.record(torch.cuda.current_stream(self.device))
         self.graph.replay()
         return self.static_loss
 

@@ -178,3 +178,33 @@ def test_bucketed_allreduce_covers_every_gradient_exactly_once(monkeypatch):
     for k, a in out[1][1].items():
         b = out[2][1][k]
         assert np.linalg.norm(a - b) <= 2e-3 * np.linalg.norm(a) + 1e-7, (k, np.linalg.norm(a - b), np.linalg.norm(a))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_prefetched_inputs_give_the_same_step(use_graph):
+    need_gpu()
+    from msml_b200.engine import TrainStep
+    B = 8
+    g = torch.Generator().manual_seed(19)
+    imgs = [torch.randn(B, 3, 112, 112, generator=g).pin_memory() for _ in range(3)]
+    labels = [torch.randint(0, 1000, (B,), generator=g).pin_memory() for _ in range(3)]
+    out = {}
+    for mode in ("direct", "prefetch"):
+        net, pfc, opt, opt_pfc = _build(fp16=True)
+        step = TrainStep(net, pfc, opt, opt_pfc, (B, 3, 112, 112), use_graph=use_graph)
+        losses = []
+        if mode == "direct":
+            for i, l in zip(imgs, labels):
+                losses.append(float(step(i, l)))
+        else:
+            step.prefetch(imgs[0], labels[0])
+            for k in range(3):
+                loss_t = step()
+                if k + 1 < 3:
+                    step.prefetch(imgs[k + 1], labels[k + 1])
+                losses.append(float(loss_t))
+            with pytest.raises(RuntimeError):
+                step()                                       # nothing staged
+        out[mode] = losses
+    for a, b in zip(out["direct"], out["prefetch"]):
+        assert abs(a - b) <= 1e-2 * abs(a), out
