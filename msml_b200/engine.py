@@ -152,15 +152,35 @@ class TrainStep:
                         self._works.append(dist.all_reduce(self.flat[lo:hi], async_op=True))
             for w in self._works:
                 w.wait()
-            self.flat.div_(self.world_size)
+        fused_clip = False
         if self.max_norm is not None:               # == clip_grad_norm_(used params, max_norm)
-            coef = torch.clamp(self.max_norm / (torch.linalg.vector_norm(self.flat) + 1e-6), max=1.0)
-            self.flat.mul_(coef)
+            norm = torch.linalg.vector_norm(self.flat)
+            if self.world_size > 1:
+                # flat still holds the SUM over ranks: fold the 1/world_size of the mean into the same scale
+                norm = norm / self.world_size
+            if self._fused_sgd_takes_scale():
+                # torch's fused SGD divides every gradient by `grad_scale` inside its own kernel (the GradScaler hook):
+                # clipping (and the 1/world_size of the all-reduce mean) costs no extra pass over the 48 M gradients
+                inv = torch.clamp((norm + 1e-6) / self.max_norm, min=1.0)
+                self.opt_backbone.grad_scale = (inv * self.world_size if self.world_size > 1 else inv).reshape(())
+                fused_clip = True
+            else:
+                coef = torch.clamp(self.max_norm / (norm + 1e-6), max=1.0)
+                self.flat.mul_(coef / self.world_size if self.world_size > 1 else coef)
+        elif self.world_size > 1:
+            self.flat.div_(self.world_size)
         self.opt_backbone.step()
+        if fused_clip:
+            self.opt_backbone.grad_scale = None
         self.opt_pfc.step()
         self.pfc.update()
         self.pfc.sub_weight.grad = None
         return loss
+
+    def _fused_sgd_takes_scale(self):
+        opt = self.opt_backbone
+        return (isinstance(opt, torch.optim.SGD) and all(g.get("fused") for g in opt.param_groups)
+                and all(not g.get("maximize") for g in opt.param_groups))
 
     # ------------------------------------------------------------------ capture / replay
     def _prepare(self):

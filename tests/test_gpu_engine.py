@@ -11,7 +11,7 @@ from gpu_util import assert_close, host, need_gpu
 pytestmark = pytest.mark.gpu
 
 
-def _build(seed=3, classes=1000, B=8, fp16=False):
+def _build(seed=3, classes=1000, B=8, fp16=False, fused=None):
     from msml_b200.backbones import MSML
     from msml_b200.headers import ArcFace, PartialFC
     from oracle.detfill import fill_state_dict_
@@ -20,7 +20,7 @@ def _build(seed=3, classes=1000, B=8, fp16=False):
     fill_state_dict_(net)
     net = net.cuda().train()
     pfc = PartialFC(0, 0, 1, B, False, ArcFace(64.0, 0.5), classes)
-    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4)
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4, fused=fused)
     opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.01, momentum=0.9, weight_decay=5e-4)
     return net, pfc, opt, opt_pfc
 
@@ -96,8 +96,9 @@ def test_bf16_engine_step_matches_plain_autograd_step():
     imgs = [torch.randn(B, 3, 112, 112, device="cuda", generator=g) for _ in range(2)]
     labels = [torch.randint(0, 1000, (B,), device="cuda", generator=g) for _ in range(2)]
 
-    net, pfc, opt, opt_pfc = _build(fp16=True)
+    net, pfc, opt, opt_pfc = _build(fp16=True, fused=True)      # fused SGD: the clip coefficient rides in its grad_scale
     step = TrainStep(net, pfc, opt, opt_pfc, (B, 3, 112, 112), use_graph=False)
+    assert step._fused_sgd_takes_scale()
     loss_e = [float(step(i, l)) for i, l in zip(imgs, labels)]
     assert hasattr(net.frb.layer1[0].conv1.weight, "_msml_shadow")          # the engine path really ran on shadows
 
