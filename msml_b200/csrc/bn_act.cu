@@ -39,7 +39,9 @@ struct BnGeom {
   int C;           // channels (contiguous)
   int vpr;         // 16-byte vectors per row
   int rows_per_pass;   // kBnThreads / vpr
-  int skip;            // debug (MSML_BN_SKIP_PHASES bitmask: 1, 2, 4 skip the work of phase 1, 2, 3; 8 = timestamps)
+  int skip;            // bitmask: 1, 2, 4 skip the work of phase 1, 2, 3 (split launches / debug); 8 = timestamps (debug);
+                       // 16 = no grid barriers (the phases run as separate plain launches)
+  int G;               // CTAs of the streaming phases (1 and 3): partial layout and slab geometry
 };
 
 // VN consecutive per-channel values as 16-byte loads (a strided scalar load per element costs one 32-byte sector each)
@@ -115,7 +117,7 @@ struct Slab {
 };
 __device__ __forceinline__ Slab slab_of(const BnGeom& g, int rl) {
   Slab s;
-  const int64_t rows_per_cta = (g.P + gridDim.x - 1) / gridDim.x;
+  const int64_t rows_per_cta = (g.P + g.G - 1) / g.G;
   s.r0 = (int64_t)blockIdx.x * rows_per_cta;
   s.r1 = s.r0 + rows_per_cta;
   if (s.r1 > g.P) s.r1 = g.P;
@@ -126,8 +128,9 @@ __device__ __forceinline__ Slab slab_of(const BnGeom& g, int rl) {
 
 // ------------------------------------------------------------------------------------------- forward (training)
 // part layout: [k][C][grid] (channel-major so that phase 2 reads the slabs of a channel coalesced)
-template <typename T, bool RES, bool PRELU>
-__global__ void __launch_bounds__(kBnThreads)
+template <typename T, bool RES, bool PRELU, int PHASE>     // PHASE 0: all three phases with grid barriers (cooperative launch);
+__global__ void __launch_bounds__(kBnThreads, 4)            // 1 / 2 / 3: that phase only (plain launch, compiled on its own);
+                                                            // 4 CTAs / SM: the 592-CTA grid is exactly one wave
 bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ prelu, float* __restrict__ running_mean,
                     float* __restrict__ running_var, long long* __restrict__ nbt, float momentum, float eps,
@@ -136,7 +139,8 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
   constexpr int VN = Vec<T>::N;
   __shared__ float red[2][kBnThreads * 8];   // [2][nslots * C] <= [2][256*8]
   cg::grid_group grid = cg::this_grid();
-  const int G = gridDim.x;
+  (void)grid;
+  const int G = g.G;
   const int cv = threadIdx.x % g.vpr, rl = threadIdx.x / g.vpr;
   const Slab sl = slab_of(g, rl);
   const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
@@ -144,7 +148,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
   dbg_stamp(g.skip, coef, g.C, 0);
 
   // ---- phase 1: slab statistics
-  if (!(g.skip & 1)) {
+  if (PHASE == 0 ? !(g.skip & 1) : PHASE == 1) {
     float s[VN], q[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) { s[i] = 0.f; q[i] = 0.f; }
@@ -189,16 +193,16 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     if (threadIdx.x == 0) part_n[blockIdx.x] = n;
   }
   dbg_stamp(g.skip, coef, g.C, 1);
-  grid.sync();
+  if (PHASE == 0) grid.sync();
   dbg_stamp(g.skip, coef, g.C, 2);
 
   // ---- phase 2: merge the slabs, one CTA per channel (all loads issued up front, then a shuffle / smem tree)
-  if (!(g.skip & 2)) {
+  if (PHASE == 0 ? !(g.skip & 2) : PHASE == 2) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
     const float Pf = (float)g.P;
     constexpr int NL = (kBnMaxCtas + kBnThreads - 1) / kBnThreads;
-    for (int c = blockIdx.x; c < g.C; c += G) {
+    for (int c = blockIdx.x; c < g.C; c += gridDim.x) {
       // thread 0 issues its (cold, HBM) parameter loads first so that their latency overlaps the merge
       float p_g = 1.f, p_b = 0.f, p_rm = 0.f, p_rv = 0.f;
       if (threadIdx.x == 0) {
@@ -247,11 +251,11 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     idle_before_barrier(blockIdx.x >= g.C);
   }
   dbg_stamp(g.skip, coef, g.C, 3);
-  grid.sync();
+  if (PHASE == 0) grid.sync();
   dbg_stamp(g.skip, coef, g.C, 4);
 
   // ---- phase 3: apply over the same slab, newest rows first (they are the likeliest L2 hits)
-  if (!(g.skip & 4)) {
+  if (PHASE == 0 ? !(g.skip & 4) : PHASE == 3) {
     float sc[VN], sh[VN], pa[VN];
     ld_coef<VN>(coef + cv * VN, sc);
     ld_coef<VN>(coef + g.C + cv * VN, sh);
@@ -351,7 +355,7 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
 // u = x*sc + sh [+ res] (sc = gamma*invstd, sh = beta - mean*sc);  du = dy * (u > 0 ? 1 : a);  xhat = x*invstd - mean*invstd
 // accumulators [3][C]:  [0] sum du   [1] sum du * xhat   [2] sum dy * u * [u <= 0]
 // dx = A*du - A*B - xhat * A*G   with A = gamma*invstd, B = sum du / P, G = sum du*xhat / P  (B = G = 0 in eval mode)
-template <typename T, bool RES, bool PRELU>
+template <typename T, bool RES, bool PRELU, int PHASE>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -363,7 +367,8 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   constexpr int NA = PRELU ? 3 : 2;
   __shared__ float red[NA][kBnThreads * 8];
   cg::grid_group grid = cg::this_grid();
-  const int G = gridDim.x;
+  (void)grid;
+  const int G = g.G;
   const int cv = threadIdx.x % g.vpr, rl = threadIdx.x / g.vpr;
   const Slab sl = slab_of(g, rl);
   const int64_t row0 = sl.r0 + rl;
@@ -390,7 +395,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   dbg_stamp(g.skip, coef, g.C, 0);
 
   // ---- phase 1: slab reductions
-  if (!(g.skip & 1)) {
+  if (PHASE == 0 ? !(g.skip & 1) : PHASE == 1) {
     float s0[VN], s1[VN], s2[VN];
 #pragma unroll
     for (int i = 0; i < VN; ++i) s0[i] = s1[i] = s2[i] = 0.f;
@@ -452,14 +457,14 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     }
   }
   dbg_stamp(g.skip, coef, g.C, 1);
-  grid.sync();
+  if (PHASE == 0) grid.sync();
   dbg_stamp(g.skip, coef, g.C, 2);
 
   // ---- phase 2: dgamma, dbeta, dprelu, coefficients; one CTA per channel
-  if (!(g.skip & 2)) {
+  if (PHASE == 0 ? !(g.skip & 2) : PHASE == 2) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float Pf = (float)g.P;
-    for (int c = blockIdx.x; c < g.C; c += G) {
+    for (int c = blockIdx.x; c < g.C; c += gridDim.x) {
       float t0 = 0.f, t1 = 0.f, t2 = 0.f;
       for (int b = threadIdx.x; b < G; b += kBnThreads) {
         t0 += part[(size_t)c * G + b];
@@ -497,11 +502,11 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     idle_before_barrier(blockIdx.x >= g.C);
   }
   dbg_stamp(g.skip, coef, g.C, 3);
-  grid.sync();
+  if (PHASE == 0) grid.sync();
   dbg_stamp(g.skip, coef, g.C, 4);
 
   // ---- phase 3: dx [, dres] over the same slab, newest rows first
-  if (!(g.skip & 4)) {
+  if (PHASE == 0 ? !(g.skip & 4) : PHASE == 3) {
     float A[VN], AB[VN], AG[VN];
     ld_coef<VN>(coef + cv * VN, A);
     ld_coef<VN>(coef + g.C + cv * VN, AB);
@@ -626,20 +631,49 @@ static int launch_grid_synced(const void* kern, int grid, void** args, cudaStrea
   return 0;
 }
 
+// Default: the three phases as three PLAIN launches of the phase-specialised kernels (phase 2 on C CTAs); the kernel
+// boundary plays the role of the grid barrier.  Measured inside CUDA graphs on B200 this beats the single cooperative
+// launch at every layer size (205 MB: 118 vs 147 us forward, 259 vs 349 us backward; 6.4 MB: 16.5 vs 18.9 us): a kernel
+// boundary costs ~2 us there, a grid barrier 2-5 us (arrival skew of 300-600 CTAs + same-address atomics) on top of the
+// dearer cooperative launch, and each phase compiled on its own needs fewer registers.  MSML_BN_FUSED=1 selects the
+// cooperative single launch (kept for that comparison).
+static int bn_fused_mode() {
+  static const int mode = getenv("MSML_BN_FUSED") ? atoi(getenv("MSML_BN_FUSED")) : 0;
+  return mode;
+}
+static int launch_plain(const void* kern, int blocks, void** args, cudaStream_t st) {
+  MSML_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kBnThreads), args, 0, st));
+  count_launch();
+  return 0;
+}
+
 template <typename T, bool RES, bool PRELU>
 static int launch_bn_fwd_fused(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
                                float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps, float* save_mean,
                                float* save_invstd, float* part, float* part_n, float* coef, BnGeom g, cudaStream_t st) {
-  auto kern = bn_fwd_fused_kernel<T, RES, PRELU>;
-  int grid = 0;
-  if (int e = coop_grid(kern, g, &grid)) return e;
   const T* xp = static_cast<const T*>(x);
   const T* rp = static_cast<const T*>(res);
   T* yp = static_cast<T*>(y);
   long long* nb = reinterpret_cast<long long*>(nbt);
   void* args[] = {&xp, &rp, &yp, &gamma, &beta, &prelu, &running_mean, &running_var, &nb, &momentum, &eps,
                   &save_mean, &save_invstd, &part, &part_n, &coef, &g};
-  return launch_grid_synced(reinterpret_cast<const void*>(kern), grid, args, st);
+  if (bn_fused_mode()) {
+    auto kern = bn_fwd_fused_kernel<T, RES, PRELU, 0>;
+    int grid = 0;
+    if (int e = coop_grid(kern, g, &grid)) return e;
+    g.G = grid;
+    return launch_grid_synced(reinterpret_cast<const void*>(kern), grid, args, st);
+  }
+  // each streaming phase gets a grid of at most ONE resident wave of its own kernel (a second, partly filled wave of the
+  // statically partitioned slabs would only add a tail); phase 3 may partition the rows differently from phase 1
+  int g1 = 0, g3 = 0;
+  if (int e = coop_grid(bn_fwd_fused_kernel<T, RES, PRELU, 1>, g, &g1)) return e;
+  if (int e = coop_grid(bn_fwd_fused_kernel<T, RES, PRELU, 3>, g, &g3)) return e;
+  g.G = g1;
+  if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st)) return e;
+  if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st)) return e;
+  g.G = g3;
+  return launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st);
 }
 
 template <typename T, bool RES, bool PRELU>
@@ -647,9 +681,6 @@ static int launch_bn_bwd_fused(const void* dy, const void* x, const void* res, c
                                const float* gamma, const float* beta, const float* prelu, void* dx, void* dres, const void* dadd, float* dgamma,
                                float* dbeta, float* dprelu, int training, int accumulate, float* part, float* coef, BnGeom g,
                                cudaStream_t st) {
-  auto kern = bn_bwd_fused_kernel<T, RES, PRELU>;
-  int grid = 0;
-  if (int e = coop_grid(kern, g, &grid)) return e;
   const T* dyp = static_cast<const T*>(dy);
   const T* xp = static_cast<const T*>(x);
   const T* rp = static_cast<const T*>(res);
@@ -658,7 +689,21 @@ static int launch_bn_bwd_fused(const void* dy, const void* x, const void* res, c
   const T* dap = static_cast<const T*>(dadd);
   void* args[] = {&dyp, &xp, &rp, &mean, &invstd, &gamma, &beta, &prelu, &dxp, &drp, &dap, &dgamma, &dbeta, &dprelu,
                   &training, &accumulate, &part, &coef, &g};
-  return launch_grid_synced(reinterpret_cast<const void*>(kern), grid, args, st);
+  if (bn_fused_mode()) {
+    auto kern = bn_bwd_fused_kernel<T, RES, PRELU, 0>;
+    int grid = 0;
+    if (int e = coop_grid(kern, g, &grid)) return e;
+    g.G = grid;
+    return launch_grid_synced(reinterpret_cast<const void*>(kern), grid, args, st);
+  }
+  int g1 = 0, g3 = 0;
+  if (int e = coop_grid(bn_bwd_fused_kernel<T, RES, PRELU, 1>, g, &g1)) return e;
+  if (int e = coop_grid(bn_bwd_fused_kernel<T, RES, PRELU, 3>, g, &g3)) return e;
+  g.G = g1;
+  if (int e = launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st)) return e;
+  if (int e = launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st)) return e;
+  g.G = g3;
+  return launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st);
 }
 
 extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
@@ -679,7 +724,7 @@ extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float*
   float* coef = part_n + kBnMaxCtas;
   const double elem = dtype == MSML_F32 ? 4.0 : 2.0;
   if (training) {
-    MSML_PROF("bn_fwd_fused", (double)P * C * elem * (res ? 3 : 2), st);
+    MSML_PROF("bn_fwd", (double)P * C * elem * (res ? 3 : 2), st);
     int rc = 0;
     MSML_BN_DISPATCH(dtype, res != nullptr, prelu != nullptr,
                      (rc = launch_bn_fwd_fused<T, RES, PRELU>(x, res, y, gamma, beta, prelu, running_mean, running_var,
@@ -722,7 +767,7 @@ extern "C" int msml_bn_bwd(const void* dy, const void* x, const void* res, const
   float* coef = part + (size_t)kBnMaxCtas * 3 * C + kBnMaxCtas;
   const double elem = dtype == MSML_F32 ? 4.0 : 2.0;
   const int both = has_prelu && has_res ? 1 : 0;
-  MSML_PROF("bn_bwd_fused", (double)P * C * elem * (3 + 2 * both + (dadd ? 1 : 0)), st);
+  MSML_PROF("bn_bwd", (double)P * C * elem * (3 + 2 * both + (dadd ? 1 : 0)), st);
   int rc = 0;
   MSML_BN_DISPATCH(dtype, has_res, has_prelu,
                    (rc = launch_bn_bwd_fused<T, RES, PRELU>(dy, x, res, save_mean, save_invstd, gamma, beta, prelu, dx, dres, dadd, dgamma,
