@@ -352,11 +352,14 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
 }
 
 // ------------------------------------------------------------------------------------------- backward
-// u = x*sc + sh [+ res] (sc = gamma*invstd, sh = beta - mean*sc);  du = dy * (u > 0 ? 1 : a);  xhat = x*invstd - mean*invstd
-// accumulators [3][C]:  [0] sum du   [1] sum du * xhat   [2] sum dy * u * [u <= 0]
-// dx = A*du - A*B - xhat * A*G   with A = gamma*invstd, B = sum du / P, G = sum du*xhat / P  (B = G = 0 in eval mode)
+// u = x*sc + sh [+ res] (sc = gamma*invstd, sh = beta - mean*sc);  du = dy * (u > 0 ? 1 : a);  xhat = (x - mean)*invstd
+// accumulators [3][C]:  [0] T0 = sum du   [1] Q1 = sum du * x   [2] sum dy * u * [u <= 0]
+//   sum du * xhat = invstd * (Q1 - mean * T0): the streaming loops carry as few per-channel vectors as possible
+//   (registers decide how many CTAs an SM holds, i.e. how many loads are in flight)
+// dx = A*(du - B - xhat*G) = sc*du + x*K1 + K0   with A = sc, B = T0 / P, G = sum du*xhat / P,
+//   K1 = -A*G*invstd, K0 = -A*B + A*G*mean*invstd      (B = G = 0 in eval mode)
 template <typename T, bool RES, bool PRELU, int PHASE>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, PHASE == 0 ? 1 : ((RES && PRELU) ? 2 : 3))   // <= 80 registers without spilling
 bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ prelu, T* __restrict__ dx, T* __restrict__ dres,
@@ -376,9 +379,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
   const uint4* rv = reinterpret_cast<const uint4*>(res) + cv;
 
-  float is[VN], nmis[VN], sc[VN], sh[VN], pa[VN];
-  {
-    float mu[VN], ga[VN], be[VN];
+  float sc[VN], sh[VN], pa[VN];
+  if (PHASE != 2) {
+    float is[VN], mu[VN], ga[VN], be[VN];
     ld_coef<VN>(invstd + cv * VN, is);
     ld_coef<VN>(mean + cv * VN, mu);
     if (gamma) ld_coef<VN>(gamma + cv * VN, ga);
@@ -386,7 +389,6 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     if (PRELU) ld_coef<VN>(prelu + cv * VN, pa);
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
-      nmis[i] = -mu[i] * is[i];
       sc[i] = (gamma ? ga[i] : 1.f) * is[i];
       sh[i] = (beta ? be[i] : 0.f) - mu[i] * sc[i];
       if (!PRELU) pa[i] = 1.f;
@@ -420,7 +422,6 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
         if (R3) Vec<T>::unpack(c4[u], rs);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-          const float xh = fmaf(f[i], is[i], nmis[i]);
           float du = d[i];
           if (PRELU) {
             float uu = fmaf(f[i], sc[i], sh[i]);
@@ -428,7 +429,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
             if (!(uu > 0.f)) { s2[i] = fmaf(d[i], uu, s2[i]); du *= pa[i]; }
           }
           s0[i] += du;
-          s1[i] = fmaf(du, xh, s1[i]);
+          s1[i] = fmaf(du, f[i], s1[i]);           // Q1 = sum du * x
         }
       }
     }
@@ -484,19 +485,22 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
         t0 = t1 = t2 = 0.f;
 #pragma unroll
         for (int w = 0; w < kBnThreads / 32; ++w) { t0 += red[0][w * 3]; t1 += red[0][w * 3 + 1]; t2 += red[0][w * 3 + 2]; }
+        const float is_c = invstd[c], mu_c = mean[c];
+        const float s1 = is_c * (t1 - mu_c * t0);          // sum du * xhat
         if (accumulate) {       // write straight into the parameters' .grad (flat gradient buffer)
           if (dbeta) dbeta[c] += t0;
-          if (dgamma) dgamma[c] += t1;
+          if (dgamma) dgamma[c] += s1;
           if (PRELU && dprelu) dprelu[c] += t2;
         } else {
           if (dbeta) dbeta[c] = t0;
-          if (dgamma) dgamma[c] = t1;
+          if (dgamma) dgamma[c] = s1;
           if (PRELU && dprelu) dprelu[c] = t2;
         }
-        const float A = (gamma ? gamma[c] : 1.f) * invstd[c];
-        coef[c] = A;
-        coef[g.C + c] = training ? A * t0 / Pf : 0.f;      // eval: statistics are constants
-        coef[2 * g.C + c] = training ? A * t1 / Pf : 0.f;
+        const float A = (gamma ? gamma[c] : 1.f) * is_c;
+        const float Bc = training ? t0 / Pf : 0.f;         // eval: statistics are constants
+        const float Gc = training ? s1 / Pf : 0.f;
+        coef[c] = -A * Gc * is_c;                          // K1
+        coef[g.C + c] = A * (Gc * mu_c * is_c - Bc);       // K0
       }
     }
     idle_before_barrier(blockIdx.x >= g.C);
@@ -507,10 +511,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
 
   // ---- phase 3: dx [, dres] over the same slab, newest rows first
   if (PHASE == 0 ? !(g.skip & 4) : PHASE == 3) {
-    float A[VN], AB[VN], AG[VN];
-    ld_coef<VN>(coef + cv * VN, A);
-    ld_coef<VN>(coef + g.C + cv * VN, AB);
-    ld_coef<VN>(coef + 2 * g.C + cv * VN, AG);
+    float K1[VN], K0[VN];
+    ld_coef<VN>(coef + cv * VN, K1);
+    ld_coef<VN>(coef + g.C + cv * VN, K0);
     uint4* dxv = reinterpret_cast<uint4*>(dx) + cv;
     uint4* drv = reinterpret_cast<uint4*>(dres) + cv;
     const uint4* dav = reinterpret_cast<const uint4*>(dadd) + cv;     // gradient of the other consumer of x (skip branch)
@@ -538,7 +541,6 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
         if (R3) Vec<T>::unpack(c4[u], rs);
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-          const float xh = fmaf(f[i], is[i], nmis[i]);
           float du = d[i];
           if (PRELU) {
             float uu = fmaf(f[i], sc[i], sh[i]);
@@ -546,7 +548,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
             if (!(uu > 0.f)) du *= pa[i];
           }
           dr[i] = du;
-          o[i] = fmaf(-xh, AG[i], fmaf(A[i], du, -AB[i]));
+          o[i] = fmaf(sc[i], du, fmaf(f[i], K1[i], K0[i]));
         }
         if (has_add) {
           float ad[VN];
