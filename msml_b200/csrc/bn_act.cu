@@ -110,6 +110,11 @@ __device__ __forceinline__ void dbg_stamp(const int skip, float* coef, int C, in
   }
 }
 
+// Programmatic dependent launch: phases 2 and 3 are launched while their predecessor still runs (launch latency and the
+// prologue overlap its tail) and block here until it has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // rows [r0, r1) of this CTA; thread-local row index k maps to row r0 + rl + k * rows_per_pass
 struct Slab {
   int64_t r0, r1;
@@ -146,6 +151,8 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
   const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
   const int64_t row0 = sl.r0 + rl;
   dbg_stamp(g.skip, coef, g.C, 0);
+  if (PHASE == 1 || PHASE == 2) pdl_launch_dependents();
+  if (PHASE == 2 || PHASE == 3) pdl_wait();
 
   // ---- phase 1: slab statistics
   if (PHASE == 0 ? !(g.skip & 1) : PHASE == 1) {
@@ -395,6 +402,8 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     }
   }
   dbg_stamp(g.skip, coef, g.C, 0);
+  if (PHASE == 1 || PHASE == 2) pdl_launch_dependents();
+  if (PHASE == 2 || PHASE == 3) pdl_wait();
 
   // ---- phase 1: slab reductions
   if (PHASE == 0 ? !(g.skip & 1) : PHASE == 1) {
@@ -643,8 +652,23 @@ static int bn_fused_mode() {
   static const int mode = getenv("MSML_BN_FUSED") ? atoi(getenv("MSML_BN_FUSED")) : 0;
   return mode;
 }
-static int launch_plain(const void* kern, int blocks, void** args, cudaStream_t st) {
-  MSML_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kBnThreads), args, 0, st));
+static int launch_plain(const void* kern, int blocks, void** args, cudaStream_t st, bool dependent = false) {
+  static const int pdl = getenv("MSML_BN_PDL") ? atoi(getenv("MSML_BN_PDL")) : 1;     // 0 disables (comparison)
+  if (dependent && pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kBnThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MSML_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  } else {
+    MSML_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kBnThreads), args, 0, st));
+  }
   count_launch();
   return 0;
 }
@@ -673,9 +697,9 @@ static int launch_bn_fwd_fused(const void* x, const void* res, void* y, const fl
   if (int e = coop_grid(bn_fwd_fused_kernel<T, RES, PRELU, 3>, g, &g3)) return e;
   g.G = g1;
   if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st)) return e;
-  if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st)) return e;
+  if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st, true)) return e;
   g.G = g3;
-  return launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st);
+  return launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st, true);
 }
 
 template <typename T, bool RES, bool PRELU>
@@ -703,9 +727,9 @@ static int launch_bn_bwd_fused(const void* dy, const void* x, const void* res, c
   if (int e = coop_grid(bn_bwd_fused_kernel<T, RES, PRELU, 3>, g, &g3)) return e;
   g.G = g1;
   if (int e = launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st)) return e;
-  if (int e = launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st)) return e;
+  if (int e = launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st, true)) return e;
   g.G = g3;
-  return launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st);
+  return launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st, true);
 }
 
 extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
