@@ -153,10 +153,10 @@ _TRAFFIC = None
 
 def ncu_traffic(name, suffix=""):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this kernel
-    (profiles/r01b_traffic.json), or None if that kernel was not captured."""
+    (profiles/r01c_traffic.json), or None if that kernel was not captured."""
     global _TRAFFIC
     if _TRAFFIC is None:
-        path = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+        path = os.path.join(ROOT, "profiles", "r01c_traffic.json")
         _TRAFFIC = json.load(open(path)) if os.path.exists(path) else {}
     rec = _TRAFFIC.get(name + suffix)
     return rec["dram_bytes_per_launch"] if rec else None

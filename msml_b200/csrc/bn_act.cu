@@ -5,21 +5,29 @@
 //
 // In the reference these are 3-6 separate ATen kernels per layer (batch_norm statistics, transform,
 // prelu, add; and five more in backward) and make up ~60 % of the training step on B200.  A layer's
-// tensors are 6-50 MB, i.e. 1-8 us of HBM time, so as separate launches the chain is bound by
-// launch / drain latency, not bandwidth.  Here each direction is ONE cooperative (grid-synchronised) kernel:
+// tensors are 6-50 MB, i.e. 1-8 us of HBM time, so the chain is bound by launch / dependency latency, not
+// bandwidth.  Each direction is three phases:
 //   forward   phase 1  read x -> per-CTA (mean, M2) slab statistics
 //             phase 2  Chan merge of the slabs (one CTA per channel), running stats, scale / shift
 //             phase 3  re-read the SAME slab newest-first (an activation of <= 51 MB is still in the
 //                      126 MB L2) [+ res], write y = prelu(x*scale + shift [+ res])
-//   backward  phase 1  read dy, x [, res] -> per-CTA partials of (sum du, sum du*xhat, sum dy*u*[u<=0])
+//   backward  phase 1  read dy, x [, res] -> per-CTA partials of (sum du, sum du*x, sum dy*u*[u<=0])
 //             phase 2  dgamma, dbeta, dprelu and the coefficients of dx
-//             phase 3  re-read the slab, write dx [, dres = du]
-// (A variant with fp64 atomics into per-channel accumulators and a single barrier was measured and was
-// slower: same-address atomics from 300-600 CTAs cost more than the second barrier.)
-// Minimum HBM traffic is one read of each input + one write of each output.
+//             phase 3  re-read the slab, write dx [, dres = du] [+ the skip branch's gradient]
+// launched as THREE PLAIN KERNELS compiled per phase (template PHASE = 1, 2, 3), phases 2 and 3 with
+// programmatic dependent launch so that their launch latency and prologue hide under the predecessor's tail.
+// Measured inside CUDA graphs this beats both alternatives that were built and timed:
+//   * ONE cooperative launch with two grid barriers (PHASE = 0, still selectable with MSML_BN_FUSED=1): a kernel
+//     boundary costs ~2 us in a graph, a grid barrier 2-5 us (arrival skew of 300-600 CTAs + same-address
+//     atomics) on top of the dearer cooperative launch, and the fused kernel carries the register budget of
+//     its heaviest phase (205 MB layer: 147 vs 116 us forward, 349 vs 197 us backward);
+//   * fp64 atomics into per-channel accumulators with a single barrier: same-address atomics from 300-600
+//     CTAs cost more than the second barrier.
+// Minimum HBM traffic is one read of each input + one write of each output (the re-reads hit L2).
 // All phases stream a (P = N*H*W) x C matrix with C contiguous: a thread owns one 16-byte channel
 // vector for its whole life, so per-channel coefficients live in registers; loads are 128-bit, several
-// rows in flight per thread.  Eval mode (running statistics) keeps the two-kernel path.
+// rows in flight per thread; each streaming phase runs exactly one resident wave of its own kernel.
+// Eval mode (running statistics) is a coefficient kernel + one apply pass.
 #include <cooperative_groups.h>
 
 #include <cstdlib>
