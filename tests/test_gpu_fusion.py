@@ -310,3 +310,37 @@ def test_bn_act_fork_fuses_the_skip_gradient(dtype):
     _y, xs = ops.bn_act_fork(x, bn)
     (xs * d2).sum().backward()
     assert_close(host(x.grad), host(d2), 0.0, atol=0.0, what="skip only")
+
+
+def test_bn_cooperative_single_launch_matches_default(tmp_path):
+    """MSML_BN_FUSED=1 (one cooperative launch with two grid barriers, kept for the measured comparison) must compute the
+    same BN forward / backward as the default three-launch path.  The mode is read once per process, so the
+    cooperative run happens in a subprocess."""
+    need_gpu()
+    import os
+    import subprocess
+    import sys
+    script = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from msml_b200 import ops
+torch.manual_seed(7)
+bn = torch.nn.BatchNorm2d(128).cuda().train(); pr = torch.nn.PReLU(128).cuda()
+with torch.no_grad():
+    bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5); pr.weight.uniform_(0.1, 0.4)
+x = torch.randn(16, 128, 14, 14, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_()
+r = torch.randn_like(x)
+y = ops.bn_act(x, bn, pr, r)
+y.backward(torch.randn_like(y))
+torch.save({"y": y.detach().float().cpu(), "dx": x.grad.float().cpu(), "dg": bn.weight.grad.cpu(), "db": bn.bias.grad.cpu(),
+            "dp": pr.weight.grad.cpu(), "rm": bn.running_mean.cpu(), "rv": bn.running_var.cpu()}, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for mode in ("0", "1"):
+        path = str(tmp_path / ("bn_%s.pt" % mode))
+        env = dict(os.environ, MSML_BN_FUSED=mode)
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=env, timeout=300)
+        outs[mode] = torch.load(path)
+    for k in outs["0"]:
+        assert_close(outs["1"][k].double().numpy(), outs["0"][k].double().numpy(), 2e-2 if k in ("y", "dx") else 1e-4,
+                     atol_frac=2e-2 if k in ("y", "dx") else 1e-4, what="cooperative vs default: " + k)
