@@ -104,6 +104,42 @@ def gen_fm():
     assert o is yf and l is None
 
 
+# --------------------------------------------------------------------------- FM operator, peer-guided branch
+FM_PEER_CASES = [  # name, C, H, B, act, arith, use_conv, mask_trans
+    ("fm_peer_c64_conv", 64, 5, 2, "sigmoid", "mul", True, "conv"),
+    ("fm_peer_c128_invert", 128, 4, 2, "tanh", "add", False, "invert"),
+]
+
+
+def gen_fm_peer():
+    """FMCnn with use_ori=True (ref fmoperator.py:129-166, 293-302, 307-308): m_bar = conv_m(gate), f_out = conv1(m_bar*yf),
+    l2 = MSE(conv2(m_bar*yt), f_out), out = arith(yf, gate) + f_out + yf.  Random (deterministic) weights: parity only."""
+    from backbones.fm.fmoperator import FMCnn
+    for name, C, H, B, act, arith, use_conv, mask_trans in FM_PEER_CASES:
+        fm = FMCnn(H, H, C, kernel_size=3, resblocks=2, activation=act, arith_strategy=arith,
+                   peer_params={"use_ori": True, "use_conv": use_conv, "mask_trans": mask_trans, "use_decoder": False})
+        fill_state_dict_(fm)
+        fm.train(True)
+        yf = det_tensor(name + ".yf", (B, C, H, H)).requires_grad_(True)
+        yo = det_tensor(name + ".yo", (B, 18, H, H))
+        yt = det_tensor(name + ".yt", (B, C, H, H))
+        dout = det_tensor(name + ".dout", (B, C, H, H))
+        out, l2 = fm(yf, yo, yt)
+        assert l2 is not None
+        (out * dout).sum().add(0.5 * l2).backward()
+        pg = {("pgrad." + k): p.grad for k, p in fm.named_parameters()
+              if k in ("res_block.1.prelu3.weight", "res_block.0.bn1.weight", "conv_m.0.weight", "conv1.0.weight", "conv2.3.weight")
+              and p.grad is not None}
+        save(name, C=C, H=H, B=B, act=act, arith=arith, use_conv=int(use_conv), mask_trans=mask_trans,
+             yf=yf, yo=yo, yt=yt, dout=dout, out=out, l2=l2, dyf=yf.grad, **pg)
+        # eval-time call (yt is None): no distillation loss, f_out still added
+        fm.eval()
+        with torch.no_grad():
+            out_e, l2_e = fm(yf.detach(), yo)
+        assert l2_e is None
+        save(name + "_eval", out=out_e)
+
+
 # --------------------------------------------------------------------------- DAP
 def gen_dap():
     from backbones.osb.unet import unet
@@ -333,7 +369,7 @@ def gen_model():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fm", "dap", "margins", "pfc", "model"]
+    which = sys.argv[1:] or ["fm", "fm_peer", "dap", "margins", "pfc", "model"]
     seeds()
     for w in which:
         globals()["gen_" + w]()

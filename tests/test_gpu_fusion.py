@@ -344,3 +344,43 @@ torch.save({"y": y.detach().float().cpu(), "dx": x.grad.float().cpu(), "dg": bn.
     for k in outs["0"]:
         assert_close(outs["1"][k].double().numpy(), outs["0"][k].double().numpy(), 2e-2 if k in ("y", "dx") else 1e-4,
                      atol_frac=2e-2 if k in ("y", "dx") else 1e-4, what="cooperative vs default: " + k)
+
+
+@pytest.mark.parametrize("name", ["fm_peer_c64_conv", "fm_peer_c128_invert"])
+def test_fmcnn_peer_branch_matches_reference_golden(name):
+    """FMCnn with the peer-guided branch on (use_ori=True; ref fmoperator.py:129-166,293-302,307-308), random
+    deterministic weights, against vectors produced by the reference's FMCnn: output, distillation loss, dyf and
+    parameter gradients in train mode; the eval call (yt=None) adds f_out without a loss."""
+    need_gpu()
+    from msml_b200.backbones.fm import FMCnn
+    from oracle.detfill import fill_state_dict_
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        g = load_golden(name)
+        C, H = int(g["C"]), int(g["H"])
+        fm = FMCnn(H, H, C, kernel_size=3, resblocks=2, activation=str(g["act"]), arith_strategy=str(g["arith"]),
+                   peer_params={"use_ori": True, "use_conv": bool(int(g["use_conv"])), "mask_trans": str(g["mask_trans"]),
+                                "use_decoder": False})
+        fill_state_dict_(fm)
+        fm = fm.cuda().train()
+        yf = dev(g["yf"]).requires_grad_(True)
+        out, l2 = fm(yf, dev(g["yo"]), dev(g["yt"]))
+        assert l2 is not None
+        (out * dev(g["dout"])).sum().add(0.5 * l2).backward()
+        assert_close(host(out), g["out"], 2e-4, atol_frac=2e-5, what="out")
+        assert abs(float(l2) - float(g["l2"])) <= 1e-4 * abs(float(g["l2"])) + 1e-7
+        assert_close(host(yf.grad), g["dyf"], 2e-3, atol_frac=2e-4, what="dyf")
+        params = dict(fm.named_parameters())
+        for k in g:
+            if k.startswith("pgrad."):
+                assert_close(host(params[k[6:]].grad), g[k], 2e-3, atol_frac=5e-4, what=k)
+        ge = load_golden(name + "_eval")
+        fm.eval()
+        with torch.no_grad():
+            out_e, l2_e = fm(dev(g["yf"]), dev(g["yo"]))
+        assert l2_e is None
+        assert_close(host(out_e), ge["out"], 2e-4, atol_frac=2e-5, what="eval out")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
