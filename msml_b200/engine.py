@@ -126,6 +126,7 @@ class TrainStep:
                 self._shadow_dst.append(w._msml_shadow)
 
     def _step(self, img, label):
+        ops.discard_pending_weight_grads()          # nothing may survive from an aborted earlier step
         self.flat.zero_()
         if self._shadow_dst:
             torch._foreach_copy_(self._shadow_dst, self._shadow_src)

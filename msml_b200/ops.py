@@ -439,6 +439,11 @@ def _is_dense(t):
     return True
 
 
+def discard_pending_weight_grads():
+    """Drop queued weight gradients (a backward pass that raised half-way would otherwise leak them into the next step)."""
+    _PENDING_WGRADS.clear()
+
+
 def flush_weight_grads():
     """Add every bf16 weight gradient queued by _ShadowWeight.backward into its fp32 flat-gradient view: one launch
     (msml_accum_bf16_multi) for all of them.  engine.TrainStep calls this right after the backward pass."""
