@@ -25,7 +25,7 @@ from . import ops
 
 class TrainStep:
     def __init__(self, backbone, pfc, opt_backbone, opt_pfc, batch_shape, world_size=1, max_norm=5.0,
-                 use_graph=True, device=None):
+                 use_graph=True, device=None, wgrad_side_stream=True):
         self.backbone, self.pfc = backbone, pfc
         self.opt_backbone, self.opt_pfc = opt_backbone, opt_pfc
         self.world_size, self.max_norm, self.use_graph = world_size, max_norm, use_graph
@@ -40,6 +40,8 @@ class TrainStep:
         self._used = None
         self._shadow_src, self._shadow_dst = [], []
         self._copy_stream, self._has_staged = None, False
+        # convolution weight gradients run on a second stream and fill the idle SMs under the latency-bound BN kernels
+        self.wgrad_side_stream = wgrad_side_stream
         if use_graph and int(pfc.sample_rate) != 1:
             raise ValueError("captured TrainStep needs PartialFC sample_rate == 1; use use_graph=False for sampled heads")
 
@@ -132,10 +134,12 @@ class TrainStep:
             torch._foreach_copy_(self._shadow_dst, self._shadow_src)
         self._works, self._reduced = [], set()
         ops.set_grad_marker_callback(self._on_marker if self.world_size > 1 else None)   # markers are placed in forward
+        ops.set_wgrad_side_stream(self.wgrad_side_stream)
         try:
             return self._step_body(img, label)
         finally:
             ops.set_grad_marker_callback(None)
+            ops.set_wgrad_side_stream(False)
 
     def _step_body(self, img, label):
         feat, _seg = self.backbone(img)

@@ -442,11 +442,13 @@ def _is_dense(t):
 def discard_pending_weight_grads():
     """Drop queued weight gradients (a backward pass that raised half-way would otherwise leak them into the next step)."""
     _PENDING_WGRADS.clear()
+    join_weight_grad_stream()
 
 
 def flush_weight_grads():
     """Add every bf16 weight gradient queued by _ShadowWeight.backward into its fp32 flat-gradient view: one launch
     (msml_accum_bf16_multi) for all of them.  engine.TrainStep calls this right after the backward pass."""
+    join_weight_grad_stream()
     if not _PENDING_WGRADS:
         return
     lib = load()
@@ -471,12 +473,92 @@ def _weight_of(m):
     return w
 
 
+def _shadow_active(m):
+    w = m.weight
+    sh = getattr(w, "_msml_shadow", None)
+    return (sh is not None and m.training and torch.is_grad_enabled() and w.requires_grad and torch.is_autocast_enabled()
+            and torch.get_autocast_dtype("cuda") == sh.dtype)
+
+
+# Weight gradients on a side stream.  In the backward pass only the data gradient of a convolution is on the critical
+# path (the next layer's backward needs it); the weight gradient is needed by the optimizer alone.  The BN / activation
+# kernels between two convolutions are latency-bound and leave most SMs idle, so the wgrad kernels run on a second stream
+# and fill that time; they are joined before the gradients are consumed (flush_weight_grads).  Inside the captured
+# CUDA graph this becomes a fork / join of kernel nodes.
+_WGRAD_STREAMS = {}
+_WGRAD_KEEPALIVE = []          # (dy, x) of wgrads still running on the side stream
+_WGRAD_SIDE = {"enabled": False, "dirty": False}
+
+
+def set_wgrad_side_stream(enabled):
+    _WGRAD_SIDE["enabled"] = bool(enabled)
+
+
+def _wgrad_stream(device):
+    st = _WGRAD_STREAMS.get(device)
+    if st is None:
+        st = torch.cuda.Stream(device)
+        _WGRAD_STREAMS[device] = st
+    return st
+
+
+def join_weight_grad_stream():
+    """Make the current stream wait for every weight gradient launched on the side stream."""
+    if _WGRAD_SIDE["dirty"]:
+        for dev, st in _WGRAD_STREAMS.items():
+            torch.cuda.current_stream(dev).wait_stream(st)
+        _WGRAD_SIDE["dirty"] = False
+    _WGRAD_KEEPALIVE.clear()
+
+
+class _ConvShadow(torch.autograd.Function):
+    """conv2d(x, bf16 shadow of w) whose backward computes dgrad on the current stream and wgrad on the side stream."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, dilation, groups):
+        sh = w._msml_shadow
+        ctx.save_for_backward(x, sh)
+        ctx.param = w
+        ctx.cfg = (stride, padding, dilation, groups)
+        return torch.nn.functional.conv2d(x, sh, None, stride, padding, dilation, groups)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, sh = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.cfg
+        p = ctx.param
+        cb = torch.ops.aten.convolution_backward
+        out_pad = [0] * len(stride)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = cb(dy, x, sh, None, stride, padding, dilation, False, out_pad, groups, [True, False, False])[0]
+        if _WGRAD_SIDE["enabled"] and _direct_grad(p):
+            main = torch.cuda.current_stream(dy.device)
+            side = _wgrad_stream(dy.device)
+            side.wait_stream(main)                       # dy (and x) are complete on the main stream
+            with torch.cuda.stream(side):
+                dw = cb(dy, x, sh, None, stride, padding, dilation, False, out_pad, groups, [False, True, False])[1]
+            _WGRAD_KEEPALIVE.append((dy, x))             # their memory must not be reused before the join
+            _WGRAD_SIDE["dirty"] = True
+        else:
+            dw = cb(dy, x, sh, None, stride, padding, dilation, False, out_pad, groups, [False, True, False])[1]
+        if _direct_grad(p):
+            if dw.dtype == torch.bfloat16 and dw.stride() == p.grad.stride() and _is_dense(dw):
+                _PENDING_WGRADS.append((p.grad, dw))
+            else:
+                join_weight_grad_stream()
+                p.grad.add_(dw)
+            return dx, None, None, None, None, None
+        return dx, dw.to(p.dtype), None, None, None, None
+
+
 def conv2d(x, m):
     """``m(x)`` for an nn.Conv2d, through the bf16 shadow weight when the engine installed one."""
-    w = _weight_of(m)
-    if w is m.weight:
+    if not _shadow_active(m):
         return m(x)
-    return torch.nn.functional.conv2d(x, w, m.bias, m.stride, m.padding, m.dilation, m.groups)
+    if m.bias is None and x.is_cuda and x.dtype == m.weight._msml_shadow.dtype and m.padding_mode == "zeros":
+        return _ConvShadow.apply(x, m.weight, tuple(m.stride), tuple(m.padding), tuple(m.dilation), m.groups)
+    return torch.nn.functional.conv2d(x, _ShadowWeight.apply(m.weight), m.bias, m.stride, m.padding, m.dilation, m.groups)
 
 
 def conv_transpose2d(x, m):
