@@ -62,7 +62,7 @@ class IResNet(nn.Module):
         """Inject a frozen teacher returning (feature, [ft0..ft3]) (ref backbones/peer/arcface.py)."""
         self.peer = peer.requires_grad_(False)
 
-    def forward(self, x, segs, ori):
+    def forward(self, x, segs, ori, segs_ready=None):
         ft = (None, None, None, None)
         if ori is not None:
             if self.peer is None:
@@ -74,8 +74,13 @@ class IResNet(nn.Module):
         for i, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
             x = ops.grad_marker(x, i)       # backward: everything from stage i on has its parameter gradients complete
             x = layer(x)
+            if segs_ready is not None:          # the OSB ran on a side stream: join it before its maps are first read
+                segs_ready()
+                segs_ready = None
             x, l = self.fm_ops[i](x, segs[i], ft[i])
             kd_terms.append(l)
+        if segs_ready is not None:
+            segs_ready()
         x = ops.bn_act(x, self.bn2)
         x = self.dropout(torch.flatten(x, 1))
         x = self.features(ops.linear(x.float(), self.fc))

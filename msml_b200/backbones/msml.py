@@ -110,13 +110,19 @@ class MSML(nn.Module):
                 # one bf16 copy of the image with the channels zero-padded 3 -> 8: both stem convolutions (OSB, FRB) then run
                 # cuDNN's tensor-core kernels instead of the 3-channel generic ones (their weights get zero input channels)
                 x, _ = ops.cat_channels_padded((x.to(torch.bfloat16),))
+            segs_ready = None
             if self.use_osb:
-                seg_list = self.osb(x)              # [seg0, seg1, seg2, seg3, seg5] small to big
+                if ops.side_stream_enabled() and x.is_cuda and self.training:
+                    # the FRB needs the segmentation maps only at its first FM operator: the OSB runs on the side stream
+                    # next to the FRB stem and stage 1 (both are chains of latency-bound kernels that leave SMs idle)
+                    seg_list, segs_ready = ops.run_on_side_stream(self.osb, x)
+                else:
+                    seg_list = self.osb(x)          # [seg0, seg1, seg2, seg3, seg5] small to big
                 final_seg = seg_list[4]
                 segs = seg_list[3::-1]              # [seg3, seg2, seg1, seg0] big to small
             else:
                 segs, final_seg = (None, None, None, None), None
-            feature, kd = self.frb(x, segs, ori)
+            feature, kd = self.frb(x, segs, ori, segs_ready)
         feature = feature.float()
         if self.training and self.classification is not None:
             final_cls = self.classification(feature, label) + kd

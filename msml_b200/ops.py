@@ -494,6 +494,26 @@ def set_wgrad_side_stream(enabled):
     _WGRAD_SIDE["enabled"] = bool(enabled)
 
 
+def side_stream_enabled():
+    return _WGRAD_SIDE["enabled"]
+
+
+def run_on_side_stream(fn, *args):
+    """Run ``fn(*args)`` on the side stream (forked from the current stream); returns (result, join) where ``join()`` makes
+    the current stream wait for it.  Used to run the occlusion-segmentation branch concurrently with the first stage of the
+    recognition branch, which does not need its outputs until the first FM operator."""
+    dev = torch.cuda.current_device()
+    main = torch.cuda.current_stream(dev)
+    side = _wgrad_stream(torch.device("cuda", dev))
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        out = fn(*args)
+
+    def join():
+        torch.cuda.current_stream(dev).wait_stream(side)
+    return out, join
+
+
 def _wgrad_stream(device):
     st = _WGRAD_STREAMS.get(device)
     if st is None:
