@@ -328,7 +328,9 @@ def run_train(args, rank, local_rank, world):
     # per-kernel roofline pass: the SAME step run eagerly (a CUDA graph cannot be bracketed kernel by
     # kernel), every launch of this library between two CUDA events on its own stream
     prof_steps = 3
-    eager = step if args.eager else TrainStep(net, pfc, opt, opt_pfc, (BATCH, 3, 112, 112), world_size=world, max_norm=5.0, use_graph=False)
+    # (single stream: with the side stream on, concurrent kernels would inflate each other's event-bracketed durations)
+    eager = step if args.eager else TrainStep(net, pfc, opt, opt_pfc, (BATCH, 3, 112, 112), world_size=world, max_norm=5.0,
+                                              use_graph=False, wgrad_side_stream=False)
     if not args.eager:
         eager.share_state_from(step)
     eager(imgs[0], labels[0])
@@ -356,7 +358,7 @@ def run_train(args, rank, local_rank, world):
                                "112x112, batch 128/GPU (BASELINE config 3)",
                    "global_batch": BATCH * world,
                    "parallelism": "dp%d backbone (flat-gradient NCCL all-reduce) + class-sharded head" % world,
-                   "execution": "eager" if args.eager else "whole step captured in one CUDA graph (msml_b200.engine.TrainStep)",
+                   "execution": "eager" if args.eager else "whole step captured in one CUDA graph, two streams (wgrad + OSB on a side stream) (msml_b200.engine.TrainStep)",
                    "l2": "per-step working set (activations, GBs) >> 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(args.steps * BATCH * world / (ms_e2e * 1e-3), 1), "unit": "imgs/s",
                 "h2d_bytes_per_step": imgs_h[0].numel() * 4 + labels_h[0].numel() * 8, "d2h_bytes_per_step": 4,
@@ -366,7 +368,7 @@ def run_train(args, rank, local_rank, world):
         "own_kernel_ms_per_step": round(mine_ms, 4),
         "roofline": rl[0] if rl else None,
         "rooflines": rl,
-        "roofline_pass": "%d eager replays of the same step after the timed region, CUDA events around every launch" % prof_steps,
+        "roofline_pass": "%d eager single-stream replays of the same step after the timed region, CUDA events around every launch" % prof_steps,
         "clocks": clocks,
         "loss": round(loss, 4),
     }

@@ -7,10 +7,17 @@ B200 that is launch-bound from Python.  ``TrainStep`` keeps the reference's sema
     x_grad, loss = pfc.forward_backward(label, F.normalize(features), opt_pfc)
     features.backward(x_grad); clip_grad_norm_(backbone, 5); opt_backbone.step(); opt_pfc.step(); pfc.update()
 
-and runs it the B200 way: gradients of all used backbone parameters live in ONE flat fp32 buffer
-(a single NCCL all-reduce replaces DDP's buckets; clipping is two kernels), and after three eager
-warm-up steps the whole step — cuDNN convolutions, this library's kernels, NCCL collectives and the
-SGD updates — is captured into a CUDA graph and replayed with no Python or launch overhead.
+and runs it the B200 way:
+  * gradients of all used backbone parameters live in ONE flat fp32 buffer ordered by backward completion; one NCCL
+    all-reduce per stage starts while the rest of the backward pass still runs; the clip coefficient and the 1/W of the
+    mean ride in the fused SGD's grad_scale;
+  * conv / linear weights have bf16 shadows refreshed by one multi-tensor copy; their bf16 gradients are added into the
+    flat buffer by one launch; BN / PReLU gradients are added by the BN backward kernels themselves;
+  * two streams: convolution weight gradients (off the critical path) and the occlusion-segmentation branch (not needed
+    before the first FM operator) run on a side stream and fill the SMs that the latency-bound BN kernels leave idle;
+  * after three eager warm-up steps the whole step — cuDNN convolutions, this library's kernels, NCCL collectives, the
+    SGD updates, the stream forks and joins — is captured into a CUDA graph and replayed with no Python or launch
+    overhead; the next batch's host-to-device copy runs under the current step (``prefetch``).
 
 Limits of the captured mode (documented, checked): PartialFC sample_rate must be 1 (sampling needs
 a data-dependent allocation), learning rates are baked in at capture time (call ``recapture()``
