@@ -7,10 +7,13 @@
 //              The (B_tot x n_s) logits matrix is NEVER written to memory.
 //   merge      combines the row stats of all ranks (after one all-gather), computes the loss.
 //   head_bwd   1. recompute S tile by tile; epilogue: p = softmax, grad = (p - smoothed one-hot)/B_tot,
-//                 chain through margin and scale -> dcos in bf16 (row-major + transposed)
-//              2. dX  = dcos Wn        split-K over the class dimension, fp32 red.add
-//              3. dW  = normalize_bwd(dcos^T X): 128 x 512 accumulator (all of TMEM), epilogue
-//                 applies (dWn - Wn * <Wn, dWn>) / ||W|| and streams fp32 rows out.
+//                 chain through margin and scale -> dcos in bf16 (row-major, the only materialised matrix),
+//                 plus rdot[n] = <Wn[n], dWn[n]> by a warp transpose-reduce
+//              2. dX  = dcos Wn        Wn read in place (MN-major), split-K over the class dimension sized to
+//                 exactly one wave, fp32 red.add
+//              3. dW  = normalize_bwd(dcos^T X): dcos and X read in place (MN-major), 128 x 256 tiles ordered so
+//                 that the two halves of a class block run side by side (dcos tile fetched from HBM once);
+//                 epilogue applies (dWn - Wn * rdot) / ||W|| and streams fp32 rows out through TMA.
 // Everything runs on the caller's stream; no allocation, no host sync.
 #include <cmath>
 
