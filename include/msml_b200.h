@@ -94,8 +94,9 @@ int msml_fm_mask_bwd(const void* dout, const void* yf, const void* m, void* dyf,
  *      (C / width) dividing 256.  dadd (nullable, same layout as x) is added to dx: the gradient that reaches x
  *      through its OTHER consumer (the skip connection of ref iresnet.py:56-67: `identity = x; out = bn1(x)`),
  *      which autograd would otherwise add in a separate pass.
- * Training-mode fwd and bwd are ONE cooperative launch each (slab statistics -> grid barrier -> finalize ->
- * grid barrier -> apply); the device must support cooperative launches (every sm_100 part does).
+ * Training-mode fwd and bwd are three plain launches each (slab statistics, per-channel finalize, apply), the last two
+ * with programmatic dependent launch; all of them are enqueued on `stream` by one call.  (MSML_BN_FUSED=1 in the
+ * environment selects the single cooperative launch with two grid barriers that these replaced; it is slower.)
  * ------------------------------------------------------------------------------------------ */
 size_t msml_bn_workspace(int64_t P, int64_t C);
 int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
