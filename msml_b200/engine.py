@@ -20,8 +20,9 @@ and runs it the B200 way:
     overhead; the next batch's host-to-device copy runs under the current step (``prefetch``).
 
 Limits of the captured mode (documented, checked): PartialFC sample_rate must be 1 (sampling needs
-a data-dependent allocation), learning rates are baked in at capture time (call ``recapture()``
-after changing them).  ``use_graph=False`` runs the identical step eagerly.
+a data-dependent allocation).  With ``fused=True`` optimizers the learning rates are turned into device tensors
+at capture time, so torch LR schedulers keep working across replays; with other optimizers, and for momentum /
+weight decay, the values are baked in (call ``recapture()`` after changing them).  ``use_graph=False`` runs the identical step eagerly.
 """
 import torch
 import torch.distributed as dist
@@ -214,12 +215,28 @@ class TrainStep:
                     if st.get("momentum_buffer") is not None:
                         st["momentum_buffer"].zero_()
 
+    def _make_lr_capturable(self):
+        """Learning rates become 0-dim device tensors: the captured optimizer kernels read them from memory, and torch's LR
+        schedulers update a tensor lr in place (``param_group["lr"].fill_``), so a schedule that steps every iteration
+        (ref train.py:193-197, 238) works across replays without recapturing."""
+        for opt in (self.opt_backbone, self.opt_pfc):
+            if opt is None:
+                continue
+            for g in opt.param_groups:
+                if not g.get("fused"):
+                    continue        # only torch's fused kernels take a tensor lr without a host read (illegal while capturing)
+                if not isinstance(g["lr"], torch.Tensor):
+                    g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=self.device)
+                elif g["lr"].device != self.device:
+                    g["lr"] = g["lr"].to(self.device)
+
     def recapture(self, preserve_state=True):
         """Three eager warm-up steps on noise (lazy state: momentum buffers, cuDNN autotuning, workspaces), then the
         capture.  The warm-up and the capture pass train on noise, so model / optimizer state is snapshotted before
         and restored afterwards unless preserve_state is False."""
         self._prepare()
         self.graph = None
+        self._make_lr_capturable()
         had_momentum = any(st.get("momentum_buffer") is not None for st in self.opt_backbone.state.values())
         snap = self._snapshot() if preserve_state else None
         mom_snap = ([st["momentum_buffer"].clone() for st in self.opt_backbone.state.values() if st.get("momentum_buffer") is not None]

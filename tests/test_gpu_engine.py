@@ -21,7 +21,7 @@ def _build(seed=3, classes=1000, B=8, fp16=False, fused=None):
     net = net.cuda().train()
     pfc = PartialFC(0, 0, 1, B, False, ArcFace(64.0, 0.5), classes)
     opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4, fused=fused)
-    opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.01, momentum=0.9, weight_decay=5e-4)
+    opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.01, momentum=0.9, weight_decay=5e-4, fused=fused)
     return net, pfc, opt, opt_pfc
 
 
@@ -209,3 +209,40 @@ def test_prefetched_inputs_give_the_same_step(use_graph):
         out[mode] = losses
     for a, b in zip(out["direct"], out["prefetch"]):
         assert abs(a - b) <= 1e-2 * abs(a), out
+
+
+def test_lr_schedule_is_honoured_by_the_captured_graph():
+    """The captured step reads the learning rate from a device tensor: a torch LR scheduler that sets it to zero must
+    freeze the weights on the next replay, and restoring it must move them again (ref train.py steps its LambdaLR
+    every iteration)."""
+    need_gpu()
+    from msml_b200.engine import TrainStep
+    B = 8
+    g = torch.Generator(device="cuda").manual_seed(23)
+    img = torch.randn(B, 3, 112, 112, device="cuda", generator=g)
+    label = torch.randint(0, 1000, (B,), device="cuda", generator=g)
+    net, pfc, opt, opt_pfc = _build(fp16=True, fused=True)
+    step = TrainStep(net, pfc, opt, opt_pfc, (B, 3, 112, 112), use_graph=True)
+    step(img, label)                                   # captures; lr is now a device tensor
+    assert isinstance(opt.param_groups[0]["lr"], torch.Tensor) and opt.param_groups[0]["lr"].is_cuda
+    factors = [1.0, 0.0, 1.0]
+    sch = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: factors[min(s, 2)])
+    sch_pfc = torch.optim.lr_scheduler.LambdaLR(opt_pfc, lambda s: factors[min(s, 2)])
+    w = lambda: (net.frb.layer2[0].conv1.weight.detach().clone(), pfc.weight.detach().clone())
+    w0 = w()
+    step(img, label)
+    w1 = w()
+    assert not torch.equal(w0[0], w1[0]) and not torch.equal(w0[1], w1[1])
+    sch.step(); sch_pfc.step()                         # factor 0: lr tensors filled with 0 in place
+    assert float(opt.param_groups[0]["lr"]) == 0.0
+    for st in opt.state.values():                      # momentum would still move the weights: clear it for the check
+        if st.get("momentum_buffer") is not None:
+            st["momentum_buffer"].zero_()
+    pfc.weight_mom.zero_()
+    step(img, label)
+    w2 = w()
+    assert torch.equal(w1[0], w2[0]) and torch.equal(w1[1], w2[1])
+    sch.step(); sch_pfc.step()                         # factor 1 again
+    step(img, label)
+    w3 = w()
+    assert not torch.equal(w2[0], w3[0]) and not torch.equal(w2[1], w3[1])
