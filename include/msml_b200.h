@@ -79,6 +79,19 @@ int msml_fm_mask_bwd(const void* dout, const void* yf, const void* m, void* dyf,
                      int64_t B, int64_t H, int64_t W, int64_t C, int64_t Hm, int64_t Wm, int64_t Cm,
                      int dtype, int act, int arith, void* stream);
 
+/* K-C  input assembly of the FM operator: channel concat + zero pad over NHWC tensors viewed as (P = N*H*W) pixel rows.
+ *   ref backbones/fm/fmoperator.py:277-279   x = torch.cat((yf, yo), dim=1)  -> same_conv
+ * fwd: cat (P, Ct) = [ yf (P, C) | yo (P, Co) | zeros ], Ct >= C + Co.  C and Ct are multiples of the 16-byte vector
+ *      width (8 for bf16 / fp16, 4 for fp32); Co is arbitrary (the 18 occlusion maps).  All tensors share `dtype`.
+ * bwd: dyf (P, C) = dcat[:, 0:C] [+ dadd]   where dadd (nullable, (P, C)) is the gradient reaching yf through its other
+ *      consumer (the fused tail, msml_fm_gate_bwd): the sum autograd would do in one more pass over a strided slice.
+ *      dyo (nullable, (P, Co)) = dcat[:, C:C+Co].
+ * One launch each; replaces three strided ATen copy kernels (fwd) and a strided add (bwd). */
+int msml_fm_cat_fwd(const void* yf, const void* yo, void* cat, int64_t P, int64_t C, int64_t Co, int64_t Ct,
+                    int dtype, void* stream);
+int msml_fm_cat_bwd(const void* dcat, const void* dadd /*nullable*/, void* dyf, void* dyo /*nullable*/,
+                    int64_t P, int64_t C, int64_t Co, int64_t Ct, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K-N  fused BatchNorm (+ residual add) (+ PReLU) over an NHWC tensor viewed as (P = N*H*W, C):
  *        y = prelu( (x - mean) * invstd * gamma + beta [+ res] )

@@ -126,7 +126,7 @@ class FMCnn(nn.Module):
     def forward(self, yf, yo, yt=None):
         """yf (B,C,H,W) face features, yo (B,18,H,W) occlusion maps, yt peer features (train only)
         -> (Z_f with the shape of yf, l2 distillation loss or None)."""
-        x, pad = ops.cat_channels_padded((yf, yo.to(yf.dtype)))        # C+18 channels, zero-padded to a multiple of 8
+        x, pad, yf = ops.fm_cat(yf, yo)        # C+18 channels zero-padded to a multiple of 8 (K-C); yf for the tail
         z = self.res_block(ops.conv2d_padded_in(x, self.same_conv, pad))
         f_out, l2 = None, None
         if self.use_ori or self.en_save:

@@ -102,6 +102,68 @@ def fm_gate_multi_bwd(douts, yfs, zs, act="sigmoid", arith="mul"):
     return dyfs, dzs
 
 
+# --------------------------------------------------------------------------------------------
+# K-C  input assembly of the FM operator: cat(yf, yo) + zero pad     ref backbones/fm/fmoperator.py:277-279
+# --------------------------------------------------------------------------------------------
+def _fm_cat_launch(yf_d, yo_d, multiple):
+    B, C, H, W = yf_d.shape
+    Co = yo_d.shape[1]
+    Ct = -(-(C + Co) // multiple) * multiple
+    cat = torch.empty((B, Ct, H, W), dtype=yf_d.dtype, device=yf_d.device, memory_format=torch.channels_last)
+    check(load().msml_fm_cat_fwd(_ptr(yf_d), _ptr(yo_d), _ptr(cat), B * H * W, C, Co, Ct, dtype_code(yf_d.dtype), stream_ptr()))
+    return cat, Ct - C - Co
+
+
+class _FMCat(torch.autograd.Function):
+    """(cat(yf, yo, zeros), yf): yf has two consumers inside the FM operator, this concat and the fused tail.  The second
+    output is yf itself for the tail; the backward kernel then adds the tail's gradient while it gathers the yf columns of
+    the concat's gradient, instead of autograd adding a strided slice in one more pass (same idea as bn_act_fork)."""
+
+    @staticmethod
+    def forward(ctx, yf, yo, multiple):
+        yf_d = yf.contiguous(memory_format=torch.channels_last)
+        yo_d = yo.to(yf.dtype).contiguous(memory_format=torch.channels_last)
+        cat, _ = _fm_cat_launch(yf_d, yo_d, multiple)
+        ctx.cfg = (tuple(yf.shape), yo.shape[1], cat.shape[1], yo.dtype)
+        ctx.set_materialize_grads(False)
+        return cat, yf_d.view_as(yf_d)
+
+    @staticmethod
+    def backward(ctx, dcat, dtail):
+        (B, C, H, W), Co, Ct, yo_dtype = ctx.cfg
+        if dcat is None:
+            return dtail, None, None
+        d = dcat.contiguous(memory_format=torch.channels_last)
+        dyf = torch.empty((B, C, H, W), dtype=d.dtype, device=d.device, memory_format=torch.channels_last)
+        dadd = _dense_like(dyf, dtail) if dtail is not None else None
+        dyo = (torch.empty((B, Co, H, W), dtype=d.dtype, device=d.device, memory_format=torch.channels_last)
+               if ctx.needs_input_grad[1] else None)
+        check(load().msml_fm_cat_bwd(_ptr(d), _ptr(dadd), _ptr(dyf), _ptr(dyo), B * H * W, C, Co, Ct, dtype_code(d.dtype),
+                                     stream_ptr()))
+        return dyf, (dyo.to(yo_dtype) if dyo is not None else None), None
+
+
+def fm_cat(yf, yo, multiple=8):
+    """-> (x, pad, yf_tail): x = cat((yf, yo), dim=1) with `pad` zero channels appended up to a multiple of ``multiple``
+    (cuDNN's bf16 tensor-core kernels need C % 8 == 0), one kernel each way; yf_tail is yf for the operator's fused tail
+    (see _FMCat).  Channel counts the vector kernel does not take go through cat_channels_padded."""
+    if yf.dim() != 4 or yo.dim() != 4 or yf.shape[0] != yo.shape[0] or yf.shape[2:] != yo.shape[2:]:
+        raise ValueError("fm_cat: yf %s and yo %s must agree in batch and spatial size" % (tuple(yf.shape), tuple(yo.shape)))
+    vn = 4 if yf.dtype == torch.float32 else 8
+    if not yf.is_cuda or yf.shape[1] % vn or multiple % vn:
+        x, pad = cat_channels_padded((yf, yo.to(yf.dtype)), multiple)
+        return x, pad, yf
+    require_cuda(yf, yo)
+    C, Co = yf.shape[1], yo.shape[1]
+    pad = (-(C + Co)) % multiple
+    if torch.is_grad_enabled() and (yf.requires_grad or yo.requires_grad):
+        x, yf_tail = _FMCat.apply(yf, yo, multiple)
+        return x, pad, yf_tail
+    yf_d = yf.contiguous(memory_format=torch.channels_last)
+    x, pad = _fm_cat_launch(yf_d, yo.to(yf.dtype).contiguous(memory_format=torch.channels_last), multiple)
+    return x, pad, yf_d
+
+
 # Extension (north_star): low-resolution / single-channel mask, NHWC.
 class _FMMask(torch.autograd.Function):
     @staticmethod

@@ -101,6 +101,68 @@ def test_fm_gate_linearity_at_full_size():
     assert (a.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("C,Co,H,W", [(64, 18, 9, 7), (128, 18, 5, 5), (512, 18, 7, 7), (8, 3, 4, 3), (16, 8, 3, 5)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_fm_cat_matches_concat(C, Co, H, W, dtype):
+    """K-C (ref fmoperator.py:277-279): cat(yf, yo) + zero pad is a pure copy -> bit-exact against numpy's concatenate;
+    backward = column slice of the concat's gradient + the tail's gradient, summed in fp32 and rounded once."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(11)
+    B = 3
+    yf0 = torch.randn(B, C, H, W, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    yo0 = torch.randn(B, Co, H, W, device="cuda")                       # fp32 NCHW, as the OSB emits outside autocast
+    yf = yf0.clone().requires_grad_(True)
+    yo = yo0.clone().requires_grad_(True)
+    x, pad, yf_tail = ops.fm_cat(yf, yo)
+    Ct = x.shape[1]
+    assert Ct % 8 == 0 and pad == Ct - C - Co and 0 <= pad < 8
+    assert x.is_contiguous(memory_format=torch.channels_last)
+    want = np.concatenate([host(yf0), host(yo0.to(dtype)), np.zeros((B, pad, H, W))], axis=1)
+    assert np.array_equal(host(x), want)
+    assert torch.equal(yf_tail, yf0)
+    dcat = torch.randn(B, Ct, H, W, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    dtail = torch.randn(B, C, H, W, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    torch.autograd.backward([x, yf_tail], [dcat, dtail])
+    want_dyf = (dcat[:, :C].float().cpu() + dtail.float().cpu()).to(dtype)
+    assert torch.equal(yf.grad.cpu(), want_dyf)
+    assert yo.grad.dtype == torch.float32
+    assert torch.equal(yo.grad.cpu(), dcat[:, C:C + Co].float().cpu())
+    # only one of the two consumers carries a gradient
+    yf = yf0.clone().requires_grad_(True)
+    x, _, yf_tail = ops.fm_cat(yf, yo0)
+    x.backward(dcat)
+    assert torch.equal(yf.grad, dcat[:, :C])
+    yf = yf0.clone().requires_grad_(True)
+    x, _, yf_tail = ops.fm_cat(yf, yo0)
+    yf_tail.backward(dtail)
+    assert torch.equal(yf.grad, dtail)
+    # no autograd: same forward, yf handed through
+    with torch.no_grad():
+        x2, pad2, t2 = ops.fm_cat(yf0, yo0)
+    assert torch.equal(x2, x) and pad2 == pad and torch.equal(t2, yf0)
+
+
+def test_fm_cat_full_size_and_argument_errors():
+    """Stage-1 shape of BASELINE config 3 (128 x 64 x 56 x 56 + 18 maps): column checks on the device; bad shapes raise."""
+    need_gpu()
+    from msml_b200 import _lib, ops
+    torch.manual_seed(12)
+    yf = torch.randn(128, 64, 56, 56, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    yo = torch.randn(128, 18, 56, 56, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x, pad, _ = ops.fm_cat(yf, yo)
+    assert x.shape == (128, 88, 56, 56) and pad == 6
+    assert torch.equal(x[:, :64], yf) and torch.equal(x[:, 64:82], yo) and not x[:, 82:].any()
+    with pytest.raises(ValueError):
+        ops.fm_cat(yf, yo[:, :, :28])
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.msml_fm_cat_fwd(yf.data_ptr(), yo.data_ptr(), x.data_ptr(), 10, 64, 18, 80, _lib.BF16, st) != 0    # Ct < C + Co
+    assert b"smaller" in lib.msml_last_error()
+    assert lib.msml_fm_cat_fwd(yf.data_ptr(), yo.data_ptr(), x.data_ptr(), 10, 60, 18, 88, _lib.BF16, st) != 0    # C % 8
+    assert lib.msml_fm_cat_bwd(None, None, x.data_ptr(), None, 10, 64, 18, 88, _lib.BF16, st) != 0                # null dcat
+
+
 @pytest.mark.parametrize("Cm,Hm,Wm", [(1, 8, 6), (1, 4, 3), (64, 8, 6), (64, 4, 3)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_fm_mask_resize_broadcast_extension(Cm, Hm, Wm, dtype):
@@ -274,6 +336,7 @@ def test_padded_channel_paths_match_unpadded(monkeypatch):
     with torch.no_grad():
         f1, s1 = net(x)
         monkeypatch.setattr(ops, "cat_channels_padded", lambda parts, multiple=8: (torch.cat(list(parts), 1), 0))
+        monkeypatch.setattr(ops, "fm_cat", lambda yf, yo, multiple=8: (torch.cat([yf, yo.to(yf.dtype)], 1), 0, yf))
         monkeypatch.setattr(unet_mod.Unet, "pad_channels", False)
         f2, s2 = net(x)
     cos = torch.nn.functional.cosine_similarity(f1.double(), f2.double())
