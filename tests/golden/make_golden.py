@@ -156,6 +156,59 @@ def gen_dap():
     save("dap", x=x, y=y, dy=dy, dx=x.grad, mask=mask)
 
 
+# --------------------------------------------------------------------------- segmentation criterion
+def consensus_cases():
+    """(name, logit, blobs, target, (alpha, beta, reduce_pixel, reduce_pixel_kl)); deterministic (numpy default_rng(0))."""
+    rng = np.random.default_rng(0)
+    cases = []
+    N, C, H, W = 3, 2, 12, 12           # ref train.py:258 usage: blobs == target == binary occlusion mask; sample 2 lacks blob 1
+    logit = (rng.normal(size=(N, C, H, W)) * 2).astype(np.float32)
+    msk = (rng.random((N, H, W)) < 0.3).astype(np.int64)
+    msk[2] = 0
+    cases.append(("binary_missing", logit, msk, msk, (10.0, 5.0, "idx", "idx")))
+    N, C, H, W = 2, 4, 5, 7             # connected-component ids that are not 0..K-1, labels differ from ids
+    logit = rng.normal(size=(N, C, H, W)).astype(np.float32)
+    ids = np.array([0, 3, 5, 9])
+    bl = ids[rng.integers(0, 4, size=(N, H, W))]
+    tg = np.vectorize({0: 1, 3: 0, 5: 3, 9: 1}.get)(bl)
+    cases.append(("four_blobs", logit, bl, tg, (10.0, 5.0, "idx", "idx")))
+    cases.append(("four_blobs_all_all", logit, bl, tg, (10.0, 5.0, "all", "all")))
+    cases.append(("four_blobs_idx_all", logit, bl, tg, (3.0, 0.7, "idx", "all")))
+    N, C, H, W = 2, 2, 6, 6             # fp32 softmax underflow: p == 0 entries leave the KL term (ref :153-158)
+    logit = rng.normal(size=(N, C, H, W)).astype(np.float32)
+    logit[0, 0, :2] += 120
+    logit[1, 1, 3] -= 200
+    msk = (rng.random((N, H, W)) < 0.5).astype(np.int64)
+    cases.append(("underflow", logit, msk, msk, (10.0, 5.0, "idx", "idx")))
+    N, C, H, W = 4, 2, 112, 112         # the shape of final_seg, (N, 1, H, W) masks
+    logit = rng.normal(size=(N, C, H, W)).astype(np.float32)
+    msk = np.zeros((N, 1, H, W), np.int64)
+    for n in range(N):                  # one rectangular occluder per image, as RandomBlock draws them
+        h0, w0 = rng.integers(0, 70, size=2)
+        msk[n, 0, h0:h0 + 20 + 10 * n, w0:w0 + 30] = 1
+    cases.append(("seg_shape", logit, msk, msk[:, 0], (10.0, 5.0, "idx", "idx")))
+    return cases
+
+
+def gen_consensus():
+    import logging
+    from tricks.consensus_loss import StructureConsensuLossFunction
+    logging.getLogger("tricks.consensus_loss").setLevel(logging.WARNING)
+    out = {}
+    for name, logit, blobs, target, cfg in consensus_cases():
+        crit = StructureConsensuLossFunction(*cfg)
+        lt = torch.tensor(logit, requires_grad=True)
+        loss = crit(lt, torch.tensor(blobs), torch.tensor(target))      # ref tricks/consensus_loss.py:177-178
+        loss.backward()
+        out[name + ".logit"] = logit
+        out[name + ".blobs"] = blobs.astype(np.int16)
+        out[name + ".target"] = target.astype(np.int16)
+        out[name + ".cfg"] = np.array([str(c) for c in cfg])
+        out[name + ".loss"] = np.float64(loss.item())
+        out[name + ".dlogit"] = lt.grad.numpy()
+    save("consensus", **out)
+
+
 # --------------------------------------------------------------------------- margin heads
 def gen_margins():
     from headers.margin_losses import AMArcFace, AMCosFace, Softmax
@@ -369,7 +422,7 @@ def gen_model():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fm", "fm_peer", "dap", "margins", "pfc", "model"]
+    which = sys.argv[1:] or ["fm", "fm_peer", "dap", "margins", "pfc", "model", "consensus"]
     seeds()
     for w in which:
         globals()["gen_" + w]()

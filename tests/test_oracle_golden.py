@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import load_golden
-from oracle import dap, fm_tail, margins, partial_fc
+from oracle import consensus, dap, fm_tail, margins, partial_fc
 
 FM = ["fm_c64_sigmoid_mul", "fm_c128_tanh_add", "fm_c64_sigmoid_div", "fm_c256_tanh_sub",
       "fm_c512_sigmoid_mul"]
@@ -129,3 +129,45 @@ def test_model_cpu_matches_reference():
     loss.backward()
     for key in ("frb.conv1.weight", "frb.layer4.1.bn3.weight", "osb.deconv5.weight"):
         close(sd[key].grad, g["grad." + key], 2e-3, 2e-3 * float(np.abs(g["grad." + key]).max()))
+
+
+CONSENSUS = ["binary_missing", "four_blobs", "four_blobs_all_all", "four_blobs_idx_all", "underflow", "seg_shape"]
+
+
+def consensus_case(g, name):
+    alpha, beta, rp, rkl = [str(v) for v in g[name + ".cfg"]]
+    return g[name + ".logit"], g[name + ".blobs"].astype(np.int64), g[name + ".target"].astype(np.int64), \
+        (float(alpha), float(beta), rp, rkl)
+
+
+@pytest.mark.parametrize("name", CONSENSUS)
+def test_consensus_loss_matches_reference(name):
+    """ref tricks/consensus_loss.py:63-178 run by make_golden.py (loss and autograd gradient)."""
+    g = load_golden("consensus")
+    logit, blobs, target, cfg = consensus_case(g, name)
+    # the reference's `p != 0` pattern is that of an fp32 softmax; only the underflow case depends on it
+    loss, dz = consensus.consensus_loss(logit, blobs, target, *cfg, softmax_dtype=np.float32 if name == "underflow" else np.float64)
+    assert abs(loss - float(g[name + ".loss"])) <= 2e-6 * abs(float(g[name + ".loss"]))
+    close(dz, g[name + ".dlogit"], 2e-4, 1e-6 * float(np.abs(g[name + ".dlogit"]).max()))
+
+
+def test_consensus_loss_gradient_is_the_derivative():
+    """Central differences of the oracle's own forward (fp64): pins the closed-form gradient independently of autograd."""
+    rng = np.random.default_rng(5)
+    logit = rng.normal(size=(2, 3, 4, 5))
+    blobs = rng.integers(0, 3, size=(2, 4, 5))
+    blobs[1][blobs[1] == 2] = 0                     # blob 2 is missing from sample 1
+    target = np.array([2, 0, 1])[blobs]
+    for cfg in ((10.0, 5.0, "idx", "idx"), (2.0, 3.0, "all", "all")):
+        # 'all' on the first term has no defined gradient for a sample that lacks a blob (the reference yields NaN): merge blob 2 away
+        blobs_c = np.where(blobs == 2, 0, blobs) if cfg[2] == "all" else blobs
+        target_c = np.array([2, 0, 1])[blobs_c]
+        _, dz = consensus.consensus_loss(logit, blobs_c, target_c, *cfg)
+        num = np.zeros_like(logit)
+        eps = 1e-6
+        for i in np.ndindex(*logit.shape):
+            zp = logit.copy(); zp[i] += eps
+            zm = logit.copy(); zm[i] -= eps
+            num[i] = (consensus.consensus_loss(zp, blobs_c, target_c, *cfg, want_grad=False)[0]
+                      - consensus.consensus_loss(zm, blobs_c, target_c, *cfg, want_grad=False)[0]) / (2 * eps)
+        close(dz, num, 1e-5, 1e-8)
