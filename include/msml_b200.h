@@ -92,6 +92,23 @@ int msml_fm_cat_fwd(const void* yf, const void* yo, void* cat, int64_t P, int64_
 int msml_fm_cat_bwd(const void* dcat, const void* dadd /*nullable*/, void* dyf, void* dyo /*nullable*/,
                     int64_t P, int64_t C, int64_t Co, int64_t Ct, int dtype, void* stream);
 
+/* K-S  structure-via-consensus segmentation criterion.
+ *   ref tricks/consensus_loss.py:63-178  StructureConsensuLossFunction(alpha, beta, reduce_pixel, reduce_pixel_kl)
+ *   .forward(logit, blobs, target), used as seg_criterion(final_seg, msk, msk) in ref train.py:228-229,258.
+ * logit (N, C, H*W) in `dtype`, NCHW (channels_last = 0) or NHWC (1), 2 <= C <= 4; blobs / target (N, H*W) int64, blob
+ * ids in [0, K), K <= 32, or -1 for a pixel that belongs to no blob (any other id, labels that differ inside a blob, or
+ * a label outside [0, C) make the loss NaN).  fwd: one pass over the logits + a one-CTA finalize; writes the scalar loss (device) and `coef`
+ * (2*K*N*C floats, device) that bwd needs.  bwd: dlogit = gout * dloss/dlogit (gout: device scalar, nullable = 1),
+ * one elementwise pass.  reduce_*_all != 0 selects the reference's 'all' normalisations ('idx' otherwise); with
+ * reduce_pixel_all a sample that lacks a blob gets a zero gradient from that blob (the reference yields NaN there). */
+size_t msml_consensus_workspace(int64_t N, int64_t C, int64_t HW, int64_t K);
+int msml_consensus_fwd(const void* logit, const int64_t* blobs, const int64_t* target, int64_t N, int64_t C, int64_t HW,
+                       int64_t K, int channels_last, int dtype, float alpha, float beta, int reduce_pixel_all,
+                       int reduce_kl_all, float* loss, float* coef, void* ws, size_t ws_bytes, void* stream);
+int msml_consensus_bwd(const void* logit, const int64_t* blobs, const float* coef, const float* gout /*nullable*/,
+                       void* dlogit, int64_t N, int64_t C, int64_t HW, int64_t K, int channels_last, int dtype,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K-N  fused BatchNorm (+ residual add) (+ PReLU) over an NHWC tensor viewed as (P = N*H*W, C):
  *        y = prelu( (x - mean) * invstd * gamma + beta [+ res] )

@@ -42,6 +42,10 @@ SIGNATURES = {
     "msml_fm_mask_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p] + [c_i64] * 7 + [c_int, c_int, c_int, c_p]),
     "msml_fm_cat_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
     "msml_fm_cat_bwd": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
+    "msml_consensus_workspace": (c_size, [c_i64, c_i64, c_i64, c_i64]),
+    "msml_consensus_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, ctypes.c_float, ctypes.c_float,
+                                   c_int, c_int, c_p, c_p, c_p, c_size, c_p]),
+    "msml_consensus_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_p]),
     "msml_bn_workspace": (c_size, [c_i64, c_i64]),
     "msml_bn_fwd": (c_int, [c_p] * 11 + [c_i64, c_i64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_p, c_size, c_p]),
     "msml_bn_bwd": (c_int, [c_p] * 14 + [c_i64, c_i64, c_int, c_int, c_int, c_p, c_size, c_p]),

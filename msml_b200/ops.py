@@ -362,6 +362,54 @@ def dap_with_mask(x, k=3):
 
 
 # --------------------------------------------------------------------------------------------
+# K-S  structure-via-consensus segmentation criterion          ref tricks/consensus_loss.py:63-178
+# --------------------------------------------------------------------------------------------
+class _Consensus(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logit, blobs, target, alpha, beta, pixel_all, kl_all, K):
+        lib = load()
+        N, C, H, W = logit.shape
+        z = _dense(logit)
+        cl = z.is_contiguous(memory_format=torch.channels_last) and not z.is_contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        coef = torch.empty(2 * K * N * C, dtype=torch.float32, device=z.device)
+        ws_bytes = lib.msml_consensus_workspace(N, C, H * W, K)
+        ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=z.device)
+        check(lib.msml_consensus_fwd(_ptr(z), _ptr(blobs), _ptr(target), N, C, H * W, K, int(cl), dtype_code(z.dtype),
+                                     float(alpha), float(beta), int(pixel_all), int(kl_all), _ptr(loss), _ptr(coef), _ptr(ws),
+                                     ws_bytes, stream_ptr()))
+        ctx.save_for_backward(z, blobs, coef)
+        ctx.cfg = (K, cl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        z, blobs, coef = ctx.saved_tensors
+        K, cl = ctx.cfg
+        N, C, H, W = z.shape
+        g = gout.to(torch.float32).contiguous()
+        dz = torch.empty_like(z)
+        check(load().msml_consensus_bwd(_ptr(z), _ptr(blobs), _ptr(coef), _ptr(g), _ptr(dz), N, C, H * W, K, int(cl),
+                                        dtype_code(z.dtype), stream_ptr()))
+        return dz, None, None, None, None, None, None, None
+
+
+def consensus_loss(logit, blobs, target, alpha=10.0, beta=5.0, reduce_pixel="idx", reduce_pixel_kl="idx", num_blobs=2):
+    """Structure-via-consensus loss of ref tricks/consensus_loss.py: logit (N, C, H, W), 2 <= C <= 4; blobs (N, 1, H, W)
+    or (N, H, W) with integer ids in [0, num_blobs) (-1: pixel of no blob); target (N, H, W) labels -> 0-dim fp32 loss."""
+    require_cuda(logit, blobs, target)
+    if logit.dim() != 4:
+        raise ValueError("consensus_loss expects logits of shape (N, C, H, W)")
+    N, C, H, W = logit.shape
+    if blobs.numel() != N * H * W or target.numel() != N * H * W:
+        raise ValueError("consensus_loss: blobs %s / target %s do not match logits %s" % (tuple(blobs.shape), tuple(target.shape),
+                                                                                         tuple(logit.shape)))
+    b = blobs.reshape(N, H * W).to(torch.int64).contiguous()
+    t = target.reshape(N, H * W).to(torch.int64).contiguous()
+    return _Consensus.apply(logit, b, t, alpha, beta, reduce_pixel == "all", reduce_pixel_kl == "all", int(num_blobs))
+
+
+# --------------------------------------------------------------------------------------------
 # tcgen05 GEMM + in-model margin heads          ref headers/margin_losses.py:275-303,390-418
 # --------------------------------------------------------------------------------------------
 def _pad_k(t):

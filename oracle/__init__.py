@@ -20,6 +20,7 @@ Modules
   dap          DAP (PixelShuffle+AvgPool)      ref backbones/osb/unet.py:158-161,223
   margins      AMArcFace / AMCosFace / Softmax ref headers/margin_losses.py:41-68,241-305,356-418
   partial_fc   PartialFC sharding/sample/step  ref headers/partial_fc.py:19-177
+  consensus    structure-via-consensus seg loss ref tricks/consensus_loss.py:63-178
   model_cpu    torch-CPU fp32 MSML backbone    ref backbones/{msml,frb/iresnet,osb/unet,fm/fmoperator}.py
   detfill      deterministic weight fill shared by the golden generator and tests
 """

@@ -27,11 +27,12 @@ def _softmax(z):
 
 
 def consensus_loss(logit, blobs, target, alpha=10.0, beta=5.0, reduce_pixel="idx", reduce_pixel_kl="idx",
-                   want_grad=True, softmax_dtype=np.float64):
+                   want_grad=True, softmax_dtype=np.float64, ids=None):
     """logit (N, C, H, W); blobs, target (N, H, W) or (N, 1, H, W) integer-valued -> (loss, dloss/dlogit or None).
 
     ``softmax_dtype=np.float32`` reproduces the reference's `p != 0` underflow pattern exactly (the test that needs it
-    says so); everything else is fp64."""
+    says so); everything else is fp64.  ``ids`` restricts the blobs that are evaluated (default: every value present,
+    ref :84; `ids=[s]` is the reference's per-blob method, ref :98-171)."""
     z = np.asarray(logit, np.float64)
     N, C, H, W = z.shape
     bl = np.asarray(blobs).reshape(N, H, W)
@@ -40,7 +41,7 @@ def consensus_loss(logit, blobs, target, alpha=10.0, beta=5.0, reduce_pixel="idx
         p = _softmax(np.asarray(logit, np.float32)).astype(np.float64)
     else:
         p = _softmax(z)
-    ids = np.unique(bl)
+    ids = np.unique(bl) if ids is None else np.asarray(ids)
     total = 0.0
     grad_p = np.zeros_like(p)
     for s in ids:
