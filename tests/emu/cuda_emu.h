@@ -1,0 +1,118 @@
+// Minimal CPU emulation of the CUDA execution model, for LOGIC checks of msml_b200 kernels without a GPU.
+// TEST INFRASTRUCTURE ONLY.  A kernel header is compiled for the host with g++ (this file included first) and each
+// CTA is executed by blockDim.x OS threads: __syncthreads is a barrier over the CTA, warp shuffles exchange values
+// through a per-warp buffer, __shared__ variables are function-local statics (CTAs run one after another).
+// What this does NOT check: memory-model races, alignment rules of vector accesses, launch limits, performance.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __forceinline__
+#undef __launch_bounds__
+#undef __shared__
+#undef __grid_constant__
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __grid_constant__
+
+namespace cuda_emu {
+struct Cta {
+  std::barrier<> all;
+  std::vector<std::unique_ptr<std::barrier<>>> warp;
+  std::vector<uint64_t> xchg;          // one 8-byte slot per thread
+  std::atomic<int> vote{0};
+  explicit Cta(int threads) : all(threads), xchg(threads) {
+    for (int w = 0; w < (threads + 31) / 32; ++w) {
+      const int n = threads - w * 32 < 32 ? threads - w * 32 : 32;
+      warp.emplace_back(new std::barrier<>(n));
+    }
+  }
+};
+inline thread_local Cta* cta = nullptr;
+}  // namespace cuda_emu
+
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+
+inline void __syncthreads() { cuda_emu::cta->all.arrive_and_wait(); }
+inline int __syncthreads_or(int pred) {
+  cuda_emu::Cta* c = cuda_emu::cta;
+  c->all.arrive_and_wait();
+  if (threadIdx.x == 0) c->vote.store(0);
+  c->all.arrive_and_wait();
+  if (pred) c->vote.fetch_or(1);
+  c->all.arrive_and_wait();
+  return c->vote.load();
+}
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+
+template <typename V>
+inline V __shfl_xor_sync(unsigned, V v, int lane_mask) {
+  static_assert(sizeof(V) <= 8, "shuffle of up to 8 bytes");
+  cuda_emu::Cta* c = cuda_emu::cta;
+  const int t = (int)threadIdx.x, w = t >> 5;
+  uint64_t bits = 0;
+  std::memcpy(&bits, &v, sizeof(V));
+  c->xchg[t] = bits;
+  c->warp[w]->arrive_and_wait();
+  const int src = (t & ~31) | ((t & 31) ^ lane_mask);
+  const uint64_t got = src < (int)blockDim.x ? c->xchg[src] : bits;
+  c->warp[w]->arrive_and_wait();
+  V out;
+  std::memcpy(&out, &got, sizeof(V));
+  return out;
+}
+
+template <typename V> inline V __ldg(const V* p) { return *p; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
+inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }
+inline float __expf(float x) { return std::exp(x); }
+inline float __fdividef(float a, float b) { return a / b; }
+inline void __nanosleep(unsigned) {}
+
+// launch<<<grid, block>>>: CTAs one after another, threads of a CTA concurrently
+template <typename F>
+inline void emu_launch(dim3 grid, int threads, F&& body) {
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        cuda_emu::Cta cta(threads);
+        std::vector<std::thread> pool;
+        pool.reserve(threads);
+        for (int t = 0; t < threads; ++t)
+          pool.emplace_back([&, t] {
+            cuda_emu::cta = &cta;
+            threadIdx = {(unsigned)t, 0, 0};
+            blockIdx = {bx, by, bz};
+            blockDim = dim3(threads);
+            gridDim = grid;
+            body();
+          });
+        for (auto& th : pool) th.join();
+      }
+}

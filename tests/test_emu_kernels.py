@@ -1,0 +1,123 @@
+"""CUDA kernels executed under a CPU emulation of the CUDA execution model (tests/emu/cuda_emu.h): a LOGIC check that
+needs no GPU.  The kernel header is compiled for the host with g++; every CTA runs as blockDim.x OS threads with real
+barriers and warp-shuffle exchanges.  It does not replace the GPU parity tests (no memory-model, alignment or
+performance coverage); it exists so that kernels written without GPU access are not shipped unexecuted.
+
+Covered: csrc/seg_loss_kernels.cuh (consensus segmentation loss) against the reference goldens
+(tests/golden/consensus.npz) and the oracle.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import consensus
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_INC = "/usr/local/cuda/include"
+c_p, c_i64, c_int, c_f = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+F32, BF16 = 0, 1
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    out = str(tmp_path_factory.mktemp("emu") / "libemu_seg.so")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC,
+                        os.path.join(HERE, "emu", "emu_seg_loss.cpp"), "-o", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = ctypes.CDLL(out)
+    lib.emu_consensus_workspace.restype = ctypes.c_size_t
+    lib.emu_consensus_workspace.argtypes = [c_i64] * 4
+    lib.emu_consensus_fwd.argtypes = [c_p, c_p, c_p] + [c_i64] * 4 + [c_int, c_int, c_f, c_f, c_int, c_int, c_p, c_p, c_p]
+    lib.emu_consensus_bwd.argtypes = [c_p] * 5 + [c_i64] * 4 + [c_int, c_int]
+    lib.emu_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+def to_bf16_bits(a):
+    """fp32 -> bf16 bit patterns (round to nearest even), as uint16."""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
+
+
+def from_bf16_bits(b):
+    return (b.astype(np.uint32) << 16).view(np.float32)
+
+
+def run(lib, logit, blobs, target, K, alpha=10.0, beta=5.0, rp="idx", rkl="idx", cl=False, gout=1.0, dtype=F32, expect_rc=0):
+    N, C, H, W = logit.shape
+    z = np.ascontiguousarray(logit.transpose(0, 2, 3, 1) if cl else logit, np.float32)
+    zbuf = to_bf16_bits(z) if dtype == BF16 else z
+    b = np.ascontiguousarray(np.asarray(blobs).reshape(N, H * W), np.int64)
+    t = np.ascontiguousarray(np.asarray(target).reshape(N, H * W), np.int64)
+    ws = np.zeros(lib.emu_consensus_workspace(N, C, H * W, K) // 4 + 1, np.float32)
+    loss = np.zeros(1, np.float32)
+    coef = np.zeros(2 * K * N * C, np.float32)
+    rc = lib.emu_consensus_fwd(zbuf.ctypes.data, b.ctypes.data, t.ctypes.data, N, C, H * W, K, int(cl), dtype, alpha, beta,
+                               int(rp == "all"), int(rkl == "all"), loss.ctypes.data, coef.ctypes.data, ws.ctypes.data)
+    if expect_rc is None:
+        return rc
+    assert rc == expect_rc, lib.emu_last_error()
+    dbuf = np.zeros_like(zbuf)
+    g = np.array([gout], np.float32)
+    assert lib.emu_consensus_bwd(zbuf.ctypes.data, b.ctypes.data, coef.ctypes.data, g.ctypes.data, dbuf.ctypes.data, N, C, H * W, K,
+                                 int(cl), dtype) == 0
+    dz = from_bf16_bits(dbuf) if dtype == BF16 else dbuf
+    return float(loss[0]), (dz.transpose(0, 3, 1, 2) if cl else dz)
+
+
+@pytest.mark.parametrize("name,cl", [("binary_missing", False), ("binary_missing", True), ("four_blobs", False), ("four_blobs", True),
+                                     ("four_blobs_all_all", False), ("four_blobs_idx_all", True), ("underflow", False),
+                                     ("underflow", True), ("seg_shape", False)])
+def test_consensus_kernels_match_reference_golden(emu, name, cl):
+    g = load_golden("consensus")
+    alpha, beta, rp, rkl = [str(v) for v in g[name + ".cfg"]]
+    blobs = g[name + ".blobs"].astype(np.int64)
+    ids, dense = np.unique(blobs, return_inverse=True)                  # the kernels take ids 0 .. K-1
+    loss, dz = run(emu, g[name + ".logit"], dense.reshape(blobs.shape), g[name + ".target"], len(ids), float(alpha), float(beta), rp, rkl, cl)
+    want = float(g[name + ".loss"])
+    assert abs(loss - want) <= 2e-6 * abs(want), (loss, want)
+    gd = g[name + ".dlogit"]
+    np.testing.assert_allclose(dz, gd, rtol=2e-4, atol=2e-6 * np.abs(gd).max())
+
+
+def test_consensus_kernels_bf16_three_classes_ignore_and_gout(emu):
+    rng = np.random.default_rng(3)
+    N, C, H, W = 3, 3, 33, 41                                           # 1353 pixels: a ragged second chunk
+    z = from_bf16_bits(to_bf16_bits(rng.normal(size=(N, C, H, W)).astype(np.float32))).reshape(N, C, H, W)
+    blobs = rng.integers(0, 3, size=(N, H, W))
+    blobs[2][blobs[2] == 1] = 2                                         # blob 1 is missing from the last sample
+    target = np.array([2, 0, 1])[blobs]
+    want, dwant = consensus.consensus_loss(z, blobs, target, 10.0, 5.0)
+    loss, dz = run(emu, z, blobs, target, 3, gout=2.5, dtype=BF16)
+    assert abs(loss - want) <= 1e-5 * abs(want)
+    np.testing.assert_allclose(dz, 2.5 * dwant, rtol=1e-2, atol=1e-2 * np.abs(dwant).max())      # the gradient is rounded to bf16
+    # pixels of blob 2 marked -1 (member of no blob) == the loss over blobs {0, 1} only; K larger than the ids present is fine
+    ign = np.where(blobs == 2, -1, blobs)
+    want2, dwant2 = consensus.consensus_loss(z, ign, target, 10.0, 5.0, ids=[0, 1])
+    loss2, dz2 = run(emu, z, ign, target, 5)
+    assert abs(loss2 - want2) <= 2e-6 * abs(want2)
+    np.testing.assert_allclose(dz2, dwant2, rtol=2e-4, atol=2e-6 * np.abs(dwant2).max())
+    assert not dz2[np.broadcast_to((ign == -1)[:, None], dz2.shape)].any()
+
+
+def test_consensus_kernels_poison_and_argument_errors(emu):
+    rng = np.random.default_rng(4)
+    z = rng.normal(size=(2, 2, 8, 8)).astype(np.float32)
+    msk = (rng.random((2, 8, 8)) < 0.4).astype(np.int64)
+    loss, _ = run(emu, z, msk, msk, 2)
+    assert np.isfinite(loss)
+    bad = msk.copy(); bad[0, 0, 0] = 7
+    assert np.isnan(run(emu, z, bad, msk, 2)[0])                        # id outside [0, K)
+    lab = msk.copy(); lab[1, 3, 3] = 1 - lab[1, 3, 3]
+    assert np.isnan(run(emu, z, msk, lab, 2)[0])                        # labels differ inside a blob (ref :103 asserts)
+    assert np.isnan(run(emu, z, msk, msk * 5, 2)[0])                    # label outside [0, C)
+    assert run(emu, np.zeros((2, 7, 8, 8), np.float32), msk, msk, 2, expect_rc=None) != 0      # C > 4
+    assert b"classes" in emu.emu_last_error()
+    assert run(emu, z, msk, msk, 40, expect_rc=None) != 0               # K > 32
