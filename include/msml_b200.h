@@ -109,6 +109,21 @@ int msml_consensus_bwd(const void* logit, const int64_t* blobs, const float* coe
                        void* dlogit, int64_t N, int64_t C, int64_t HW, int64_t K, int channels_last, int dtype,
                        void* stream);
 
+/* K-O  sharded-weight SGD of the PartialFC head.
+ *   ref train.py:188-191,299-300 (opt_pfc.step(); module_partial_fc.update()), headers/partial_fc.py:93-94,101-104,112-115.
+ * One pass over the n_s sampled rows of the shard (row = index[r], or r when index is NULL: sample_rate 1):
+ *   d = dw[r] + weight_decay * w[row];  mom[row] = momentum * mom[row] + (1 - dampening) * d;
+ *   w[row] -= lr * (nesterov ? d + momentum * mom[row] : mom[row])          (torch.optim.SGD with an existing momentum buffer)
+ * in place in weight / weight_mom (num_local, D): the gather of ref :93-94 and the scatter of ref :101-104 disappear.
+ * lr is read from lr_dev (device scalar) when given, else taken by value.  wn_bf16 (nullable, (n_s, D)) and inv_norm
+ * (nullable, (n_s)) receive normalize(w') and 1 / max(||w'||, 1e-12), i.e. ref :115 for the NEXT step (same rows:
+ * sample_rate 1).  index entries must be distinct (they are: sorted unique sample); entries outside [0, num_local) are
+ * skipped.  D is a multiple of 128, at most 1024. */
+int msml_pfc_sgd_update(float* weight, float* weight_mom, const float* dw, const int64_t* index /*nullable*/, int64_t n_s,
+                        int64_t num_local, int64_t D, const float* lr_dev /*nullable*/, float lr, float momentum,
+                        float weight_decay, float dampening, int nesterov, void* wn_bf16 /*nullable*/,
+                        float* inv_norm /*nullable*/, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K-N  fused BatchNorm (+ residual add) (+ PReLU) over an NHWC tensor viewed as (P = N*H*W, C):
  *        y = prelu( (x - mean) * invstd * gamma + beta [+ res] )

@@ -1,8 +1,11 @@
 // Gradient plumbing kernels of the training step (SURVEY.md 8f-2 neighbourhood).
+//   msml_pfc_sgd_update   : fused momentum SGD + weight decay + in-place write-back (+ next normalised bf16 centres) on the sampled
+//     rows of the PartialFC shard; kernel and algorithm in pfc_sgd_kernels.cuh.
 //   msml_accum_bf16_multi : dst_f32[i] += float(src_bf16[i]) for up to MSML_ACCUM_MAX_SEGMENTS tensors in ONE launch.
 //     The bf16 weight gradients cuDNN returns are added into the fp32 flat-gradient views of engine.TrainStep after
 //     the backward pass: one launch instead of one mixed-dtype ATen add (a non-vectorised kernel) per weight.
 #include "common.cuh"
+#include "pfc_sgd_kernels.cuh"
 
 namespace msml {
 
@@ -82,5 +85,29 @@ extern "C" int msml_accum_bf16_multi(int nseg, float* const* dst, const void* co
     accum_bf16_multi_kernel<<<blocks, kAccThreads, 0, st>>>(segs);
     MSML_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" int msml_pfc_sgd_update(float* weight, float* weight_mom, const float* dw, const int64_t* index, int64_t n_s,
+                                   int64_t num_local, int64_t D, const float* lr_dev, float lr, float momentum, float weight_decay,
+                                   float dampening, int nesterov, void* wn_bf16, float* inv_norm, void* stream) {
+  if (int e = pfc_sgd_check(n_s, num_local, D)) return e;
+  if (n_s == 0) return 0;
+  MSML_REQUIRE(weight && weight_mom && dw, MSML_EINVAL, "null pointer");
+  MSML_REQUIRE(!nesterov || (momentum > 0.f && dampening == 0.f), MSML_EINVAL, "nesterov needs momentum > 0 and zero dampening");
+  MSML_REQUIRE(aligned16(weight) && aligned16(weight_mom) && aligned16(dw) && aligned16(wn_bf16), MSML_EALIGN,
+               "weight, weight_mom, dw and wn must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  SgdParams p{lr, momentum, weight_decay, dampening, nesterov};
+  const unsigned grid = (unsigned)((n_s + kSgdThreads / 32 - 1) / (kSgdThreads / 32));
+  __nv_bfloat16* wn = static_cast<__nv_bfloat16*>(wn_bf16);
+  MSML_PROF("pfc_sgd_update", (double)n_s * D * (20.0 + (wn ? 2.0 : 0.0)), st);
+  switch (D / 128) {
+#define MSML_SGD_CASE(V) case V: pfc_sgd_kernel<V><<<grid, kSgdThreads, 0, st>>>(weight, weight_mom, dw, index, n_s, num_local, lr_dev, p, wn, inv_norm); break;
+    MSML_SGD_CASE(1) MSML_SGD_CASE(2) MSML_SGD_CASE(3) MSML_SGD_CASE(4) MSML_SGD_CASE(5) MSML_SGD_CASE(6) MSML_SGD_CASE(7) MSML_SGD_CASE(8)
+#undef MSML_SGD_CASE
+    default: return set_error(MSML_EUNSUPPORTED, "D=%lld unsupported", (long long)D);
+  }
+  MSML_LAUNCH_CHECK();
   return 0;
 }

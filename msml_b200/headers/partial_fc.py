@@ -177,6 +177,8 @@ class PartialFC(Module):
     @torch.no_grad()
     def update(self):
         """Scatter the sampled rows back into the shard (ref :101-104)."""
+        if getattr(self, "_fused_sgd", None) is not None:
+            return          # headers.PartialFCSGD updates the shard rows in place: the gathered copies are stale, not newer
         lib = load()
         rows = self.index.numel()
         check(lib.msml_scatter_rows_f32(_ptr(self.weight_mom), _ptr(self.index), _ptr(self.sub_weight_mom), rows,

@@ -1,0 +1,73 @@
+"""Fused optimizer for the PartialFC head.
+
+The reference trains the class centres with a stock optimizer over ``module_partial_fc.parameters()`` and lets
+PartialFC swap the sampled rows in and out of it every step (ref train.py:188-191,299-300; headers/partial_fc.py:93-94
+gather, :112-114 optimizer-state surgery, :101-104 scatter back):
+
+    opt_pfc = torch.optim.SGD([{'params': module_partial_fc.parameters()}], lr=..., momentum=0.9, weight_decay=5e-4)
+    ...  opt_pfc.step(); module_partial_fc.update()
+
+``PartialFCSGD(module_partial_fc, lr=..., momentum=0.9, weight_decay=5e-4)`` is a drop-in for that optimizer: same
+hyper-parameters, same ``param_groups`` (LR schedulers work), same ``step()`` / ``zero_grad()``.  Its step is ONE kernel
+(msml_pfc_sgd_update, csrc/pfc_sgd_kernels.cuh) that applies momentum SGD with weight decay to the sampled rows
+in place in the shard (``weight`` / ``weight_mom``), so ``module_partial_fc.update()`` has nothing left to scatter and
+becomes a no-op.  Arithmetic is torch.optim.SGD's with an existing momentum buffer (PartialFC always supplies one).
+"""
+import ctypes
+
+import torch
+
+from .._lib import check, load, stream_ptr
+
+__all__ = ["PartialFCSGD"]
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class PartialFCSGD(torch.optim.Optimizer):
+    def __init__(self, module, lr, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=False):
+        if not isinstance(lr, torch.Tensor) and lr < 0.0:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if momentum < 0.0:
+            raise ValueError("Invalid momentum value: {}".format(momentum))
+        if weight_decay < 0.0:
+            raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+        for attr in ("weight", "weight_mom", "sub_weight", "num_local", "sample_rate"):
+            if not hasattr(module, attr):
+                raise TypeError("PartialFCSGD drives a PartialFC module (missing attribute %r)" % attr)
+        load()
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov)
+        super().__init__([{"params": list(module.parameters())}], defaults)
+        self.module = module
+        module._fused_sgd = self            # PartialFC.update() has nothing to scatter once this optimizer owns the update
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        m = self.module
+        dw = m.sub_weight.grad
+        if dw is None:
+            return loss
+        g = self.param_groups[-1]
+        if dw.dtype != torch.float32 or not dw.is_contiguous():
+            dw = dw.to(torch.float32).contiguous()
+        n_s, D = dw.shape
+        index = None if int(m.sample_rate) == 1 else m.index
+        if index is not None and index.numel() != n_s:
+            raise RuntimeError("PartialFCSGD: gradient has %d rows but the sample index has %d" % (n_s, index.numel()))
+        lr = g["lr"]
+        lr_dev = lr if isinstance(lr, torch.Tensor) and lr.is_cuda else None        # captured steps read it from memory
+        if lr_dev is not None and lr_dev.dtype != torch.float32:
+            raise RuntimeError("PartialFCSGD: a tensor lr must be float32")
+        check(load().msml_pfc_sgd_update(_ptr(m.weight), _ptr(m.weight_mom), _ptr(dw), _ptr(index), n_s, m.num_local, D,
+                                         _ptr(lr_dev), 0.0 if lr_dev is not None else float(lr), float(g["momentum"]),
+                                         float(g["weight_decay"]), float(g["dampening"]), int(bool(g["nesterov"])), None, None,
+                                         stream_ptr()))
+        return loss

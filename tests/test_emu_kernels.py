@@ -4,7 +4,8 @@ barriers and warp-shuffle exchanges.  It does not replace the GPU parity tests (
 performance coverage); it exists so that kernels written without GPU access are not shipped unexecuted.
 
 Covered: csrc/seg_loss_kernels.cuh (consensus segmentation loss) against the reference goldens
-(tests/golden/consensus.npz) and the oracle.
+(tests/golden/consensus.npz) and the oracle; csrc/pfc_sgd_kernels.cuh (fused PartialFC SGD) against the
+reference recipe gather -> torch.optim.SGD -> scatter (ref headers/partial_fc.py:93-94,101-104,112-114) on CPU.
 """
 import ctypes
 import os
@@ -23,15 +24,19 @@ c_p, c_i64, c_int, c_f = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c
 F32, BF16 = 0, 1
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
+def build_emu(tmp_path_factory, source):
     if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("needs g++ and the CUDA headers")
-    out = str(tmp_path_factory.mktemp("emu") / "libemu_seg.so")
+    out = str(tmp_path_factory.mktemp("emu") / ("lib" + source.replace(".cpp", ".so")))
     r = subprocess.run(["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-I" + CUDA_INC,
-                        os.path.join(HERE, "emu", "emu_seg_loss.cpp"), "-o", out], capture_output=True, text=True)
+                        os.path.join(HERE, "emu", source), "-o", out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    lib = ctypes.CDLL(out)
+    return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_seg_loss.cpp")
     lib.emu_consensus_workspace.restype = ctypes.c_size_t
     lib.emu_consensus_workspace.argtypes = [c_i64] * 4
     lib.emu_consensus_fwd.argtypes = [c_p, c_p, c_p] + [c_i64] * 4 + [c_int, c_int, c_f, c_f, c_int, c_int, c_p, c_p, c_p]
@@ -121,3 +126,66 @@ def test_consensus_kernels_poison_and_argument_errors(emu):
     assert run(emu, np.zeros((2, 7, 8, 8), np.float32), msk, msk, 2, expect_rc=None) != 0      # C > 4
     assert b"classes" in emu.emu_last_error()
     assert run(emu, z, msk, msk, 40, expect_rc=None) != 0               # K > 32
+
+
+# ------------------------------------------------------------------------------------------------ fused PartialFC SGD
+@pytest.fixture(scope="module")
+def emu_sgd(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_pfc_sgd.cpp")
+    lib.emu_pfc_sgd_update.argtypes = [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_f, c_f, c_f, c_f, c_int, c_p, c_p]
+    lib.emu_sgd_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+@pytest.mark.parametrize("D", [128, 512])
+@pytest.mark.parametrize("sampled", [False, True])
+@pytest.mark.parametrize("nesterov,dampening", [(False, 0.0), (True, 0.0), (False, 0.3)])
+def test_pfc_sgd_kernel_matches_reference_recipe(emu_sgd, D, sampled, nesterov, dampening):
+    """gather weight[index] / weight_mom[index] -> stock SGD with the supplied momentum buffer -> scatter back
+    (ref partial_fc.py:93-94,112-114,101-104 + train.py:188-191,299-300) vs ONE in-place pass of the kernel."""
+    import torch
+    torch.manual_seed(0)
+    num_local = 50
+    n_s = 21 if sampled else num_local
+    W = torch.randn(num_local, D) * 0.01
+    M = torch.randn(num_local, D) * 0.001
+    index = torch.sort(torch.randperm(num_local)[:n_s]).values if sampled else torch.arange(num_local)
+    dw = torch.randn(n_s, D) * 0.1
+    sub = torch.nn.Parameter(W[index].clone())
+    subm = M[index].clone()
+    opt = torch.optim.SGD([sub], lr=0.1, momentum=0.9, weight_decay=5e-4, dampening=dampening, nesterov=nesterov)
+    opt.state[sub]["momentum_buffer"] = subm
+    sub.grad = dw.clone()
+    opt.step()
+    Wref, Mref = W.clone(), M.clone()
+    Wref[index] = sub.data
+    Mref[index] = subm
+    w, m, g = W.numpy().copy(), M.numpy().copy(), dw.numpy().copy()
+    idx = index.numpy().copy()
+    wn = np.zeros((n_s, D), np.uint16)
+    inv = np.zeros(n_s, np.float32)
+    lr = np.array([0.1], np.float32)                                    # read through the device-scalar path
+    rc = emu_sgd.emu_pfc_sgd_update(w.ctypes.data, m.ctypes.data, g.ctypes.data, idx.ctypes.data if sampled else None, n_s, num_local, D,
+                                    lr.ctypes.data, 0.0, 0.9, 5e-4, dampening, int(nesterov), wn.ctypes.data, inv.ctypes.data)
+    assert rc == 0, emu_sgd.emu_sgd_last_error()
+    np.testing.assert_allclose(w, Wref.numpy(), rtol=2e-6, atol=1e-8)      # fma vs mul + add: a few ulps of the 1e-2 scale
+    np.testing.assert_allclose(m, Mref.numpy(), rtol=2e-6, atol=1e-8)
+    if sampled:                                                         # rows outside the sample are untouched, bit for bit
+        rest = np.setdiff1d(np.arange(num_local), idx)
+        assert np.array_equal(w[rest], W.numpy()[rest]) and np.array_equal(m[rest], M.numpy()[rest])
+    want_wn = torch.nn.functional.normalize(torch.from_numpy(w[idx])).to(torch.bfloat16).float().numpy()
+    assert np.abs(from_bf16_bits(wn) - want_wn).max() <= 2.0 ** -8 * np.abs(want_wn).max()      # at most one bf16 ulp
+    np.testing.assert_allclose(inv, 1.0 / np.linalg.norm(w[idx], axis=1), rtol=1e-6)
+
+
+def test_pfc_sgd_kernel_skips_bad_rows_and_rejects_bad_shapes(emu_sgd):
+    w = np.ones((4, 128), np.float32)
+    m = np.zeros((4, 128), np.float32)
+    g = np.ones((2, 128), np.float32)
+    idx = np.array([1, 9], np.int64)                                    # 9 is outside the shard: skipped, never dereferenced
+    assert emu_sgd.emu_pfc_sgd_update(w.ctypes.data, m.ctypes.data, g.ctypes.data, idx.ctypes.data, 2, 4, 128, None, 0.5, 0.0, 0.0, 0.0, 0,
+                                      None, None) == 0
+    assert np.allclose(w[1], 0.5) and np.array_equal(w[[0, 2, 3]], np.ones((3, 128), np.float32))
+    assert emu_sgd.emu_pfc_sgd_update(w.ctypes.data, m.ctypes.data, g.ctypes.data, None, 2, 4, 100, None, 0.5, 0.0, 0.0, 0.0, 0, None, None) != 0
+    assert b"multiples of 128" in emu_sgd.emu_sgd_last_error()
+    assert emu_sgd.emu_pfc_sgd_update(w.ctypes.data, m.ctypes.data, g.ctypes.data, None, 9, 4, 128, None, 0.5, 0.0, 0.0, 0.0, 0, None, None) != 0

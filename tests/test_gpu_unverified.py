@@ -16,11 +16,23 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.xfail(strict=False, reason="csrc/seg_loss.cu (consensus loss, SURVEY 8f-4) has never run on a GPU; oracle and goldens are pinned on CPU")
-def test_consensus_loss_kernels_first_gpu_run():
-    need_gpu()
+def run_checks(name):
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
-                        os.path.join(HERE, "unverified", "check_consensus.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(HERE, "unverified", name)], capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-2000:])
     assert r.returncode == 0
+
+
+@pytest.mark.xfail(strict=False, reason="csrc/seg_loss.cu (consensus loss, SURVEY 8f-4) has never run on a GPU; its logic is "
+                                        "checked under CPU emulation (tests/test_emu_kernels.py)")
+def test_consensus_loss_kernels_first_gpu_run():
+    need_gpu()
+    run_checks("check_consensus.py")
+
+
+@pytest.mark.xfail(strict=False, reason="csrc/pfc_sgd_kernels.cuh (fused PartialFC SGD, SURVEY 8f-2) has never run on a GPU; its "
+                                        "logic is checked under CPU emulation (tests/test_emu_kernels.py)")
+def test_fused_pfc_sgd_first_gpu_run():
+    need_gpu()
+    run_checks("check_pfc_sgd.py")
