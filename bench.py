@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            (N=1; N>1 under torch.distributed.run)
     python bench.py --impl reference --gpus N --steps K --warmup W     CPU port of the reference step
     python bench.py --workload fusion|head ...               micro-benchmarks (BASELINE configs 2 / 4)
+    python bench.py --workload aux                           FM concat, consensus loss, fused PartialFC SGD, each alone
 
 Default workload = BASELINE.json config 3: ires50_msml + PartialFC(ArcFace s=64 m=0.5, 93,431
 classes, sample_rate 1) bf16 training step, 112x112 synthetic images, batch 128 per GPU.
@@ -251,6 +252,117 @@ def head_microbench(iters=5, b_tot=1024, n_s=125000):
                 frac_of_bf16_burst_peak=round(6.0 * b_tot * n_s * 512 / (gemm_ms * 1e-3) / 1e12 / pk["tf_burst"], 4), rooflines=rl)
 
 
+def aux_microbench(iters=10):
+    """The kernels around the two hot ops, each timed alone with CUDA events (median of `iters`, inputs > L2 or rotated) next to
+    the ATen sequence it replaces on the same GPU:
+      fm_cat    FM input assembly at BASELINE config-2 shapes (B = 512, 4 scales)      vs torch.cat + strided add
+      consensus segmentation criterion on final_seg (B = 512, 2 x 112 x 112)           (no ATen twin here: the reference loops in Python)
+      pfc_sgd   fused PartialFC optimizer, config 3 at W = 1 (93,431 x 512, full) and a config-4 sample (12,500 of 125,000 rows)
+                vs gather -> torch.optim.SGD(fused) -> scatter."""
+    import torch
+    from msml_b200 import _lib, ops
+    lib = _lib.load()
+    pk = peaks()
+    g = torch.Generator(device="cuda").manual_seed(1)
+
+    def med(fn, n=iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+
+    def entry(name, ms, nbytes, base_ms=None):
+        gbs = nbytes / ms / 1e6
+        return dict(kernel=name, bound="hbm", ms=round(ms, 4), achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
+                    algorithmic_bytes=nbytes, aten_ms=None if base_ms is None else round(base_ms, 4))
+
+    out = []
+    B = 512
+    shapes = [(B, 64, 56, 56), (B, 128, 28, 28), (B, 256, 14, 14), (B, 512, 7, 7)]
+    fwd_b = bwd_b = 0
+    yfs, yos, dcs, dts = [], [], [], []
+    for (b, c, h, w) in shapes:
+        mk = lambda ch: torch.randn(b, ch, h, w, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        ct = -(-(c + 18) // 8) * 8
+        yfs.append(mk(c)); yos.append(mk(18)); dcs.append(mk(ct)); dts.append(mk(c))
+        fwd_b += b * h * w * (c + 18 + ct) * 2
+        bwd_b += b * h * w * 3 * c * 2
+
+    def cat_fwd():
+        for yf, yo in zip(yfs, yos):
+            ops.fm_cat(yf, yo)
+
+    def cat_fwd_aten():
+        for yf, yo in zip(yfs, yos):
+            ops.cat_channels_padded((yf, yo))
+
+    def cat_bwd():
+        st = torch.cuda.current_stream().cuda_stream
+        for yf, dc, dt in zip(yfs, dcs, dts):
+            b, c, h, w = yf.shape
+            dyf = torch.empty_like(yf)
+            _lib.check(lib.msml_fm_cat_bwd(dc.data_ptr(), dt.data_ptr(), dyf.data_ptr(), None, b * h * w, c, 18, dc.shape[1], _lib.BF16, st))
+
+    def cat_bwd_aten():
+        for yf, dc, dt in zip(yfs, dcs, dts):
+            dt + dc[:, :yf.shape[1]]
+    with torch.no_grad():
+        out.append(entry("fm_cat_fwd@config2", med(cat_fwd), fwd_b, med(cat_fwd_aten)))
+        out.append(entry("fm_cat_bwd@config2", med(cat_bwd), bwd_b, med(cat_bwd_aten)))
+    del yfs, yos, dcs, dts
+
+    N, H, W = 512, 112, 112
+    z = torch.randn(N, 2, H, W, device="cuda", generator=g).requires_grad_(True)
+    msk = torch.zeros(N, H, W, dtype=torch.int64, device="cuda")
+    msk[:, 30:70, 20:80] = 1
+    one = torch.ones((), device="cuda")
+    holder = {}
+
+    def seg_fwd():
+        holder["loss"] = ops.consensus_loss(z, msk, msk)
+
+    def seg_bwd():
+        z.grad = None
+        holder["loss"].backward(one, retain_graph=True)
+    out.append(entry("consensus_fwd@B512", med(seg_fwd), N * H * W * (2 * 4 + 16)))
+    out.append(entry("consensus_bwd@B512", med(seg_bwd), N * H * W * (2 * 2 * 4 + 8)))
+    del z, msk, holder
+
+    st = torch.cuda.current_stream().cuda_stream
+    for tag, num_local, n_s in (("config3_w1_full", 93431, 93431), ("config4_sampled", 125000, 12500)):
+        w = torch.randn(num_local, 512, device="cuda", generator=g) * 0.01
+        mom = torch.zeros_like(w)
+        dw = torch.randn(n_s, 512, device="cuda", generator=g) * 0.01
+        index = None if n_s == num_local else torch.sort(torch.randperm(num_local, device="cuda", generator=g)[:n_s]).values
+
+        def fused():
+            _lib.check(lib.msml_pfc_sgd_update(w.data_ptr(), mom.data_ptr(), dw.data_ptr(), index.data_ptr() if index is not None else None,
+                                               n_s, num_local, 512, None, 0.1, 0.9, 5e-4, 0.0, 0, None, None, st))
+        sub = torch.nn.Parameter(w if index is None else w[index].clone())
+        subm = mom if index is None else mom[index].clone()
+        opt = torch.optim.SGD([sub], lr=0.1, momentum=0.9, weight_decay=5e-4, fused=True)
+        opt.state[sub]["momentum_buffer"] = subm
+        sub.grad = dw
+
+        def stock():
+            if index is not None:
+                sub.data.copy_(w[index]); subm.copy_(mom[index])
+            opt.step()
+            if index is not None:
+                w[index] = sub.data; mom[index] = subm
+        with torch.no_grad():
+            out.append(entry("pfc_sgd_update@" + tag, med(fused), n_s * 512 * 20, med(stock)))
+        del w, mom, dw, sub, subm, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_train(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -476,7 +588,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "fusion", "head", "infer"])
+    ap.add_argument("--workload", default="train", choices=["train", "fusion", "head", "infer", "aux"])
     ap.add_argument("--classes", type=int, default=1_000_000)
     ap.add_argument("--sample-rate", type=float, default=1.0)
     ap.add_argument("--batch", type=int, default=BATCH, help="head workload only: per-rank batch (1024 on one GPU reproduces the "
@@ -525,6 +637,16 @@ def main():
                               "config": {"workload": "4-scale mask fusion, batch 512, bf16 NHWC, fwd+bwd, one launch each way"},
                               "roofline": {"bound": "hbm", "achieved": fm["fwd_bwd_gbs"], "peak": pk["hbm"], "unit": "GB/s",
                                            "frac": round(fm["fwd_bwd_gbs"] / pk["hbm"], 4), "traffic": None}, "detail": fm}))
+        return 0
+
+    if args.workload == "aux":
+        torch.cuda.set_device(local_rank)
+        if rank == 0:
+            rl = aux_microbench(iters=max(args.steps, 5))
+            emit({"metric": "auxiliary kernels GB/s (FM concat, consensus loss, fused PartialFC SGD)", "value": rl[0]["achieved"], "unit": "GB/s",
+                  "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": rl[0]["ms"], "higher_is_better": True, "dtype": "bf16",
+                  "data": "synthetic", "vs_baseline": None, "scaling": "weak",
+                  "config": {"workload": "each kernel alone, median of CUDA-event timings; inputs larger than L2"}, "roofline": rl[0], "rooflines": rl})
         return 0
 
     if args.workload == "infer":
