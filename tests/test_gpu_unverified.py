@@ -36,3 +36,9 @@ def test_consensus_loss_kernels_first_gpu_run():
 def test_fused_pfc_sgd_first_gpu_run():
     need_gpu()
     run_checks("check_pfc_sgd.py")
+
+
+@pytest.mark.xfail(strict=False, reason="msml_b200/datasets/dataloaderx.py (SURVEY 8f-4 data path) has never run on a GPU")
+def test_dataloaderx_first_gpu_run():
+    need_gpu()
+    run_checks("check_dataloaderx.py")

@@ -1,5 +1,6 @@
 """CPU tests of the host-side logic that needs no GPU: gradient-buffer ordering for the overlapped all-reduce, dense-layout
 detection, channel padding helper, stale-gradient hygiene."""
+import pytest
 import torch
 
 from msml_b200 import ops
@@ -70,3 +71,22 @@ def test_grad_marker_is_identity_without_a_callback():
     finally:
         ops.set_grad_marker_callback(None)
     assert seen == [7] and torch.equal(x.grad, torch.ones(3))
+
+
+def test_background_generator_order_end_and_errors():
+    """ref datasets/dataloaderx.py:12-38: items in order, StopIteration at the end (and again afterwards); unlike the
+    reference, a failing producer re-raises in the consumer instead of leaving it blocked."""
+    from msml_b200.datasets import BackgroundGenerator
+    g = BackgroundGenerator(iter(range(20)), None, max_prefetch=3)
+    assert list(g) == list(range(20))
+    with pytest.raises(StopIteration):
+        next(g)
+
+    def boom():
+        yield 1
+        raise KeyError("bad record")
+    g = BackgroundGenerator(boom(), None)
+    assert next(g) == 1
+    with pytest.raises(KeyError):
+        next(g)
+    assert next(g, "done") == "done"
