@@ -58,6 +58,7 @@ int num_sms();
 
 // ---- 128-bit streaming accesses -------------------------------------------------------------
 // Read-once / write-once streams: bypass L1 allocation on loads, evict-first on stores.
+#ifndef MSML_CPU_EMU
 __device__ __forceinline__ uint4 ld_stream(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -69,6 +70,10 @@ __device__ __forceinline__ void st_stream(void* p, const uint4& v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+#else   // host build under tests/emu/cuda_emu.h (logic checks without a GPU): cache hints have no meaning there
+inline uint4 ld_stream(const void* p) { return *static_cast<const uint4*>(p); }
+inline void st_stream(void* p, const uint4& v) { *static_cast<uint4*>(p) = v; }
+#endif
 
 // ---- element packs: one 16-byte vector = VEC<T>::N elements ------------------------------------
 template <typename T>

@@ -5,7 +5,9 @@ performance coverage); it exists so that kernels written without GPU access are 
 
 Covered: csrc/seg_loss_kernels.cuh (consensus segmentation loss) against the reference goldens
 (tests/golden/consensus.npz) and the oracle; csrc/pfc_sgd_kernels.cuh (fused PartialFC SGD) against the
-reference recipe gather -> torch.optim.SGD -> scatter (ref headers/partial_fc.py:93-94,101-104,112-114) on CPU.
+reference recipe gather -> torch.optim.SGD -> scatter (ref headers/partial_fc.py:93-94,101-104,112-114) on CPU;
+csrc/fm_cat_kernels.cuh (FM concat) — a kernel that IS verified on a B200 with the same assertions
+(tests/test_gpu_fusion.py::test_fm_cat_matches_concat), run here to cross-check the emulation itself.
 """
 import ctypes
 import os
@@ -189,3 +191,40 @@ def test_pfc_sgd_kernel_skips_bad_rows_and_rejects_bad_shapes(emu_sgd):
     assert emu_sgd.emu_pfc_sgd_update(w.ctypes.data, m.ctypes.data, g.ctypes.data, None, 2, 4, 100, None, 0.5, 0.0, 0.0, 0.0, 0, None, None) != 0
     assert b"multiples of 128" in emu_sgd.emu_sgd_last_error()
     assert emu_sgd.emu_pfc_sgd_update(w.ctypes.data, m.ctypes.data, g.ctypes.data, None, 9, 4, 128, None, 0.5, 0.0, 0.0, 0.0, 0, None, None) != 0
+
+
+# ------------------------------------------------------------------------------------------------ FM concat (GPU-verified kernel)
+@pytest.fixture(scope="module")
+def emu_cat(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_fm_cat.cpp")
+    lib.emu_fm_cat_fwd.argtypes = [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int]
+    lib.emu_fm_cat_bwd.argtypes = [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int]
+    return lib
+
+
+@pytest.mark.parametrize("C,Co,P", [(64, 18, 3 * 9 * 7), (128, 18, 75), (8, 3, 36), (16, 8, 45), (64, 18, 5000)])
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_fm_cat_kernels_match_concat(emu_cat, C, Co, P, dtype):
+    """Same assertions as the GPU test: the forward is a pure copy (bit-exact vs numpy), the backward is the column slice
+    plus the tail's gradient summed in fp32 and rounded once; sms=1 forces several trips of the grid-stride loops."""
+    rng = np.random.default_rng(11)
+    Ct = -(-(C + Co) // 8) * 8
+    rnd = lambda *shape: from_bf16_bits(to_bf16_bits(rng.normal(size=shape).astype(np.float32))).reshape(shape)   # bf16-representable
+    yf, yo, dcat, dtail = rnd(P, C), rnd(P, Co), rnd(P, Ct), rnd(P, C)
+    enc = (lambda a: to_bf16_bits(a).reshape(a.shape)) if dtype == BF16 else (lambda a: np.ascontiguousarray(a, np.float32))
+    dec = (lambda b: from_bf16_bits(b).reshape(b.shape)) if dtype == BF16 else (lambda b: b)
+    yf_b, yo_b, dcat_b, dtail_b = enc(yf), enc(yo), enc(dcat), enc(dtail)
+    cat_b = np.full_like(enc(np.zeros((P, Ct), np.float32)), 0x7F if dtype == BF16 else 7)       # poisoned: every element must be written
+    assert emu_cat.emu_fm_cat_fwd(yf_b.ctypes.data, yo_b.ctypes.data, cat_b.ctypes.data, P, C, Co, Ct, dtype, 1) == 0
+    want = np.concatenate([yf, yo, np.zeros((P, Ct - C - Co), np.float32)], axis=1)
+    assert np.array_equal(dec(cat_b), want)
+    dyf_b, dyo_b = np.zeros_like(yf_b), np.zeros_like(yo_b)
+    assert emu_cat.emu_fm_cat_bwd(dcat_b.ctypes.data, dtail_b.ctypes.data, dyf_b.ctypes.data, dyo_b.ctypes.data, P, C, Co, Ct, dtype, 1) == 0
+    want_dyf = dcat[:, :C] + dtail
+    if dtype == BF16:
+        want_dyf = from_bf16_bits(to_bf16_bits(want_dyf)).reshape(P, C)
+    assert np.array_equal(dec(dyf_b), want_dyf)
+    assert np.array_equal(dec(dyo_b), dcat[:, C:C + Co])
+    dyf2 = np.zeros_like(yf_b)
+    assert emu_cat.emu_fm_cat_bwd(dcat_b.ctypes.data, None, dyf2.ctypes.data, None, P, C, Co, Ct, dtype, 2) == 0
+    assert np.array_equal(dec(dyf2), dcat[:, :C])
