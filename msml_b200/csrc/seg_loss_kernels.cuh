@@ -194,7 +194,6 @@ seg_finalize_kernel(const float* __restrict__ partf, const int* __restrict__ par
   }
   for (int64_t i = threadIdx.x; i < N * g.chunks; i += kSegThreads) poison |= partbad[i];
   __syncthreads();      // acc is read back below by other threads of this (single) CTA
-  __threadfence_block();
 
   double total = 0.0;
   int nb = 0;

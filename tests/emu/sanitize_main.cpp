@@ -1,0 +1,136 @@
+// Standalone sanitizer run of the emulated kernels.  TEST INFRASTRUCTURE ONLY.
+// Built twice by tests/test_emu_kernels.py: with -fsanitize=address,undefined (every buffer is an exact-size heap
+// allocation, so an out-of-bounds access of a kernel is reported) and with -fsanitize=thread (the threads of a CTA are
+// real threads: a missing __syncthreads or two threads writing one location shows up as a data race) — the CPU
+// counterparts of compute-sanitizer's memcheck and racecheck.  Exit code 0 = ran to completion; the sanitizers abort or
+// print a report otherwise.
+#define MSML_CPU_EMU 1
+#include "cuda_emu.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <random>
+#include <string>
+
+#include "../../msml_b200/csrc/fm_cat_kernels.cuh"
+#include "../../msml_b200/csrc/pfc_sgd_kernels.cuh"
+#include "../../msml_b200/csrc/seg_loss_kernels.cuh"
+
+namespace msml {
+static char g_err[512];
+char* err_buf() { return g_err; }
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace msml
+
+using namespace msml;
+
+static std::mt19937 rng(7);
+static float frand() { return std::normal_distribution<float>(0.f, 1.f)(rng); }
+
+template <typename T> static T conv(float v);
+template <> float conv<float>(float v) { return v; }
+template <> __nv_bfloat16 conv<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T, int C>
+static int run_seg(int64_t N, int64_t HW, int K, int cl) {
+  SegGeom g;
+  if (seg_geom(N, C, HW, K, cl, sizeof(T) == 4 ? MSML_F32 : MSML_BF16, &g)) return 1;
+  std::vector<T> logit(N * C * HW), dlogit(N * C * HW);
+  for (auto& v : logit) v = conv<T>(frand());
+  std::vector<int64_t> blobs(N * HW), target(N * HW);
+  for (int64_t i = 0; i < N * HW; ++i) {
+    int b = (int)(rng() % (K + 1)) - 1;                       // -1 .. K-1: ignored pixels included
+    if (i >= (N - 1) * HW && b == 1) b = 0;                   // blob 1 is missing from the last sample
+    blobs[i] = b;
+    target[i] = b < 0 ? 0 : (b + 1) % C;
+  }
+  std::vector<float> partf(seg_partf(g)), acc(seg_acc(g)), coef(2 * (size_t)K * N * C), loss(1), gout(1, 1.5f);
+  std::vector<int> parti(seg_parti(g)), partbad(seg_partbad(g));
+  emu_launch(dim3((unsigned)g.chunks, (unsigned)N), kSegThreads,
+             [&] { seg_stats_kernel<T, C>(logit.data(), blobs.data(), target.data(), partf.data(), parti.data(), partbad.data(), g); });
+  emu_launch(dim3(1), kSegThreads, [&] {
+    seg_finalize_kernel<C>(partf.data(), parti.data(), partbad.data(), target.data(), acc.data(), coef.data(), loss.data(), 10.f, 5.f, 0, 0, g);
+  });
+  emu_launch(dim3((unsigned)g.chunks, (unsigned)N), kSegThreads,
+             [&] { seg_bwd_kernel<T, C>(logit.data(), blobs.data(), coef.data(), gout.data(), dlogit.data(), g); });
+  if (!(loss[0] == loss[0])) { fprintf(stderr, "consensus loss is NaN\n"); return 1; }
+  return 0;
+}
+
+template <int V>
+static int run_sgd(int64_t num_local, int64_t n_s, bool sampled) {
+  constexpr int D = 128 * V;
+  std::vector<float> w(num_local * D), m(num_local * D), dw(n_s * D), inv(n_s);
+  for (auto& v : w) v = 0.01f * frand();
+  for (auto& v : m) v = 0.001f * frand();
+  for (auto& v : dw) v = 0.1f * frand();
+  std::vector<int64_t> index(n_s);
+  for (int64_t r = 0; r < n_s; ++r) index[r] = r * num_local / n_s;     // distinct, sorted
+  std::vector<__nv_bfloat16> wn(n_s * D);
+  SgdParams p{0.1f, 0.9f, 5e-4f, 0.f, 0};
+  const unsigned grid = (unsigned)((n_s + kSgdThreads / 32 - 1) / (kSgdThreads / 32));
+  emu_launch(dim3(grid), kSgdThreads, [&] {
+    pfc_sgd_kernel<V>(w.data(), m.data(), dw.data(), sampled ? index.data() : nullptr, n_s, num_local, nullptr, p, wn.data(), inv.data());
+  });
+  return 0;
+}
+
+template <typename T>
+static int run_cat(int64_t P, int64_t C, int64_t Co, int sms) {
+  const int vn = sizeof(T) == 4 ? 4 : 8;
+  const int64_t Ct = (C + Co + 7) / 8 * 8;
+  CatGeom g;
+  if (cat_geom(P, C, Co, Ct, sizeof(T) == 4 ? MSML_F32 : MSML_BF16, &g)) return 1;
+  (void)vn;
+  std::vector<T> yf(P * C), yo(P * Co), cat(P * Ct), dcat(P * Ct), dadd(P * C), dyf(P * C), dyo(P * Co);
+  for (auto& v : yf) v = conv<T>(frand());
+  for (auto& v : yo) v = conv<T>(frand());
+  for (auto& v : dcat) v = conv<T>(frand());
+  for (auto& v : dadd) v = conv<T>(frand());
+  g.nvec = P * g.vt;
+  emu_launch(dim3((unsigned)cat_grid(g.nvec, sms)), kCatThreads, [&] { fm_cat_fwd_kernel<T>(yf.data(), yo.data(), cat.data(), g); });
+  g.nvec = P * g.vf;
+  emu_launch(dim3((unsigned)cat_grid(g.nvec, sms)), kCatThreads,
+             [&] { fm_cat_bwd_kernel<T, true>(dcat.data(), dadd.data(), dyf.data(), dyo.data(), g); });
+  return 0;
+}
+
+// Seeded defects: the test suite checks that the sanitizers DO report them (a detector that never fires proves nothing).
+static void racy_kernel(float* out) {            // a reduction that forgot its __syncthreads
+  __shared__ float buf[64];
+  buf[threadIdx.x] = (float)threadIdx.x;
+  if (threadIdx.x == 0) { float s = 0.f; for (int i = 0; i < 64; ++i) s += buf[i]; out[0] = s; }
+}
+static void oob_kernel(const float* in, float* out, int n) {      // the classic missing tail guard
+  out[threadIdx.x] = in[threadIdx.x + 1];
+  (void)n;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "--seed-race") {
+    std::vector<float> out(1);
+    emu_launch(dim3(1), 64, [&] { racy_kernel(out.data()); });
+    return 0;
+  }
+  if (argc > 1 && std::string(argv[1]) == "--seed-oob") {
+    std::vector<float> in(64), out(64);
+    emu_launch(dim3(1), 64, [&] { oob_kernel(in.data(), out.data(), 64); });
+    return 0;
+  }
+  int rc = 0;
+  rc |= run_seg<float, 2>(3, 1353, 3, 0);
+  rc |= run_seg<__nv_bfloat16, 3>(2, 1030, 4, 1);
+  rc |= run_seg<float, 4>(2, 77, 2, 1);
+  rc |= run_sgd<1>(20, 9, true);
+  rc |= run_sgd<4>(11, 11, false);
+  rc |= run_cat<float>(301, 64, 18, 1);
+  rc |= run_cat<__nv_bfloat16>(130, 128, 18, 2);
+  printf("emulated kernels ran to completion, rc=%d\n", rc);
+  return rc;
+}

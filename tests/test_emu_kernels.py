@@ -228,3 +228,27 @@ def test_fm_cat_kernels_match_concat(emu_cat, C, Co, P, dtype):
     dyf2 = np.zeros_like(yf_b)
     assert emu_cat.emu_fm_cat_bwd(dcat_b.ctypes.data, None, dyf2.ctypes.data, None, P, C, Co, Ct, dtype, 2) == 0
     assert np.array_equal(dec(dyf2), dcat[:, :C])
+
+
+# ------------------------------------------------------------------------------------------------ memcheck / racecheck on CPU
+@pytest.mark.parametrize("flags,seed,needle", [
+    (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"], "--seed-oob", "AddressSanitizer"),
+    (["-fsanitize=thread"], "--seed-race", "ThreadSanitizer: data race"),
+])
+def test_emulated_kernels_are_clean_under_sanitizers(tmp_path, flags, seed, needle):
+    """tests/emu/sanitize_main.cpp runs the consensus, PartialFC-SGD and FM-concat kernels on exact-size heap buffers
+    with real threads per CTA: AddressSanitizer plays compute-sanitizer's memcheck, ThreadSanitizer its racecheck.
+    The same binary with a seeded defect must be REPORTED, otherwise a clean run would mean nothing."""
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    exe = str(tmp_path / "sanitize")
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-I" + CUDA_INC] + flags +
+                       [os.path.join(HERE, "emu", "sanitize_main.cpp"), "-o", exe], capture_output=True, text=True)
+    if r.returncode != 0 and ("cannot find" in r.stderr or "unrecognized" in r.stderr):
+        pytest.skip("sanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-3000:]
+    clean = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert clean.returncode == 0 and "Sanitizer" not in clean.stderr, clean.stderr[-3000:]
+    assert "ran to completion, rc=0" in clean.stdout
+    seeded = subprocess.run([exe, seed], capture_output=True, text=True, timeout=600)
+    assert needle in seeded.stderr and seeded.returncode != 0
