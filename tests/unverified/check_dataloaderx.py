@@ -30,7 +30,7 @@ def test_dataloaderx_delivers_every_batch_on_the_device():
                 n = y.numel()
                 assert torch.equal(y.cpu(), label[seen:seen + n])
                 assert torch.equal(x.cpu(), img[seen:seen + n]) and torch.equal(m.cpu(), msk[seen:seen + n])
-                assert x.is_contiguous(memory_format=torch.channels_last) == (cl or n == 1)
+                assert x.is_contiguous(memory_format=torch.channels_last) == cl
                 (x * 2).sum().item()                             # consumed on the current stream
                 seen += n
             assert seen == 44

@@ -7,7 +7,6 @@ subprocess and reports xfail / xpass.  The kernel's logic is covered on CPU by t
 import os
 import sys
 
-import numpy as np
 import pytest
 import torch
 
