@@ -42,3 +42,10 @@ def test_fused_pfc_sgd_first_gpu_run():
 def test_dataloaderx_first_gpu_run():
     need_gpu()
     run_checks("check_dataloaderx.py")
+
+
+@pytest.mark.xfail(strict=False, reason="edge-case probes of the PartialFC head written without GPU access (rank with no positive row, "
+                                        "batch of one, repeated class, two-class shard); never run yet")
+def test_head_edge_case_probes_first_gpu_run():
+    need_gpu()
+    run_checks("check_head_edge_cases.py")

@@ -7,7 +7,7 @@ set -u
 O=gpurun_out
 mkdir -p $O
 # 1. the pending checks, verbosely and OUTSIDE the xfail wrapper (each file in its own process)
-for f in check_consensus check_pfc_sgd check_dataloaderx; do
+for f in check_consensus check_pfc_sgd check_dataloaderx check_head_edge_cases; do
   timeout 300 python -m pytest -x -q -p no:cacheprovider tests/unverified/$f.py > $O/r02_$f.log 2>&1
   echo "$f rc=$? : $(tail -1 $O/r02_$f.log)"
 done
