@@ -12,9 +12,11 @@
 #include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -95,24 +97,45 @@ inline float __expf(float x) { return std::exp(x); }
 inline float __fdividef(float a, float b) { return a / b; }
 inline void __nanosleep(unsigned) {}
 
-// launch<<<grid, block>>>: CTAs one after another, threads of a CTA concurrently
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+
+// cooperative groups: only what kernels that ALSO have a multi-launch form need to compile; a grid-wide barrier cannot be
+// emulated with CTAs that run one after another, so grid.sync() aborts if it is ever reached
+namespace cooperative_groups {
+struct grid_group {
+  void sync() const { std::abort(); }
+};
+inline grid_group this_grid() { return {}; }
+}  // namespace cooperative_groups
+
+// launch<<<grid, block>>>: CTAs one after another, the threads of a CTA concurrently.  The OS threads are created once
+// per launch and walk through the CTAs together; a thread that returns from the kernel early leaves the CTA barrier
+// (as an exited CUDA thread does) and the barrier is rebuilt for the next CTA.
 template <typename F>
 inline void emu_launch(dim3 grid, int threads, F&& body) {
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        cuda_emu::Cta cta(threads);
-        std::vector<std::thread> pool;
-        pool.reserve(threads);
-        for (int t = 0; t < threads; ++t)
-          pool.emplace_back([&, t] {
-            cuda_emu::cta = &cta;
-            threadIdx = {(unsigned)t, 0, 0};
+  cuda_emu::Cta cta(threads);
+  std::barrier<> cta_end(threads);
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      cuda_emu::cta = &cta;
+      threadIdx = {(unsigned)t, 0, 0};
+      blockDim = dim3(threads);
+      gridDim = grid;
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
             blockIdx = {bx, by, bz};
-            blockDim = dim3(threads);
-            gridDim = grid;
             body();
-          });
-        for (auto& th : pool) th.join();
-      }
+            cta.all.arrive_and_drop();                 // exited threads no longer take part in __syncthreads
+            cta_end.arrive_and_wait();                 // the whole CTA has finished
+            if (t == 0) {
+              cta.all.~barrier();
+              new (&cta.all) std::barrier<>(threads);
+            }
+            cta_end.arrive_and_wait();                 // the barrier is fresh before anyone enters the next CTA
+          }
+    });
+  for (auto& th : pool) th.join();
 }

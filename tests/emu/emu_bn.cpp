@@ -1,0 +1,103 @@
+// Host build of csrc/bn_act_kernels.cuh under the CPU emulation (tests/emu/cuda_emu.h).  TEST INFRASTRUCTURE ONLY.
+// Mirrors the three-launch sequence of msml_bn_fwd / msml_bn_bwd (csrc/bn_act.cu: slab statistics on G1 CTAs, per-channel
+// finalize on C CTAs, apply on G3 CTAs) on host memory.  These kernels are verified on a B200; here they get a logic
+// re-run plus AddressSanitizer / ThreadSanitizer coverage (sanitize_main.cpp).
+#define MSML_CPU_EMU 1
+#include "cuda_emu.h"
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../msml_b200/csrc/bn_act_kernels.cuh"
+
+#ifndef MSML_EMU_NO_ERR
+namespace msml {
+static char g_err[512];
+char* err_buf() { return g_err; }
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace msml
+#endif
+
+using namespace msml;
+
+static bool emu_bn_geom(int64_t P, int64_t C, int dtype, BnGeom* g) {
+  const int vn = dtype == MSML_F32 ? 4 : 8;
+  if (P <= 0 || C <= 0 || C % vn) return false;
+  const int vpr = (int)(C / vn);
+  if (vpr > kBnThreads || kBnThreads % vpr) return false;
+  g->P = P; g->C = (int)C; g->vpr = vpr; g->rows_per_pass = kBnThreads / vpr; g->skip = 0; g->G = 1;
+  return true;
+}
+static size_t emu_bn_ws_floats(int C) { return (size_t)kBnMaxCtas * 3 * C + kBnMaxCtas + 3 * (size_t)C + 16; }
+
+template <typename T, bool RES, bool PRELU>
+static void fwd3(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu, float* rm, float* rv,
+                 long long* nbt, float momentum, float eps, float* mean, float* invstd, float* ws, BnGeom g, int G1, int G3) {
+  float* part = ws;
+  float* part_n = part + (size_t)kBnMaxCtas * 3 * g.C;
+  float* coef = part_n + kBnMaxCtas;
+  const T* xp = static_cast<const T*>(x);
+  const T* rp = static_cast<const T*>(res);
+  T* yp = static_cast<T*>(y);
+  g.G = G1;
+  emu_launch(dim3(G1), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 1>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g); });
+  emu_launch(dim3(g.C), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 2>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g); });
+  g.G = G3;
+  emu_launch(dim3(G3), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 3>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g); });
+}
+
+template <typename T, bool RES, bool PRELU>
+static void bwd3(const void* dy, const void* x, const void* res, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                 const float* prelu, void* dx, void* dres, const void* dadd, float* dgamma, float* dbeta, float* dprelu, int training,
+                 int accumulate, float* ws, BnGeom g, int G1, int G3) {
+  float* part = ws;
+  float* coef = part + (size_t)kBnMaxCtas * 3 * g.C + kBnMaxCtas;
+  const T* dyp = static_cast<const T*>(dy);
+  const T* xp = static_cast<const T*>(x);
+  const T* rp = static_cast<const T*>(res);
+  T* dxp = static_cast<T*>(dx);
+  T* drp = static_cast<T*>(dres);
+  const T* dap = static_cast<const T*>(dadd);
+  g.G = G1;
+  emu_launch(dim3(G1), kBnThreads, [&] { bn_bwd_fused_kernel<T, RES, PRELU, 1>(dyp, xp, rp, mean, invstd, gamma, beta, prelu, dxp, drp, dap, dgamma, dbeta, dprelu, training, accumulate, part, coef, g); });
+  emu_launch(dim3(g.C), kBnThreads, [&] { bn_bwd_fused_kernel<T, RES, PRELU, 2>(dyp, xp, rp, mean, invstd, gamma, beta, prelu, dxp, drp, dap, dgamma, dbeta, dprelu, training, accumulate, part, coef, g); });
+  g.G = G3;
+  emu_launch(dim3(G3), kBnThreads, [&] { bn_bwd_fused_kernel<T, RES, PRELU, 3>(dyp, xp, rp, mean, invstd, gamma, beta, prelu, dxp, drp, dap, dgamma, dbeta, dprelu, training, accumulate, part, coef, g); });
+}
+
+#define BN_DISPATCH(dtype, has_res, has_prelu, CALL)                                                            \
+  if (dtype == MSML_F32) { using T = float;                                                                     \
+    if (has_res) { if (has_prelu) { constexpr bool RES = true, PRELU = true; CALL; } else { constexpr bool RES = true, PRELU = false; CALL; } } \
+    else { if (has_prelu) { constexpr bool RES = false, PRELU = true; CALL; } else { constexpr bool RES = false, PRELU = false; CALL; } } }      \
+  else { using T = __nv_bfloat16;                                                                               \
+    if (has_res) { if (has_prelu) { constexpr bool RES = true, PRELU = true; CALL; } else { constexpr bool RES = true, PRELU = false; CALL; } } \
+    else { if (has_prelu) { constexpr bool RES = false, PRELU = true; CALL; } else { constexpr bool RES = false, PRELU = false; CALL; } } }
+
+extern "C" int emu_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu, float* rm, float* rv,
+                          long long* nbt, float* mean, float* invstd, int64_t P, int64_t C, int dtype, float momentum, float eps, int G1, int G3) {
+  BnGeom g;
+  if (!emu_bn_geom(P, C, dtype, &g) || G1 < 1 || G3 < 1 || G1 > kBnMaxCtas || G3 > kBnMaxCtas) return 1;
+  std::vector<float> ws(emu_bn_ws_floats((int)C));
+  BN_DISPATCH(dtype, res != nullptr, prelu != nullptr,
+              (fwd3<T, RES, PRELU>(x, res, y, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, ws.data(), g, G1, G3)));
+  return 0;
+}
+
+extern "C" int emu_bn_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* beta, const float* prelu,
+                          const float* mean, const float* invstd, void* dx, void* dres, const void* dadd, float* dgamma, float* dbeta,
+                          float* dprelu, int64_t P, int64_t C, int dtype, int training, int accumulate, int G1, int G3) {
+  BnGeom g;
+  if (!emu_bn_geom(P, C, dtype, &g) || G1 < 1 || G3 < 1 || G1 > kBnMaxCtas || G3 > kBnMaxCtas) return 1;
+  std::vector<float> ws(emu_bn_ws_floats((int)C));
+  const bool has_res = res != nullptr, has_prelu = prelu != nullptr;
+  BN_DISPATCH(dtype, has_res, has_prelu,
+              (bwd3<T, RES, PRELU>(dy, x, res, mean, invstd, gamma, beta, prelu, dx, dres, dadd, dgamma, dbeta, dprelu, training, accumulate,
+                                   ws.data(), g, G1, G3)));
+  return 0;
+}

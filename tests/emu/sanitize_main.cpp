@@ -28,6 +28,9 @@ int set_error(int code, const char* fmt, ...) {
 }
 }  // namespace msml
 
+#define MSML_EMU_NO_ERR 1
+#include "emu_bn.cpp"      // the three-launch BN harness (emu_bn_fwd / emu_bn_bwd)
+
 using namespace msml;
 
 static std::mt19937 rng(7);
@@ -101,6 +104,25 @@ static int run_cat(int64_t P, int64_t C, int64_t Co, int sms) {
   return 0;
 }
 
+template <typename T>
+static int run_bn(int64_t P, int64_t C, bool prelu, bool res, int G1, int G3) {
+  const int dtype = sizeof(T) == 4 ? MSML_F32 : MSML_BF16;
+  std::vector<T> x(P * C), r(P * C), y(P * C), dy(P * C), dx(P * C), dres(P * C), dadd(P * C);
+  for (auto& v : x) v = conv<T>(1.f + 2.f * frand());
+  for (auto& v : r) v = conv<T>(frand());
+  for (auto& v : dy) v = conv<T>(frand());
+  for (auto& v : dadd) v = conv<T>(frand());
+  std::vector<float> gamma(C, 1.1f), beta(C, -0.2f), a(C, 0.25f), rm(C, 0.f), rv(C, 1.f), mean(C), invstd(C), dg(C, 0.f), db(C, 0.f), dp(C, 0.f);
+  long long nbt = 0;
+  const bool both = prelu && res;
+  int rc = emu_bn_fwd(x.data(), res ? r.data() : nullptr, y.data(), gamma.data(), beta.data(), prelu ? a.data() : nullptr, rm.data(), rv.data(),
+                      &nbt, mean.data(), invstd.data(), P, C, dtype, 0.1f, 1e-5f, G1, G3);
+  rc |= emu_bn_bwd(dy.data(), x.data(), both ? r.data() : nullptr, gamma.data(), beta.data(), prelu ? a.data() : nullptr, mean.data(),
+                   invstd.data(), dx.data(), both ? dres.data() : nullptr, dadd.data(), dg.data(), db.data(), prelu ? dp.data() : nullptr, P, C,
+                   dtype, 1, 1, G1, G3);
+  return rc | (nbt != 1);
+}
+
 // Seeded defects: the test suite checks that the sanitizers DO report them (a detector that never fires proves nothing).
 static void racy_kernel(float* out) {            // a reduction that forgot its __syncthreads
   __shared__ float buf[64];
@@ -129,6 +151,10 @@ int main(int argc, char** argv) {
   rc |= run_seg<float, 4>(2, 77, 2, 1);
   rc |= run_sgd<1>(20, 9, true);
   rc |= run_sgd<4>(11, 11, false);
+  rc |= run_bn<float>(162, 32, false, false, 3, 5);
+  rc |= run_bn<__nv_bfloat16>(162, 32, true, true, 3, 5);
+  rc |= run_bn<__nv_bfloat16>(75, 128, true, false, 2, 3);
+  rc |= run_bn<float>(53, 64, false, true, 4, 2);
   rc |= run_cat<float>(301, 64, 18, 1);
   rc |= run_cat<__nv_bfloat16>(130, 128, 18, 2);
   printf("emulated kernels ran to completion, rc=%d\n", rc);

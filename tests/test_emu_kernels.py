@@ -7,7 +7,8 @@ Covered: csrc/seg_loss_kernels.cuh (consensus segmentation loss) ag
 (tests/golden/consensus.npz) and the oracle; csrc/pfc_sgd_kernels.cuh (fused PartialFC SGD) against the
 reference recipe gather -> torch.optim.SGD -> scatter (ref headers/partial_fc.py:93-94,101-104,112-114) on CPU;
 csrc/fm_cat_kernels.cuh (FM concat) — a kernel that IS verified on a B200 with the same assertions
-(tests/test_gpu_fusion.py::test_fm_cat_matches_concat), run here to cross-check the emulation itself.
+(tests/test_gpu_fusion.py::test_fm_cat_matches_concat), run here to cross-check the emulation itself;
+csrc/bn_act_kernels.cuh (fused BatchNorm + residual + PReLU, also verified on a B200) against oracle/bn_act.py.
 """
 import ctypes
 import os
@@ -18,6 +19,7 @@ import numpy as np
 import pytest
 
 from conftest import load_golden
+from oracle import bn_act as obn
 from oracle import consensus
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -252,3 +254,65 @@ def test_emulated_kernels_are_clean_under_sanitizers(tmp_path, flags, seed, need
     assert "ran to completion, rc=0" in clean.stdout
     seeded = subprocess.run([exe, seed], capture_output=True, text=True, timeout=600)
     assert needle in seeded.stderr and seeded.returncode != 0
+
+
+# ------------------------------------------------------------------------------------------------ fused BN (+res) (+PReLU) (GPU-verified)
+@pytest.fixture(scope="module")
+def emu_bn(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_bn.cpp")
+    lib.emu_bn_fwd.argtypes = [c_p] * 11 + [c_i64, c_i64, c_int, c_f, c_f, c_int, c_int]
+    lib.emu_bn_bwd.argtypes = [c_p] * 14 + [c_i64, c_i64, c_int, c_int, c_int, c_int, c_int]
+    return lib
+
+
+@pytest.mark.parametrize("P,C,G1,G3,prelu,res,dtype", [
+    (162, 32, 3, 5, False, False, F32), (162, 32, 3, 5, True, False, BF16), (162, 32, 3, 5, False, True, BF16), (162, 32, 3, 5, True, True, F32),
+    (401, 64, 7, 4, True, True, BF16), (401, 64, 7, 4, False, False, BF16),
+    (98, 256, 2, 2, True, True, BF16),           # 32 channel vectors per row: the warp-per-slot fold; one finalize CTA per channel
+])
+def test_bn_kernels_match_oracle(emu_bn, P, C, G1, G3, prelu, res, dtype):
+    """The three-launch forward and backward (slab statistics -> per-channel finalize -> apply) on slabs that do not
+    divide the rows evenly, vs the numpy fp64 oracle (ref iresnet.py:56-67 / fmoperator.py:52-68 semantics)."""
+    rng = np.random.default_rng(P + C)
+    q = (lambda a: from_bf16_bits(to_bf16_bits(a)).reshape(a.shape)) if dtype == BF16 else (lambda a: a.astype(np.float32))
+    x = q(rng.normal(1.0, 2.0, size=(P, C)).astype(np.float32))
+    r = q(rng.normal(size=(P, C)).astype(np.float32)) if res else None
+    dy = q(rng.normal(size=(P, C)).astype(np.float32))
+    dadd = q(rng.normal(size=(P, C)).astype(np.float32))
+    gamma = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    beta = rng.uniform(-0.5, 0.5, C).astype(np.float32)
+    a = rng.uniform(0.1, 0.4, C).astype(np.float32) if prelu else None
+    rm0, rv0 = rng.normal(size=C).astype(np.float32), rng.uniform(0.5, 2.0, C).astype(np.float32)
+    enc = (lambda t: to_bf16_bits(t).reshape(t.shape)) if dtype == BF16 else (lambda t: np.ascontiguousarray(t, np.float32))
+    dec = (lambda b: from_bf16_bits(b).reshape(b.shape)) if dtype == BF16 else (lambda b: b)
+    ptr = lambda t: t.ctypes.data if t is not None else None
+    xb, rb, dyb, daddb = enc(x), (enc(r) if res else None), enc(dy), enc(dadd)
+    yb = np.zeros_like(xb)
+    rm, rv, nbt = rm0.copy(), rv0.copy(), np.array([4], np.int64)
+    mean, invstd = np.zeros(C, np.float32), np.zeros(C, np.float32)
+    assert emu_bn.emu_bn_fwd(ptr(xb), ptr(rb), ptr(yb), ptr(gamma), ptr(beta), ptr(a), ptr(rm), ptr(rv), ptr(nbt), ptr(mean), ptr(invstd),
+                             P, C, dtype, 0.1, 1e-5, G1, G3) == 0
+    y_want, st = obn.bn_act_fwd(x, gamma, beta, a, r, True, rm0, rv0)
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == BF16 else dict(rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(dec(yb), y_want, **tol)
+    np.testing.assert_allclose(mean, st["mean"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(invstd, st["invstd"], rtol=1e-5)
+    np.testing.assert_allclose(rm, st["running_mean"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rv, st["running_var"], rtol=1e-5)
+    assert nbt[0] == 5
+    both = prelu and res
+    dxb, dresb = np.zeros_like(xb), (np.zeros_like(xb) if both else None)
+    grads = np.full((3, C), 0.25, np.float32)                          # accumulate mode adds on top of what is there
+    assert emu_bn.emu_bn_bwd(ptr(dyb), ptr(xb), ptr(rb) if both else None, ptr(gamma), ptr(beta), ptr(a), ptr(mean), ptr(invstd), ptr(dxb),
+                             ptr(dresb), ptr(daddb), ptr(grads[0]), ptr(grads[1]), ptr(grads[2]) if prelu else None, P, C, dtype, 1, 1,
+                             G1, G3) == 0
+    want = obn.bn_act_bwd(dy, x, gamma, beta, a, r, True)
+    gt = dict(rtol=3e-2, atol=3e-2) if dtype == BF16 else dict(rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(dec(dxb), want["dx"] + dadd, **gt)
+    if both:
+        np.testing.assert_allclose(dec(dresb), want["dres"], **gt)
+    scale = np.abs(want["dgamma"]).max() + 1.0
+    np.testing.assert_allclose(grads[0] - 0.25, want["dgamma"], rtol=1e-3, atol=1e-4 * scale)
+    np.testing.assert_allclose(grads[1] - 0.25, want["dbeta"], rtol=1e-3, atol=1e-4 * scale)
+    if prelu:
+        np.testing.assert_allclose(grads[2] - 0.25, want["dprelu"], rtol=1e-3, atol=1e-4 * scale)
