@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def run_checks(name):
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider",
-                        os.path.join(HERE, "unverified", name)], capture_output=True, text=True, timeout=600)
+                        os.path.join(HERE, "unverified", name)], capture_output=True, text=True, timeout=300)
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-2000:])
     assert r.returncode == 0
