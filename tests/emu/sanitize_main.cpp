@@ -30,6 +30,7 @@ int set_error(int code, const char* fmt, ...) {
 
 #define MSML_EMU_NO_ERR 1
 #include "emu_bn.cpp"      // the three-launch BN harness (emu_bn_fwd / emu_bn_bwd)
+#include "emu_fm_gate.cpp" // the K-A harness (emu_fm_gate_fwd_multi / emu_fm_gate_bwd_multi)
 
 using namespace msml;
 
@@ -123,6 +124,27 @@ static int run_bn(int64_t P, int64_t C, bool prelu, bool res, int G1, int G3) {
   return rc | (nbt != 1);
 }
 
+template <typename T>
+static int run_gate(int act, int arith, bool with_fout) {
+  const int dtype = sizeof(T) == 4 ? MSML_F32 : MSML_BF16;
+  const int64_t n[3] = {9413, 19, 2307};                       // scalar tails, a segment smaller than one vector pass
+  std::vector<T> yf[3], z[3], fo[3], out[3], d[3], dyf[3], dz[3];
+  const void *pyf[3], *pz[3], *pfo[3], *pd[3];
+  void *pout[3], *pdyf[3], *pdz[3];
+  for (int i = 0; i < 3; ++i) {
+    for (auto* v : {&yf[i], &z[i], &fo[i], &out[i], &d[i], &dyf[i], &dz[i]}) v->resize(n[i]);
+    for (auto& v : yf[i]) v = conv<T>(frand());
+    for (auto& v : z[i]) v = conv<T>(frand());
+    for (auto& v : fo[i]) v = conv<T>(frand());
+    for (auto& v : d[i]) v = conv<T>(frand());
+    pyf[i] = yf[i].data(); pz[i] = z[i].data(); pfo[i] = fo[i].data(); pd[i] = d[i].data();
+    pout[i] = out[i].data(); pdyf[i] = dyf[i].data(); pdz[i] = dz[i].data();
+  }
+  int rc = emu_fm_gate_fwd_multi(with_fout ? 1 : 3, pyf, pz, with_fout ? pfo : nullptr, pout, n, dtype, act, arith, 2);
+  rc |= emu_fm_gate_bwd_multi(3, pd, pyf, pz, pdyf, pdz, n, dtype, act, arith, 2);
+  return rc;
+}
+
 // Seeded defects: the test suite checks that the sanitizers DO report them (a detector that never fires proves nothing).
 static void racy_kernel(float* out) {            // a reduction that forgot its __syncthreads
   __shared__ float buf[64];
@@ -155,6 +177,9 @@ int main(int argc, char** argv) {
   rc |= run_bn<__nv_bfloat16>(162, 32, true, true, 3, 5);
   rc |= run_bn<__nv_bfloat16>(75, 128, true, false, 2, 3);
   rc |= run_bn<float>(53, 64, false, true, 4, 2);
+  rc |= run_gate<float>(1, 3, false);
+  rc |= run_gate<__nv_bfloat16>(0, 0, false);
+  rc |= run_gate<__nv_bfloat16>(1, 2, true);
   rc |= run_cat<float>(301, 64, 18, 1);
   rc |= run_cat<__nv_bfloat16>(130, 128, 18, 2);
   printf("emulated kernels ran to completion, rc=%d\n", rc);

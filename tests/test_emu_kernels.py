@@ -8,7 +8,9 @@ Covered: csrc/seg_loss_kernels.cuh (consensus segmentation loss) ag
 reference recipe gather -> torch.optim.SGD -> scatter (ref headers/partial_fc.py:93-94,101-104,112-114) on CPU;
 csrc/fm_cat_kernels.cuh (FM concat) — a kernel that IS verified on a B200 with the same assertions
 (tests/test_gpu_fusion.py::test_fm_cat_matches_concat), run here to cross-check the emulation itself;
-csrc/bn_act_kernels.cuh (fused BatchNorm + residual + PReLU, also verified on a B200) against oracle/bn_act.py.
+csrc/bn_act_kernels.cuh (fused BatchNorm + residual + PReLU, also verified on a B200) against oracle/bn_act.py;
+csrc/fm_gate_kernels.cuh (K-A, the north-star mask-fusion tail, verified on a B200) against the reference goldens and
+oracle/fm_tail.py.
 """
 import ctypes
 import os
@@ -21,6 +23,7 @@ import pytest
 from conftest import load_golden
 from oracle import bn_act as obn
 from oracle import consensus
+from oracle import fm_tail
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_INC = "/usr/local/cuda/include"
@@ -316,3 +319,63 @@ def test_bn_kernels_match_oracle(emu_bn, P, C, G1, G3, prelu, res, dtype):
     np.testing.assert_allclose(grads[1] - 0.25, want["dbeta"], rtol=1e-3, atol=1e-4 * scale)
     if prelu:
         np.testing.assert_allclose(grads[2] - 0.25, want["dprelu"], rtol=1e-3, atol=1e-4 * scale)
+
+
+# ------------------------------------------------------------------------------------------------ K-A mask-fusion tail (GPU-verified)
+ACTS = {"tanh": 0, "sigmoid": 1}
+ARITHS = {"add": 0, "sub": 1, "div": 2, "mul": 3}
+
+
+@pytest.fixture(scope="module")
+def emu_gate(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_fm_gate.cpp")
+    lib.emu_fm_gate_fwd_multi.argtypes = [c_int, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int]
+    lib.emu_fm_gate_bwd_multi.argtypes = [c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int]
+    return lib
+
+
+def gate_run(lib, yfs, zs, douts, act, arith, dtype, sms, fouts=None):
+    """One forward and one backward launch over len(yfs) segments -> (outs, dyfs, dzs) as fp32 arrays."""
+    enc = (lambda t: to_bf16_bits(t).reshape(t.shape)) if dtype == BF16 else (lambda t: np.ascontiguousarray(t, np.float32))
+    dec = (lambda b: from_bf16_bits(b).reshape(b.shape)) if dtype == BF16 else (lambda b: b)
+    n = len(yfs)
+    arr = lambda bufs: (c_p * n)(*[b.ctypes.data for b in bufs])
+    yb, zb, db = [enc(t) for t in yfs], [enc(t) for t in zs], [enc(t) for t in douts]
+    fb = [enc(t) for t in fouts] if fouts is not None else None
+    ob, dyb, dzb = [np.zeros_like(b) for b in yb], [np.zeros_like(b) for b in yb], [np.zeros_like(b) for b in yb]
+    sizes = (c_i64 * n)(*[b.size for b in yb])
+    assert lib.emu_fm_gate_fwd_multi(n, arr(yb), arr(zb), arr(fb) if fb else None, arr(ob), sizes, dtype, ACTS[act], ARITHS[arith], sms) == 0
+    assert lib.emu_fm_gate_bwd_multi(n, arr(db), arr(yb), arr(zb), arr(dyb), arr(dzb), sizes, dtype, ACTS[act], ARITHS[arith], sms) == 0
+    return [dec(b) for b in ob], [dec(b) for b in dyb], [dec(b) for b in dzb]
+
+
+@pytest.mark.parametrize("name", ["fm_c64_sigmoid_mul", "fm_c128_tanh_add", "fm_c64_sigmoid_div", "fm_c256_tanh_sub"])
+def test_fm_gate_kernels_match_reference_golden(emu_gate, name):
+    """ref backbones/fm/fmoperator.py:288,304-310 run by make_golden.py: out, the direct dyf and dz (fp32 mode)."""
+    g = load_golden(name)
+    act, arith = str(g["act"]), str(g["arith"])
+    outs, dyfs, dzs = gate_run(emu_gate, [g["yf"]], [g["z"]], [g["dout"]], act, arith, F32, sms=1)
+    np.testing.assert_allclose(outs[0], g["out"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dyfs[0], g["dyf_direct"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dzs[0], g["dz"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_fm_gate_kernels_four_scales_one_launch_with_ragged_tails(emu_gate, dtype):
+    """Four segments of very different sizes through ONE launch (CTAs dealt in proportion), sizes that are not whole vectors,
+    the peer term f_out, all on 2 'SMs' so that the persistent loops take several trips; vs oracle/fm_tail.py."""
+    rng = np.random.default_rng(8)
+    q = (lambda a: from_bf16_bits(to_bf16_bits(a)).reshape(a.shape)) if dtype == BF16 else (lambda a: a)
+    sizes = [64 * 7 * 7 * 3 + 5, 128 * 5 * 5, 19, 256 * 9 + 3]
+    mk = lambda: [q(rng.normal(size=n).astype(np.float32)) for n in sizes]
+    yfs, zs, ds, fos = mk(), mk(), mk(), mk()
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == BF16 else dict(rtol=2e-5, atol=2e-5)
+    for act, arith in (("sigmoid", "mul"), ("tanh", "add"), ("sigmoid", "sub")):
+        outs, dyfs, dzs = gate_run(emu_gate, yfs, zs, ds, act, arith, dtype, sms=2)
+        for i in range(4):
+            np.testing.assert_allclose(outs[i], fm_tail.fm_gate_fwd(yfs[i], zs[i], act, arith), **tol)
+            wdyf, wdz = fm_tail.fm_gate_bwd(ds[i], yfs[i], zs[i], act, arith)
+            np.testing.assert_allclose(dyfs[i], wdyf, **tol)
+            np.testing.assert_allclose(dzs[i], wdz, **tol)
+    outs, _, _ = gate_run(emu_gate, yfs[:1], zs[:1], ds[:1], "sigmoid", "mul", dtype, sms=1, fouts=fos[:1])
+    np.testing.assert_allclose(outs[0], fm_tail.fm_gate_fwd(yfs[0], zs[0], "sigmoid", "mul") + fos[0], **tol)
