@@ -71,6 +71,7 @@ static void bwd3(const void* dy, const void* x, const void* res, const float* me
   emu_launch(dim3(G3), kBnThreads, [&] { bn_bwd_fused_kernel<T, RES, PRELU, 3>(dyp, xp, rp, mean, invstd, gamma, beta, prelu, dxp, drp, dap, dgamma, dbeta, dprelu, training, accumulate, part, coef, g); });
 }
 
+#ifndef MSML_EMU_TEMPLATES_ONLY   // sanitize_main.cpp instantiates a few variants itself instead of all of them
 #define BN_DISPATCH(dtype, has_res, has_prelu, CALL)                                                            \
   if (dtype == MSML_F32) { using T = float;                                                                     \
     if (has_res) { if (has_prelu) { constexpr bool RES = true, PRELU = true; CALL; } else { constexpr bool RES = true, PRELU = false; CALL; } } \
@@ -101,3 +102,4 @@ extern "C" int emu_bn_bwd(const void* dy, const void* x, const void* res, const 
                                    ws.data(), g, G1, G3)));
   return 0;
 }
+#endif

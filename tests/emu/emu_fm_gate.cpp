@@ -51,6 +51,7 @@ static void run_bwd(const BwdSegs& s) {
   emu_launch(dim3(s.block_end[MSML_MAX_SEGMENTS - 1]), kThreads, [&] { fm_gate_bwd_kernel<T, ACT, ARITH>(s); });
 }
 
+#ifndef MSML_EMU_TEMPLATES_ONLY   // sanitize_main.cpp instantiates a few variants itself instead of all of them
 // `sms` plays the SM count: small values force several trips of the persistent loops and uneven CTA dealing
 extern "C" int emu_fm_gate_fwd_multi(int nseg, const void* const* yf, const void* const* z, const void* const* f_out, void* const* out,
                                      const int64_t* n, int dtype, int act, int arith, int sms) {
@@ -74,3 +75,4 @@ extern "C" int emu_fm_gate_bwd_multi(int nseg, const void* const* dout, const vo
   GATE_DISPATCH(dtype, act, arith, (run_bwd<T, ACT, ARITH>(s)));
   return 0;
 }
+#endif

@@ -29,6 +29,7 @@ int set_error(int code, const char* fmt, ...) {
 }  // namespace msml
 
 #define MSML_EMU_NO_ERR 1
+#define MSML_EMU_TEMPLATES_ONLY 1
 #include "emu_bn.cpp"      // the three-launch BN harness (emu_bn_fwd / emu_bn_bwd)
 #include "emu_fm_gate.cpp" // the K-A harness (emu_fm_gate_fwd_multi / emu_fm_gate_bwd_multi)
 
@@ -105,44 +106,51 @@ static int run_cat(int64_t P, int64_t C, int64_t Co, int sms) {
   return 0;
 }
 
-template <typename T>
-static int run_bn(int64_t P, int64_t C, bool prelu, bool res, int G1, int G3) {
+template <typename T, bool RES, bool PRELU>
+static int run_bn(int64_t P, int64_t C, int G1, int G3) {
   const int dtype = sizeof(T) == 4 ? MSML_F32 : MSML_BF16;
+  BnGeom g;
+  if (!emu_bn_geom(P, C, dtype, &g)) return 1;
   std::vector<T> x(P * C), r(P * C), y(P * C), dy(P * C), dx(P * C), dres(P * C), dadd(P * C);
   for (auto& v : x) v = conv<T>(1.f + 2.f * frand());
   for (auto& v : r) v = conv<T>(frand());
   for (auto& v : dy) v = conv<T>(frand());
   for (auto& v : dadd) v = conv<T>(frand());
   std::vector<float> gamma(C, 1.1f), beta(C, -0.2f), a(C, 0.25f), rm(C, 0.f), rv(C, 1.f), mean(C), invstd(C), dg(C, 0.f), db(C, 0.f), dp(C, 0.f);
+  std::vector<float> ws(emu_bn_ws_floats((int)C));
   long long nbt = 0;
-  const bool both = prelu && res;
-  int rc = emu_bn_fwd(x.data(), res ? r.data() : nullptr, y.data(), gamma.data(), beta.data(), prelu ? a.data() : nullptr, rm.data(), rv.data(),
-                      &nbt, mean.data(), invstd.data(), P, C, dtype, 0.1f, 1e-5f, G1, G3);
-  rc |= emu_bn_bwd(dy.data(), x.data(), both ? r.data() : nullptr, gamma.data(), beta.data(), prelu ? a.data() : nullptr, mean.data(),
-                   invstd.data(), dx.data(), both ? dres.data() : nullptr, dadd.data(), dg.data(), db.data(), prelu ? dp.data() : nullptr, P, C,
-                   dtype, 1, 1, G1, G3);
-  return rc | (nbt != 1);
+  constexpr bool both = PRELU && RES;
+  fwd3<T, RES, PRELU>(x.data(), RES ? r.data() : nullptr, y.data(), gamma.data(), beta.data(), PRELU ? a.data() : nullptr, rm.data(), rv.data(),
+                      &nbt, 0.1f, 1e-5f, mean.data(), invstd.data(), ws.data(), g, G1, G3);
+  bwd3<T, both, PRELU>(dy.data(), x.data(), both ? r.data() : nullptr, mean.data(), invstd.data(), gamma.data(), beta.data(),
+                       PRELU ? a.data() : nullptr, dx.data(), both ? dres.data() : nullptr, dadd.data(), dg.data(), db.data(),
+                       PRELU ? dp.data() : nullptr, 1, 1, ws.data(), g, G1, G3);
+  return nbt != 1;
 }
 
-template <typename T>
-static int run_gate(int act, int arith, bool with_fout) {
-  const int dtype = sizeof(T) == 4 ? MSML_F32 : MSML_BF16;
+template <typename T, int ACT, int ARITH>
+static int run_gate(bool with_fout) {
   const int64_t n[3] = {9413, 19, 2307};                       // scalar tails, a segment smaller than one vector pass
+  const int vn = sizeof(T) == 4 ? 4 : 8;
   std::vector<T> yf[3], z[3], fo[3], out[3], d[3], dyf[3], dz[3];
-  const void *pyf[3], *pz[3], *pfo[3], *pd[3];
-  void *pout[3], *pdyf[3], *pdz[3];
+  FwdSegs fs{};
+  BwdSegs bs{};
+  fs.nseg = with_fout ? 1 : 3;
+  bs.nseg = 3;
   for (int i = 0; i < 3; ++i) {
     for (auto* v : {&yf[i], &z[i], &fo[i], &out[i], &d[i], &dyf[i], &dz[i]}) v->resize(n[i]);
     for (auto& v : yf[i]) v = conv<T>(frand());
     for (auto& v : z[i]) v = conv<T>(frand());
     for (auto& v : fo[i]) v = conv<T>(frand());
     for (auto& v : d[i]) v = conv<T>(frand());
-    pyf[i] = yf[i].data(); pz[i] = z[i].data(); pfo[i] = fo[i].data(); pd[i] = d[i].data();
-    pout[i] = out[i].data(); pdyf[i] = dyf[i].data(); pdz[i] = dz[i].data();
+    fs.yf[i] = yf[i].data(); fs.z[i] = z[i].data(); fs.f_out[i] = with_fout ? fo[i].data() : nullptr; fs.out[i] = out[i].data(); fs.n[i] = n[i];
+    bs.dout[i] = d[i].data(); bs.yf[i] = yf[i].data(); bs.z[i] = z[i].data(); bs.dyf[i] = dyf[i].data(); bs.dz[i] = dz[i].data(); bs.n[i] = n[i];
   }
-  int rc = emu_fm_gate_fwd_multi(with_fout ? 1 : 3, pyf, pz, with_fout ? pfo : nullptr, pout, n, dtype, act, arith, 2);
-  rc |= emu_fm_gate_bwd_multi(3, pd, pyf, pz, pdyf, pdz, n, dtype, act, arith, 2);
-  return rc;
+  deal_blocks(fs.nseg, n, vn, with_fout ? kUnroll3 : kUnroll, kCtasPerSm, fs.block_end, 2);
+  deal_blocks(3, n, vn, kUnroll3, kCtasPerSmBwd, bs.block_end, 2);
+  run_fwd<T, ACT, ARITH>(fs, with_fout);
+  run_bwd<T, ACT, ARITH>(bs);
+  return 0;
 }
 
 // Seeded defects: the test suite checks that the sanitizers DO report them (a detector that never fires proves nothing).
@@ -156,7 +164,17 @@ static void oob_kernel(const float* in, float* out, int n) {      // the classic
   (void)n;
 }
 
+static void misaligned_kernel(const float* in, uint4* out) {      // a 128-bit access on a pointer that is only 4-byte aligned
+  if (threadIdx.x == 0) out[0] = ld_stream(in + 1);
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "--seed-misaligned") {
+    std::vector<float> in(16);
+    std::vector<uint4> out(1);
+    emu_launch(dim3(1), 32, [&] { misaligned_kernel(in.data(), out.data()); });
+    return 0;
+  }
   if (argc > 1 && std::string(argv[1]) == "--seed-race") {
     std::vector<float> out(1);
     emu_launch(dim3(1), 64, [&] { racy_kernel(out.data()); });
@@ -173,13 +191,13 @@ int main(int argc, char** argv) {
   rc |= run_seg<float, 4>(2, 77, 2, 1);
   rc |= run_sgd<1>(20, 9, true);
   rc |= run_sgd<4>(11, 11, false);
-  rc |= run_bn<float>(162, 32, false, false, 3, 5);
-  rc |= run_bn<__nv_bfloat16>(162, 32, true, true, 3, 5);
-  rc |= run_bn<__nv_bfloat16>(75, 128, true, false, 2, 3);
-  rc |= run_bn<float>(53, 64, false, true, 4, 2);
-  rc |= run_gate<float>(1, 3, false);
-  rc |= run_gate<__nv_bfloat16>(0, 0, false);
-  rc |= run_gate<__nv_bfloat16>(1, 2, true);
+  rc |= run_bn<float, false, false>(162, 32, 3, 5);
+  rc |= run_bn<__nv_bfloat16, true, true>(162, 32, 3, 5);
+  rc |= run_bn<__nv_bfloat16, false, true>(75, 128, 2, 3);
+  rc |= run_bn<float, true, false>(53, 64, 4, 2);
+  rc |= run_gate<float, 1, 3>(false);
+  rc |= run_gate<__nv_bfloat16, 0, 0>(false);
+  rc |= run_gate<__nv_bfloat16, 1, 2>(true);
   rc |= run_cat<float>(301, 64, 18, 1);
   rc |= run_cat<__nv_bfloat16>(130, 128, 18, 2);
   printf("emulated kernels ran to completion, rc=%d\n", rc);

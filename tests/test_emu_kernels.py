@@ -236,27 +236,49 @@ def test_fm_cat_kernels_match_concat(emu_cat, C, Co, P, dtype):
 
 
 # ------------------------------------------------------------------------------------------------ memcheck / racecheck on CPU
-@pytest.mark.parametrize("flags,seed,needle", [
-    (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"], "--seed-oob", "AddressSanitizer"),
-    (["-fsanitize=thread"], "--seed-race", "ThreadSanitizer: data race"),
-])
-def test_emulated_kernels_are_clean_under_sanitizers(tmp_path, flags, seed, needle):
-    """tests/emu/sanitize_main.cpp runs the consensus, PartialFC-SGD and FM-concat kernels on exact-size heap buffers
-    with real threads per CTA: AddressSanitizer plays compute-sanitizer's memcheck, ThreadSanitizer its racecheck.
-    The same binary with a seeded defect must be REPORTED, otherwise a clean run would mean nothing."""
+SANITIZERS = {
+    "asan": (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"], "--seed-oob", "AddressSanitizer"),
+    "tsan": (["-fsanitize=thread"], "--seed-race", "ThreadSanitizer: data race"),
+}
+
+
+@pytest.fixture(scope="module")
+def sanitizer_builds(tmp_path_factory):
+    """Both sanitizer builds of tests/emu/sanitize_main.cpp, compiled side by side."""
     if shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("needs g++ and the CUDA headers")
-    exe = str(tmp_path / "sanitize")
-    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-I" + CUDA_INC] + flags +
-                       [os.path.join(HERE, "emu", "sanitize_main.cpp"), "-o", exe], capture_output=True, text=True)
-    if r.returncode != 0 and ("cannot find" in r.stderr or "unrecognized" in r.stderr):
+    d = tmp_path_factory.mktemp("sanitize")
+    procs = {}
+    for tag, (flags, _, _) in SANITIZERS.items():
+        exe = str(d / tag)
+        procs[tag] = (exe, subprocess.Popen(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-I" + CUDA_INC] + flags +
+                                            [os.path.join(HERE, "emu", "sanitize_main.cpp"), "-o", exe],
+                                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    out = {}
+    for tag, (exe, p) in procs.items():
+        _, err = p.communicate()
+        out[tag] = (exe, p.returncode, err)
+    return out
+
+
+@pytest.mark.parametrize("tag", ["asan", "tsan"])
+def test_emulated_kernels_are_clean_under_sanitizers(sanitizer_builds, tag):
+    """tests/emu/sanitize_main.cpp runs the consensus, PartialFC-SGD, FM-concat, BatchNorm and mask-fusion kernels on
+    exact-size heap buffers with real threads per CTA: AddressSanitizer plays compute-sanitizer's memcheck, ThreadSanitizer
+    its racecheck.  The same binary with a seeded defect must be REPORTED, otherwise a clean run would mean nothing."""
+    exe, rc, err = sanitizer_builds[tag]
+    _, seed, needle = SANITIZERS[tag]
+    if rc != 0 and ("cannot find" in err or "unrecognized" in err):
         pytest.skip("sanitizer runtime not installed")
-    assert r.returncode == 0, r.stderr[-3000:]
+    assert rc == 0, err[-3000:]
     clean = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert clean.returncode == 0 and "Sanitizer" not in clean.stderr, clean.stderr[-3000:]
     assert "ran to completion, rc=0" in clean.stdout
     seeded = subprocess.run([exe, seed], capture_output=True, text=True, timeout=600)
     assert needle in seeded.stderr and seeded.returncode != 0
+    if tag == "asan":       # UBSan's alignment check: a 128-bit access through a 4-byte-aligned pointer (cudaErrorMisalignedAddress on a GPU)
+        mis = subprocess.run([exe, "--seed-misaligned"], capture_output=True, text=True, timeout=600)
+        assert "misaligned address" in mis.stderr and mis.returncode != 0
 
 
 # ------------------------------------------------------------------------------------------------ fused BN (+res) (+PReLU) (GPU-verified)
