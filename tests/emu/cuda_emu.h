@@ -84,6 +84,30 @@ inline V __shfl_xor_sync(unsigned, V v, int lane_mask) {
   return out;
 }
 
+template <typename V>
+inline V __shfl_up_sync(unsigned, V v, int delta) {
+  static_assert(sizeof(V) <= 8, "shuffle of up to 8 bytes");
+  cuda_emu::Cta* c = cuda_emu::cta;
+  const int t = (int)threadIdx.x, w = t >> 5, lane = t & 31;
+  uint64_t bits = 0;
+  std::memcpy(&bits, &v, sizeof(V));
+  c->xchg[t] = bits;
+  c->warp[w]->arrive_and_wait();
+  const uint64_t got = lane >= delta ? c->xchg[t - delta] : bits;
+  c->warp[w]->arrive_and_wait();
+  V out;
+  std::memcpy(&out, &got, sizeof(V));
+  return out;
+}
+inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+// atomics on shared (function-local statics) and global memory: real atomic read-modify-writes between the CTA's threads
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+
 template <typename V> inline V __ldg(const V* p) { return *p; }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }

@@ -32,6 +32,7 @@ int set_error(int code, const char* fmt, ...) {
 #define MSML_EMU_TEMPLATES_ONLY 1
 #include "emu_bn.cpp"      // the three-launch BN harness (emu_bn_fwd / emu_bn_bwd)
 #include "emu_fm_gate.cpp" // the K-A harness (emu_fm_gate_fwd_multi / emu_fm_gate_bwd_multi)
+#include "emu_pfc_sample.cpp"  // the K-D harness (remap, mark, radix select with tickets and atomics, searchsorted, row copies)
 
 using namespace msml;
 
@@ -153,6 +154,25 @@ static int run_gate(bool with_fout) {
   return 0;
 }
 
+static int run_pfc(int64_t num_local, int64_t num_sample, int64_t n_labels) {
+  std::vector<float> perm(num_local);
+  for (auto& v : perm) v = (float)(rng() % 997) / 997.f;        // ties at the threshold
+  std::vector<int64_t> tl(n_labels);
+  for (auto& v : tl) v = (int64_t)(rng() % (2 * num_local));
+  emu_pfc_remap(tl.data(), n_labels, 100, num_local);
+  emu_pfc_mark_positive(perm.data(), tl.data(), n_labels, num_local);
+  std::vector<int64_t> index(num_sample > n_labels ? num_sample : n_labels), n_index(1);
+  emu_pfc_select(perm.data(), num_local, num_sample, index.data(), n_index.data());
+  if (n_index[0] < num_sample || n_index[0] > (int64_t)index.size()) return 1;
+  for (int64_t i = 1; i < n_index[0]; ++i) if (index[i] <= index[i - 1]) return 1;     // sorted, distinct
+  emu_pfc_searchsorted(tl.data(), n_labels, index.data(), n_index.data());
+  const int64_t D = 32, rows = n_index[0];
+  std::vector<float> w(num_local * D, 1.f), sub(rows * D);
+  emu_gather_rows(w.data(), index.data(), sub.data(), rows, D);
+  emu_scatter_rows(w.data(), index.data(), sub.data(), rows, D);
+  return 0;
+}
+
 // Seeded defects: the test suite checks that the sanitizers DO report them (a detector that never fires proves nothing).
 static void racy_kernel(float* out) {            // a reduction that forgot its __syncthreads
   __shared__ float buf[64];
@@ -198,6 +218,8 @@ int main(int argc, char** argv) {
   rc |= run_gate<float, 1, 3>(false);
   rc |= run_gate<__nv_bfloat16, 0, 0>(false);
   rc |= run_gate<__nv_bfloat16, 1, 2>(true);
+  rc |= run_pfc(9000, 2700, 300);
+  rc |= run_pfc(4096, 40, 200);                                   // positives outnumber num_sample
   rc |= run_cat<float>(301, 64, 18, 1);
   rc |= run_cat<__nv_bfloat16>(130, 128, 18, 2);
   printf("emulated kernels ran to completion, rc=%d\n", rc);
