@@ -24,6 +24,7 @@ import pytest
 from conftest import load_golden
 from oracle import bn_act as obn
 from oracle import consensus
+from oracle import dap as odap
 from oracle import fm_tail
 from oracle import partial_fc as opfc
 
@@ -479,3 +480,34 @@ def test_pfc_sampling_kernels_bit_exact_vs_oracle(emu_pfc, num_local, sr, n_labe
     want = np.zeros_like(w)
     want[index] = w[index]
     assert np.array_equal(w2, want)
+
+
+# ------------------------------------------------------------------------------------------------ K-B DAP + argmax mask (GPU-verified)
+@pytest.fixture(scope="module")
+def emu_dap(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_dap.cpp")
+    lib.emu_dap_fwd.argtypes = [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int]
+    lib.emu_dap_bwd.argtypes = [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int]
+    lib.emu_dap_fwd.restype = lib.emu_dap_bwd.restype = None
+    return lib
+
+
+@pytest.mark.parametrize("cl", [False, True])
+def test_dap_kernels_match_reference_golden(emu_dap, cl):
+    """ref backbones/osb/unet.py:158-161,223 + train.py:357 run by make_golden.py (ties planted): y, dx and the argmax mask
+    bit for bit (first index on ties)."""
+    g = load_golden("dap")
+    x, dy = g["x"], g["dy"]
+    B, CK, H, W = x.shape
+    G, kk = dy.shape[1], CK // dy.shape[1]
+    lay = (lambda a: np.ascontiguousarray(a.transpose(0, 2, 3, 1))) if cl else (lambda a: np.ascontiguousarray(a))
+    unlay = (lambda a, C: a.reshape(B, H, W, C).transpose(0, 3, 1, 2)) if cl else (lambda a, C: a.reshape(B, C, H, W))
+    xb, dyb = lay(x.astype(np.float32)), lay(dy.astype(np.float32))
+    yb, dxb = np.zeros(B * G * H * W, np.float32), np.zeros(B * CK * H * W, np.float32)
+    mask = np.full(B * H * W, -1, np.int64)
+    emu_dap.emu_dap_fwd(xb.ctypes.data, yb.ctypes.data, mask.ctypes.data, B, G, kk, H * W, int(cl), F32, 2)
+    emu_dap.emu_dap_bwd(dyb.ctypes.data, dxb.ctypes.data, B, G, kk, H * W, int(cl), F32, 2)
+    np.testing.assert_allclose(unlay(yb, G), g["y"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(unlay(dxb, CK), g["dx"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(mask.reshape(B, H, W), g["mask"])
+    assert np.array_equal(mask.reshape(B, H, W), odap.argmax_mask(unlay(yb, G)))
