@@ -32,6 +32,8 @@ int set_error(int code, const char* fmt, ...) {
 #define MSML_EMU_TEMPLATES_ONLY 1
 #include "emu_bn.cpp"      // the three-launch BN harness (emu_bn_fwd / emu_bn_bwd)
 #include "emu_fm_gate.cpp" // the K-A harness (emu_fm_gate_fwd_multi / emu_fm_gate_bwd_multi)
+#include "emu_dap.cpp"         // K-B: DAP + argmax mask
+#include "emu_head_small.cpp"  // margin math, weight normalisation, statistics merge, bf16 transpose
 #include "emu_pfc_sample.cpp"  // the K-D harness (remap, mark, radix select with tickets and atomics, searchsorted, row copies)
 
 using namespace msml;
@@ -173,6 +175,42 @@ static int run_pfc(int64_t num_local, int64_t num_sample, int64_t n_labels) {
   return 0;
 }
 
+static int run_small() {
+  // K-B
+  const int64_t B = 2, G = 2, kk = 9, HW = 131;
+  std::vector<__nv_bfloat16> x(B * G * kk * HW), y(B * G * HW), dy(B * G * HW), dx(B * G * kk * HW);
+  for (auto& v : x) v = conv<__nv_bfloat16>(frand());
+  for (auto& v : dy) v = conv<__nv_bfloat16>(frand());
+  std::vector<int64_t> mask(B * HW);
+  emu_dap_fwd(x.data(), y.data(), mask.data(), B, G, kk, HW, 1, MSML_BF16, 2);
+  emu_dap_bwd(dy.data(), dx.data(), B, G, kk, HW, 0, MSML_BF16, 1);
+  // head
+  const int64_t n = 19, D = 128;
+  std::vector<float> w(n * D), inv(n);
+  for (auto& v : w) v = 0.01f * frand();
+  std::vector<__nv_bfloat16> wn(n * D), wt(D * 24);
+  emu_wnorm_cast(w.data(), wn.data(), inv.data(), n, D, 1);
+  emu_transpose_bf16(wn.data(), wt.data(), n, D, 24);
+  const int W = 2, B_tot = 70, n_blocks = 5;
+  std::vector<float> pmax(n_blocks * B_tot), psum(n_blocks * B_tot), tgt(B_tot), stats(3 * B_tot * W), gstats(2 * B_tot), loss(1);
+  for (auto& v : pmax) v = 8.f * frand();
+  for (auto& v : psum) v = 1.f + (float)(rng() % 7);
+  for (auto& v : tgt) v = frand();
+  std::vector<int64_t> tl(B_tot);
+  for (int r = 0; r < W; ++r) {
+    for (int i = 0; i < B_tot; ++i) tl[i] = (i % W == r) ? i : -1;
+    emu_head_local_stats(pmax.data(), psum.data(), tgt.data(), tl.data(), n_blocks, B_tot, stats.data() + (size_t)r * 3 * B_tot);
+  }
+  emu_head_merge_stats(stats.data(), W, B_tot, gstats.data(), loss.data());
+  std::vector<float> cosm(6 * 11), dl(6 * 11, 1.f);
+  for (auto& v : cosm) v = 0.9f * std::tanh(frand());
+  std::vector<float> cos0 = cosm;
+  std::vector<int64_t> lab = {3, -1, 10, 0, -1, 7};
+  emu_margin_fwd(cosm.data(), lab.data(), 6, 11, 11, 0, 64.f, 0.5f, 1.2f, 0.1f);
+  emu_margin_bwd(dl.data(), cos0.data(), lab.data(), 6, 11, 11, 1, 64.f, 0.4f, 0.f, 0.f);
+  return !(loss[0] == loss[0]);
+}
+
 // Seeded defects: the test suite checks that the sanitizers DO report them (a detector that never fires proves nothing).
 static void racy_kernel(float* out) {            // a reduction that forgot its __syncthreads
   __shared__ float buf[64];
@@ -218,6 +256,7 @@ int main(int argc, char** argv) {
   rc |= run_gate<float, 1, 3>(false);
   rc |= run_gate<__nv_bfloat16, 0, 0>(false);
   rc |= run_gate<__nv_bfloat16, 1, 2>(true);
+  rc |= run_small();
   rc |= run_pfc(9000, 2700, 300);
   rc |= run_pfc(4096, 40, 200);                                   // positives outnumber num_sample
   rc |= run_cat<float>(301, 64, 18, 1);

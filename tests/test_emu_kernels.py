@@ -26,6 +26,7 @@ from oracle import bn_act as obn
 from oracle import consensus
 from oracle import dap as odap
 from oracle import fm_tail
+from oracle import margins as omarg
 from oracle import partial_fc as opfc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -511,3 +512,89 @@ def test_dap_kernels_match_reference_golden(emu_dap, cl):
     np.testing.assert_allclose(unlay(dxb, CK), g["dx"], rtol=1e-6, atol=1e-7)
     assert np.array_equal(mask.reshape(B, H, W), g["mask"])
     assert np.array_equal(mask.reshape(B, H, W), odap.argmax_mask(unlay(yb, G)))
+
+
+# ------------------------------------------------------------------------------------------------ head: margin math, statistics merge, weight normalisation
+@pytest.fixture(scope="module")
+def emu_head(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_head_small.cpp")
+    lib.emu_wnorm_cast.argtypes = [c_p, c_p, c_p, c_i64, c_i64, c_int]
+    lib.emu_head_local_stats.argtypes = [c_p, c_p, c_p, c_p, c_int, c_int, c_p]
+    lib.emu_head_merge_stats.argtypes = [c_p, c_int, c_int, c_p, c_p]
+    lib.emu_margin_fwd.argtypes = [c_p, c_p, c_i64, c_i64, c_i64, c_int, c_f, c_f, c_f, c_f]
+    lib.emu_margin_bwd.argtypes = [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_int, c_f, c_f, c_f, c_f]
+    for f in ("emu_wnorm_cast", "emu_head_local_stats", "emu_head_merge_stats", "emu_margin_fwd", "emu_margin_bwd"):
+        getattr(lib, f).restype = None
+    return lib
+
+
+@pytest.mark.parametrize("tag", ["arc_p", "arc_f", "arc_am_p", "arc_am_f", "cos_p", "cos_f", "cos_am_p", "cos_am_f"])
+def test_margin_kernels_match_reference_golden(emu_head, tag):
+    """ref headers/margin_losses.py:390-418 (AMArcFace) / :275-303 (AMCosFace) run by make_golden.py on the reference's own
+    6 x 8 fixture (labels with -1) and random inputs, k != 0 included: logits from the cosine matrix, and d logits -> d cos."""
+    g = load_golden("margins")
+    kind = 0 if tag.startswith("arc") else 1
+    s_, m_, a_, k_ = [float(v) for v in g[tag + ".smak"]]
+    cos = omarg.l2_normalize(g[tag + ".e"].astype(np.float64)) @ omarg.l2_normalize(g[tag + ".w"].astype(np.float64)).T
+    label = np.ascontiguousarray(g[tag + ".label"], np.int64)
+    B, C = cos.shape
+    buf = np.ascontiguousarray(cos, np.float32)
+    emu_head.emu_margin_fwd(buf.ctypes.data, label.ctypes.data, B, C, C, kind, s_, m_, a_, k_)
+    np.testing.assert_allclose(buf, g[tag + ".logits"], rtol=2e-5, atol=2e-5 * s_)
+    dl = np.array(g[tag + ".dl"], np.float32)                   # a copy: the kernel works in place
+    cos32 = np.ascontiguousarray(cos, np.float32)
+    emu_head.emu_margin_bwd(dl.ctypes.data, cos32.ctypes.data, label.ctypes.data, B, C, C, kind, s_, m_, a_, k_)
+    want = g[tag + ".dl"].astype(np.float64) * omarg.margin_dcos(cos, label, "arc" if kind == 0 else "cos", s_, m_, a_, k_)
+    np.testing.assert_allclose(dl, want, rtol=2e-4, atol=1e-4 * np.abs(want).max())
+
+
+def test_head_statistics_merge_and_loss(emu_head):
+    """Per-tile partials -> per-rank (max, sum, target logit) -> merge over W ranks -> loss = -mean log p_target
+    (ref partial_fc.py:135-144,159-163: three all-reduces there, one gathered (W, 3, B_tot) array here)."""
+    rng = np.random.default_rng(9)
+    W, B_tot, n_blocks = 3, 37, 11
+    log2e = 1.4426950408889634
+    logits = [rng.normal(0, 8, size=(B_tot, n_blocks * 16)) for _ in range(W)]               # per rank, 16 classes per tile
+    owner = rng.integers(0, W, B_tot)                                                        # the rank holding each row's target class
+    tcol = rng.integers(0, n_blocks * 16, B_tot)
+    gathered = np.zeros((W, 3, B_tot), np.float32)
+    for r in range(W):
+        tiles = logits[r].reshape(B_tot, n_blocks, 16)
+        pmax = np.ascontiguousarray((tiles.max(axis=2) * log2e).T, np.float32)               # (n_blocks, B_tot), log2 units
+        psum = np.ascontiguousarray(np.exp2(tiles * log2e - tiles.max(axis=2, keepdims=True) * log2e).sum(axis=2).T, np.float32)
+        tl = np.where(owner == r, tcol, -1).astype(np.int64)
+        tgt = logits[r][np.arange(B_tot), tcol].astype(np.float32)
+        stats = np.zeros((3, B_tot), np.float32)
+        emu_head.emu_head_local_stats(pmax.ctypes.data, psum.ctypes.data, tgt.ctypes.data,
+                                      tl.ctypes.data, n_blocks, B_tot, stats.ctypes.data)
+        np.testing.assert_allclose(stats[0], logits[r].max(axis=1), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(stats[1], np.exp(logits[r] - logits[r].max(axis=1, keepdims=True)).sum(axis=1), rtol=1e-4)
+        assert np.array_equal(np.isinf(stats[2]), owner != r)
+        gathered[r] = stats
+    gstats = np.zeros((2, B_tot), np.float32)
+    loss = np.zeros(1, np.float32)
+    emu_head.emu_head_merge_stats(gathered.ctypes.data, W, B_tot, gstats.ctypes.data, loss.ctypes.data)
+    full = np.concatenate(logits, axis=1)
+    gmax = full.max(axis=1)
+    gsum = np.exp(full - gmax[:, None]).sum(axis=1)
+    p_t = np.exp(np.array([logits[owner[i]][i, tcol[i]] for i in range(B_tot)]) - gmax) / gsum
+    np.testing.assert_allclose(gstats[0], gmax, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(gstats[1], gsum, rtol=1e-4)
+    want = -np.mean(np.log(np.maximum(p_t, 1e-30)))
+    assert abs(float(loss[0]) - want) <= 1e-4 * abs(want)
+
+
+def test_weight_normalise_cast_kernel(emu_head):
+    """ref partial_fc.py:115 F.normalize(sub_weight) -> unit-norm bf16 rows + 1 / max(||w||, 1e-12), a zero row included."""
+    rng = np.random.default_rng(10)
+    n, D = 21, 512
+    w = (rng.normal(size=(n, D)) * 0.01).astype(np.float32)
+    w[5] = 0.0
+    wn = np.zeros((n, D), np.uint16)
+    inv = np.zeros(n, np.float32)
+    emu_head.emu_wnorm_cast(w.ctypes.data, wn.ctypes.data, inv.ctypes.data, n, D, 1)
+    want = omarg.l2_normalize(w.astype(np.float64))
+    got = from_bf16_bits(wn).reshape(n, D)
+    assert np.abs(got - want).max() <= 2.0 ** -8 * np.abs(want).max()
+    np.testing.assert_allclose(inv, 1.0 / np.maximum(np.linalg.norm(w.astype(np.float64), axis=1), 1e-12), rtol=1e-5)
+    assert not got[5].any()
