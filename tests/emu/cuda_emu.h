@@ -107,6 +107,18 @@ inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline float atomicAdd(float* p, float v) {                      // red.add.f32: a compare-and-swap loop on the bit pattern
+  unsigned* u = reinterpret_cast<unsigned*>(p);
+  unsigned old = __atomic_load_n(u, __ATOMIC_RELAXED), want;
+  float f;
+  do {
+    std::memcpy(&f, &old, 4);
+    f += v;
+    std::memcpy(&want, &f, 4);
+  } while (!__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  std::memcpy(&f, &old, 4);
+  return f;
+}
 
 template <typename V> inline V __ldg(const V* p) { return *p; }
 inline int min(int a, int b) { return a < b ? a : b; }

@@ -33,6 +33,7 @@ int set_error(int code, const char* fmt, ...) {
 #include "emu_bn.cpp"      // the three-launch BN harness (emu_bn_fwd / emu_bn_bwd)
 #include "emu_fm_gate.cpp" // the K-A harness (emu_fm_gate_fwd_multi / emu_fm_gate_bwd_multi)
 #include "emu_dap.cpp"         // K-B: DAP + argmax mask
+#include "emu_fm_mask.cpp"     // K-A extension: shared-memory gate tile, float atomics
 #include "emu_head_small.cpp"  // margin math, weight normalisation, statistics merge, bf16 transpose
 #include "emu_pfc_sample.cpp"  // the K-D harness (remap, mark, radix select with tickets and atomics, searchsorted, row copies)
 
@@ -175,6 +176,20 @@ static int run_pfc(int64_t num_local, int64_t num_sample, int64_t n_labels) {
   return 0;
 }
 
+template <typename T>
+static int run_mask(int64_t Cm, int64_t Hm, int64_t Wm) {
+  const MaskGeom g{2, 7, 5, 64, Hm, Wm, Cm};                 // 70 pixels: a ragged last CTA of 32
+  const int64_t n = g.B * g.H * g.W * g.C, nm = g.B * Hm * Wm * Cm;
+  std::vector<T> yf(n), out(n), dout(n), dyf(n), m(nm);
+  for (auto& v : yf) v = conv<T>(frand());
+  for (auto& v : dout) v = conv<T>(frand());
+  for (auto& v : m) v = conv<T>(frand());
+  std::vector<float> dm(nm, 0.f);
+  mask_fwd<T, 1, 3>(yf.data(), m.data(), out.data(), g);
+  mask_bwd<T, 1, 3>(dout.data(), yf.data(), m.data(), dyf.data(), dm.data(), g);
+  return 0;
+}
+
 static int run_small() {
   // K-B
   const int64_t B = 2, G = 2, kk = 9, HW = 131;
@@ -256,6 +271,8 @@ int main(int argc, char** argv) {
   rc |= run_gate<float, 1, 3>(false);
   rc |= run_gate<__nv_bfloat16, 0, 0>(false);
   rc |= run_gate<__nv_bfloat16, 1, 2>(true);
+  rc |= run_mask<float>(1, 4, 3);
+  rc |= run_mask<__nv_bfloat16>(64, 7, 5);
   rc |= run_small();
   rc |= run_pfc(9000, 2700, 300);
   rc |= run_pfc(4096, 40, 200);                                   // positives outnumber num_sample

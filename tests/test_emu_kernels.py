@@ -598,3 +598,62 @@ def test_weight_normalise_cast_kernel(emu_head):
     assert np.abs(got - want).max() <= 2.0 ** -8 * np.abs(want).max()
     np.testing.assert_allclose(inv, 1.0 / np.maximum(np.linalg.norm(w.astype(np.float64), axis=1), 1e-12), rtol=1e-5)
     assert not got[5].any()
+
+
+# ------------------------------------------------------------------------------------------------ K-A extension: resized / broadcast mask
+@pytest.fixture(scope="module")
+def emu_mask(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_fm_mask.cpp")
+    lib.emu_fm_mask.argtypes = [c_p] * 6 + [c_i64] * 7 + [c_int, c_int]
+    return lib
+
+
+@pytest.mark.parametrize("Cm,Hm,Wm", [(1, 8, 6), (1, 4, 3), (64, 8, 6), (64, 4, 3)])
+@pytest.mark.parametrize("dtype,sigmoid_mul", [(F32, True), (BF16, True), (F32, False)])
+def test_fm_mask_kernels_match_oracle(emu_mask, Cm, Hm, Wm, dtype, sigmoid_mul):
+    """north_star: "mask logits resized to each feature scale, normalised into gates and multiplied into the feature maps, forward
+    and backward" — nearest resize (2x and ragged), single-channel broadcast or per-channel mask, dMask reduced over the channels
+    and over the resize fan-out; vs oracle/fm_tail.py."""
+    rng = np.random.default_rng(Cm + Hm)
+    B, H, W, C = 2, 8, 6, 64
+    q = (lambda a: from_bf16_bits(to_bf16_bits(a)).reshape(a.shape)) if dtype == BF16 else (lambda a: a)
+    yf = q(rng.normal(size=(B, H, W, C)).astype(np.float32))
+    m = q(rng.normal(size=(B, Hm, Wm, Cm)).astype(np.float32))
+    dout = q(rng.normal(size=(B, H, W, C)).astype(np.float32))
+    enc = (lambda t: to_bf16_bits(t).reshape(t.shape)) if dtype == BF16 else (lambda t: np.ascontiguousarray(t, np.float32))
+    dec = (lambda b: from_bf16_bits(b).reshape(b.shape)) if dtype == BF16 else (lambda b: b)
+    yb, mb, db = enc(yf), enc(m), enc(dout)
+    ob, dyb = np.zeros_like(yb), np.zeros_like(yb)
+    dm = np.zeros((B, Hm, Wm, Cm), np.float32)                          # zero-filled by the caller (C-ABI contract)
+    assert emu_mask.emu_fm_mask(db.ctypes.data, yb.ctypes.data, mb.ctypes.data, ob.ctypes.data, dyb.ctypes.data, dm.ctypes.data,
+                                B, H, W, C, Hm, Wm, Cm, dtype, int(sigmoid_mul)) == 0
+    act, arith = ("sigmoid", "mul") if sigmoid_mul else ("tanh", "add")
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == BF16 else dict(rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(dec(ob), fm_tail.fm_mask_fwd(yf, m, act, arith), **tol)
+    wdyf, wdm = fm_tail.fm_mask_bwd(dout, yf, m, act, arith)
+    np.testing.assert_allclose(dec(dyb), wdyf, **tol)
+    np.testing.assert_allclose(dm, wdm, rtol=1e-4, atol=1e-4 * np.abs(wdm).max())
+
+
+# ------------------------------------------------------------------------------------------------ multi-tensor gradient accumulate
+def test_accum_bf16_multi_kernel(tmp_path_factory):
+    """dst_f32 += float(src_bf16) over many tensors in one launch: sizes around the 8192-element block, ragged tails, a tensor whose
+    fp32 view is only 4-byte aligned (the scalar path), more tensors than one launch takes."""
+    lib = build_emu(tmp_path_factory, "emu_accum.cpp")
+    lib.emu_accum_bf16_multi.argtypes = [c_int, c_p, c_p, c_p]
+    rng = np.random.default_rng(12)
+    sizes = [8192, 8193, 5, 16384 + 7, 1, 300] * 17                      # 102 tensors: two launches (96 segments each)
+    flat = rng.normal(size=sum(sizes) + len(sizes) * 4 + 1).astype(np.float32)
+    want = flat.copy()
+    dsts, srcs, keep = [], [], []
+    off = 1                                                              # the first view starts 4 bytes into the buffer
+    for n in sizes:
+        g = to_bf16_bits(rng.normal(size=n).astype(np.float32))
+        keep.append(g)
+        dsts.append(flat[off:off + n].ctypes.data)
+        srcs.append(g.ctypes.data)
+        want[off:off + n] += from_bf16_bits(g)
+        off += (n + 3) // 4 * 4
+    k = len(sizes)
+    assert lib.emu_accum_bf16_multi(k, (c_p * k)(*dsts), (c_p * k)(*srcs), (c_i64 * k)(*sizes)) == 0
+    assert np.array_equal(flat, want)
