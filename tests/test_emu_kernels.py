@@ -299,6 +299,9 @@ def emu_bn(tmp_path_factory):
     (162, 32, 3, 5, False, False, F32), (162, 32, 3, 5, True, False, BF16), (162, 32, 3, 5, False, True, BF16), (162, 32, 3, 5, True, True, F32),
     (401, 64, 7, 4, True, True, BF16), (401, 64, 7, 4, False, False, BF16),
     (98, 256, 2, 2, True, True, BF16),           # 32 channel vectors per row: the warp-per-slot fold; one finalize CTA per channel
+    (5, 16, 9, 7, True, True, BF16),             # more CTAs than rows: empty slabs must merge as zero-weight partials
+    (2, 8, 1, 1, False, False, BF16),            # one channel vector per row, two rows
+    (3, 4, 2, 3, True, False, F32),              # fp32, one vector per row
 ])
 def test_bn_kernels_match_oracle(emu_bn, P, C, G1, G3, prelu, res, dtype):
     """The three-launch forward and backward (slab statistics -> per-channel finalize -> apply) on slabs that do not
