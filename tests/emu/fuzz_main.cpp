@@ -118,8 +118,9 @@ static void fuzz_seg() {
   std::vector<int> parti(seg_parti(g)), partbad(seg_partbad(g));
   emu_launch(dim3((unsigned)g.chunks, (unsigned)N), kSegThreads,
              [&] { seg_stats_kernel<float, 2>(logit.data(), blobs.data(), target.data(), partf.data(), parti.data(), partbad.data(), g); });
+  const int pixel_all = ri(0, 1), kl_all = ri(0, 1);            // drawn once, outside the emulated threads
   emu_launch(dim3(1), kSegThreads, [&] {
-    seg_finalize_kernel<2>(partf.data(), parti.data(), partbad.data(), target.data(), acc.data(), coef.data(), loss.data(), 10.f, 5.f, ri(0, 1), ri(0, 1), g);
+    seg_finalize_kernel<2>(partf.data(), parti.data(), partbad.data(), target.data(), acc.data(), coef.data(), loss.data(), 10.f, 5.f, pixel_all, kl_all, g);
   });
   emu_launch(dim3((unsigned)g.chunks, (unsigned)N), kSegThreads,
              [&] { seg_bwd_kernel<float, 2>(logit.data(), blobs.data(), coef.data(), nullptr, dlogit.data(), g); });
