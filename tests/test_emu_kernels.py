@@ -255,7 +255,7 @@ def sanitizer_builds(tmp_path_factory):
     procs = {}
     for tag, (flags, _, _) in SANITIZERS.items():
         exe = str(d / tag)
-        procs[tag] = (exe, subprocess.Popen(["g++", "-std=c++20", "-O1", "-g", "-pthread", "-I" + CUDA_INC] + flags +
+        procs[tag] = (exe, subprocess.Popen(["g++", "-std=c++20", "-O1", "-pthread", "-I" + CUDA_INC] + flags +      # add -g to symbolise a report
                                             [os.path.join(HERE, "emu", "sanitize_main.cpp"), "-o", exe],
                                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     out = {}
