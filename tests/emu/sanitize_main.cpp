@@ -134,7 +134,7 @@ static int run_bn(int64_t P, int64_t C, int G1, int G3) {
 
 template <typename T, int ACT, int ARITH>
 static int run_gate(bool with_fout) {
-  const int64_t n[3] = {9413, 19, 2307};                       // scalar tails, a segment smaller than one vector pass
+  const int64_t n[3] = {3077, 19, 1203};                       // scalar tails, a segment smaller than one vector pass
   const int vn = sizeof(T) == 4 ? 4 : 8;
   std::vector<T> yf[3], z[3], fo[3], out[3], d[3], dyf[3], dz[3];
   FwdSegs fs{};
@@ -259,14 +259,14 @@ int main(int argc, char** argv) {
     return 0;
   }
   int rc = 0;
-  rc |= run_seg<float, 2>(3, 1353, 3, 0);
+  rc |= run_seg<float, 2>(2, 1353, 3, 0);
   rc |= run_seg<__nv_bfloat16, 3>(2, 1030, 4, 1);
   rc |= run_seg<float, 4>(2, 77, 2, 1);
   rc |= run_sgd<1>(20, 9, true);
   rc |= run_sgd<4>(11, 11, false);
   rc |= run_bn<float, false, false>(162, 32, 3, 5);
   rc |= run_bn<__nv_bfloat16, true, true>(162, 32, 3, 5);
-  rc |= run_bn<__nv_bfloat16, false, true>(75, 128, 2, 3);
+  rc |= run_bn<__nv_bfloat16, false, true>(40, 64, 2, 3);
   rc |= run_bn<float, true, false>(53, 64, 4, 2);
   rc |= run_gate<float, 1, 3>(false);
   rc |= run_gate<__nv_bfloat16, 0, 0>(false);
@@ -274,7 +274,7 @@ int main(int argc, char** argv) {
   rc |= run_mask<float>(1, 4, 3);
   rc |= run_mask<__nv_bfloat16>(64, 7, 5);
   rc |= run_small();
-  rc |= run_pfc(9000, 2700, 300);
+  rc |= run_pfc(4100, 1200, 200);                                // two CTAs, ragged second tile
   rc |= run_pfc(4096, 40, 200);                                   // positives outnumber num_sample
   rc |= run_cat<float>(301, 64, 18, 1);
   rc |= run_cat<__nv_bfloat16>(130, 128, 18, 2);
