@@ -95,3 +95,19 @@ def test_partial_fc_rejects_unfusable_margin_callable():
     from msml_b200.headers import PartialFC
     with pytest.raises(TypeError, match="kind, s, m, a, k"):
         PartialFC(0, 0, 1, 8, False, lambda logits, label: logits, 100)
+
+
+def test_cpu_emulation_macro_never_reaches_the_product_build():
+    """MSML_CPU_EMU (plain-C++ stand-ins for inline PTX, used by tests/emu to run the kernels on the host) must be defined by the
+    emulation harness only: not by the build flags, not by any source under msml_b200/."""
+    import glob
+    import os
+    from msml_b200 import _build
+    assert not any("MSML_CPU_EMU" in f for f in _build.NVCC_FLAGS)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, "msml_b200", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".cu", ".cuh", ".h", ".py")):
+            text = open(path, encoding="utf-8", errors="ignore").read()
+            assert "#define MSML_CPU_EMU" not in text and "-DMSML_CPU_EMU" not in text, path
+    defs = [p for p in glob.glob(os.path.join(root, "tests", "emu", "*.cpp")) if "#define MSML_CPU_EMU" in open(p).read()]
+    assert defs, "the emulation harness is where the macro is defined"
