@@ -12,9 +12,12 @@ One step = backbone forward -> F.normalize -> PartialFC.forward_backward -> feat
 -> clip_grad_norm_(5) -> SGD steps -> pfc.update()   (ref train.py:283-300, the PartialFC variant).
 
 Prints ONE JSON line (rank 0).  `value` = imgs/s with inputs resident in HBM; `e2e` = the same step
-fed from pinned host memory each step with the loss read back each step.  `roofline` is measured
-live: every launch of this library is bracketed by CUDA events on its own stream inside the timed
-region (msml_profile_*), work = algorithmic bytes / flops of that launch.
+fed from pinned host memory each step with the loss read back each step.  `roofline.achieved` is measured
+live: every launch of this library is bracketed by CUDA events on its own stream (msml_profile_*), work =
+algorithmic bytes / flops of that launch.  `roofline.traffic` is NOT measured in this run: it is the DRAM byte count of
+that kernel from the committed `ncu --set full` capture named in `traffic_source`.  Before anything is timed, every
+rank runs one head step on seeded embeddings and rank 0 checks the loss it reports against the fp64 oracle evaluated
+on the gathered inputs (`head_check`): the class-sharded path is verified on the very ranks that are benchmarked.
 """
 import argparse
 import json
@@ -89,11 +92,11 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ CPU port
 def cpu_step_factory(batch, frb="iresnet50", threads=None):
-    """The reference's step restated on CPU (oracle/): torch-CPU fp32 backbone + numpy PartialFC."""
-    import numpy as np
+    """The reference's step restated on CPU in torch fp32, all host threads (oracle/model_cpu.py + oracle/partial_fc_torch.py:
+    the same ATen calls the reference issues, ref train.py:283-300 and headers/partial_fc.py:96-177)."""
     import torch
     from msml_b200.backbones import MSML
-    from oracle import model_cpu, partial_fc as opfc
+    from oracle import model_cpu, partial_fc_torch as pt
     if threads:
         torch.set_num_threads(threads)
     torch.manual_seed(1)
@@ -101,24 +104,30 @@ def cpu_step_factory(batch, frb="iresnet50", threads=None):
     sd = model_cpu.trainable_state(net)
     params = [v for v in sd.values() if v.requires_grad]
     opt = torch.optim.SGD(params, lr=0.1 * batch / 512, momentum=0.9, weight_decay=5e-4)
-    rng = np.random.default_rng(1)
-    weight = rng.normal(0, 0.01, (NUM_CLASSES, 512))
-    mom = np.zeros_like(weight)
+    weight = torch.normal(0, 0.01, (NUM_CLASSES, 512))
+    mom = torch.zeros_like(weight)
+    split = {"backbone_s": 0.0, "head_s": 0.0}
 
     def step():
+        t0 = time.perf_counter()
         img = torch.randn(batch, 3, 112, 112)
         label = torch.randint(0, NUM_CLASSES, (batch,))
         feat, _seg = model_cpu.msml_forward(sd, img, frb, training=True, fm_params=FM_PARAMS)
         featn = torch.nn.functional.normalize(feat)
-        res = opfc.step([featn.detach().numpy()], [label.numpy()], [weight], NUM_CLASSES, "arc", S, M)
-        featn.backward(torch.from_numpy(res["x_grad"][0]).float())
+        t1 = time.perf_counter()
+        x_grad, w_grad, loss = pt.head_step(featn, label, weight, "arc", S, M)      # PartialFC.forward_backward
+        t2 = time.perf_counter()
+        featn.backward(x_grad)
         torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 5)
         opt.step()
         opt.zero_grad()
-        g = res["w_grad"][0] + 5e-4 * weight          # SGD(momentum .9, wd 5e-4) on the class centres
-        mom[...] = 0.9 * mom + g
-        weight[...] -= 0.1 * mom
-        return float(res["loss"])
+        t3 = time.perf_counter()
+        pt.sgd_update(weight, mom, w_grad)                                          # opt_pfc.step() (sample_rate 1: update() is a no-op)
+        t4 = time.perf_counter()
+        split["backbone_s"] += (t1 - t0) + (t3 - t2)
+        split["head_s"] += (t2 - t1) + (t4 - t3)
+        return float(loss)
+    step.split = split
     return step
 
 
@@ -128,13 +137,16 @@ def run_cpu(batch, steps, warmup):
     step = cpu_step_factory(batch, threads=cores)
     for _ in range(warmup):
         step()
+    step.split.update(backbone_s=0.0, head_s=0.0)
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
     return dict(value=steps * batch / dt, unit="imgs/s", cores=torch.get_num_threads(), kind="port",
-                sample="%d steps of batch %d (of the %d/GPU workload), fp32, oracle/model_cpu.py + oracle/partial_fc.py" % (steps, batch, BATCH),
-                ms_per_step=dt / steps * 1e3)
+                sample="%d steps of batch %d (of the %d/GPU workload), torch-CPU fp32 on all host threads: oracle/model_cpu.py "
+                       "(backbone) + oracle/partial_fc_torch.py (PartialFC step, the reference's own ATen call sequence)" % (steps, batch, BATCH),
+                ms_per_step=dt / steps * 1e3, head_share=round(step.split["head_s"] / max(dt, 1e-9), 4),
+                backbone_share=round(step.split["backbone_s"] / max(dt, 1e-9), 4))
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -150,20 +162,30 @@ def collect_profile(lib):
 
 
 _TRAFFIC = None
+TRAFFIC_FILES = ("r02_traffic.json", "r01c_traffic.json")      # newest capture first
 
 
 def ncu_traffic(name, suffix=""):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this kernel
-    (profiles/r01c_traffic.json), or None if that kernel was not captured."""
+    """-> (dram__bytes_read.sum + dram__bytes_write.sum per launch, source) from the newest COMMITTED `ncu --set full`
+    capture of this kernel (profiles/*_traffic.json), or (None, None) if it was never captured.  Not measured in this run:
+    ncu cannot run inside a timed benchmark, so the number is a property of the kernel at the captured commit and the
+    JSON line says which file it came from."""
     global _TRAFFIC
     if _TRAFFIC is None:
-        path = os.path.join(ROOT, "profiles", "r01c_traffic.json")
-        _TRAFFIC = json.load(open(path)) if os.path.exists(path) else {}
-    rec = _TRAFFIC.get(name + suffix)
-    return rec["dram_bytes_per_launch"] if rec else None
+        _TRAFFIC = []
+        for f in TRAFFIC_FILES:
+            path = os.path.join(ROOT, "profiles", f)
+            if os.path.exists(path):
+                _TRAFFIC.append((f, json.load(open(path))))
+    for f, table in _TRAFFIC:
+        rec = table.get(name + suffix)
+        if rec:
+            return rec["dram_bytes_per_launch"], "profiles/%s (%s)" % (f, rec.get("captured", table.get("_captured", "ncu --set full, earlier commit")))
+    return None, None
 
 
 def roofline_entry(name, rec, pk, sustained=True, traffic_suffix=""):
+    traffic, traffic_source = ncu_traffic(name, traffic_suffix)
     avg_s = rec["total_ms"] / rec["launches"] * 1e-3
     per_launch = rec["work"] / rec["launches"]
     if name.endswith("_gemm"):
@@ -174,15 +196,15 @@ def roofline_entry(name, rec, pk, sustained=True, traffic_suffix=""):
         if t_hbm > t_tensor:   # short-M contraction: the class-centre stream binds, not the tensor pipe
             gbs = bytes_pl / avg_s / 1e9
             return dict(kernel=name, bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
-                        traffic=ncu_traffic(name, traffic_suffix), launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=bytes_pl,
+                        traffic=traffic, traffic_source=traffic_source, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=bytes_pl,
                         tflops=round(ach, 2), note="HBM-bound at this M: min bytes = operands + outputs streamed once",
                         peak_source=pk["source"])
         return dict(kernel=name, bound="tensor", achieved=round(ach, 2), peak=peak, unit="TFLOP/s", frac=round(ach / peak, 4),
-                    traffic=ncu_traffic(name, traffic_suffix), launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
+                    traffic=traffic, traffic_source=traffic_source, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
                     peak_source=pk["source"] + (", sustained" if sustained else ", burst"))
     ach = per_launch / avg_s / 1e9
     return dict(kernel=name, bound="hbm", achieved=round(ach, 1), peak=pk["hbm"], unit="GB/s", frac=round(ach / pk["hbm"], 4),
-                traffic=ncu_traffic(name, traffic_suffix), launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
+                traffic=traffic, traffic_source=traffic_source, launches=rec["launches"], avg_us=round(avg_s * 1e6, 2), work_per_launch=per_launch,
                 peak_source=pk["source"])
 
 
@@ -212,8 +234,8 @@ def fusion_microbench(iters=20, batch=512):
     return dict(batch=batch, fwd_ms=round(fwd, 4), bwd_ms=round(bwd, 4), fwd_gbs=round(3 * elems * 2 / fwd / 1e6, 1),
                 bwd_gbs=round(5 * elems * 2 / bwd / 1e6, 1), fwd_bwd_gbs=round(8 * elems * 2 / (fwd + bwd) / 1e6, 1),
                 algorithmic_bytes=8 * elems * 2,
-                ncu_dram_bytes={"fwd": ncu_traffic("fm_gate_fwd", "@config2"), "bwd": ncu_traffic("fm_gate_bwd", "@config2")}
-                if batch == 512 else None)
+                ncu_dram_bytes={"fwd": ncu_traffic("fm_gate_fwd", "@config2")[0], "bwd": ncu_traffic("fm_gate_bwd", "@config2")[0],
+                                "source": ncu_traffic("fm_gate_fwd", "@config2")[1]} if batch == 512 else None)
 
 
 def head_microbench(iters=5, b_tot=1024, n_s=125000):
@@ -363,6 +385,50 @@ def aux_microbench(iters=10):
     return out
 
 
+def head_parity_check(pfc, rank, world, dev, batch, classes, tol=1e-3):
+    """One head step on seeded L2-normalised embeddings on every rank (real NCCL ranks when world > 1); rank 0 gathers
+    the inputs and the class shards and evaluates the reference's loss in fp64 (oracle/partial_fc.py: forward_loss follows
+    ref headers/partial_fc.py:132-163 over all simulated ranks).  Raises if the loss the ranks report differs by more
+    than `tol` relative.  Only for sample_rate 1 (the sampled path is checked index-for-index in run_head)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    feat = torch.nn.functional.normalize(torch.randn(batch, 512, device=dev, generator=g))
+    label = torch.randint(0, classes, (batch,), device=dev, generator=g)
+    x_grad, loss = pfc.forward_backward(label, feat, None)
+    pfc.sub_weight.grad = None
+    feat16 = feat.to(torch.bfloat16)                   # what the head contracts (it gathers the embeddings in bf16)
+    nl_max = classes // world + 1
+    wpad = torch.zeros(nl_max, 512, device=dev)
+    wpad[:pfc.num_local] = pfc.weight
+    if world > 1:
+        feats = [torch.empty_like(feat16) for _ in range(world)]
+        labels = [torch.empty_like(label) for _ in range(world)]
+        ws = [torch.empty_like(wpad) for _ in range(world)]
+        losses = [torch.empty_like(loss) for _ in range(world)]
+        dist.all_gather(feats, feat16); dist.all_gather(labels, label); dist.all_gather(ws, wpad); dist.all_gather(losses, loss)
+    else:
+        feats, labels, ws, losses = [feat16], [label], [wpad], [loss]
+    out = None
+    if rank == 0:
+        from oracle import partial_fc as opfc
+        t0 = time.perf_counter()
+        weights = [ws[r][:opfc.shard_geometry(classes, world, r)[0]].double().cpu().numpy() for r in range(world)]
+        want, _, _ = opfc.forward_loss([f.double().cpu().numpy() for f in feats], [l.cpu().numpy() for l in labels], weights,
+                                       classes, "arc", S, M)
+        got = [float(l) for l in losses]
+        rel = max(abs(v - want) for v in got) / abs(want)
+        out = {"loss_per_rank": [round(v, 6) for v in got], "oracle_loss_fp64": round(float(want), 6), "max_rel_err": float("%.3g" % rel),
+               "tolerance": tol, "ranks": world, "b_tot": batch * world, "classes": classes, "x_grad_finite": bool(torch.isfinite(x_grad).all()),
+               "oracle_s": round(time.perf_counter() - t0, 1)}
+        if not (rel <= tol and np.isfinite(want)):
+            raise SystemExit("bench.py: head parity check FAILED on %d rank(s): %r" % (world, out))
+    if world > 1:
+        dist.barrier()
+    return out
+
+
 def run_train(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -385,6 +451,7 @@ def run_train(args, rank, local_rank, world):
     opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
     opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
     step = TrainStep(net, pfc, opt, opt_pfc, (BATCH, 3, 112, 112), world_size=world, max_norm=5.0, use_graph=not args.eager)
+    head_check = head_parity_check(pfc, rank, world, dev, BATCH, NUM_CLASSES)     # before anything trains the class centres
 
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     n_buf = 4
@@ -483,42 +550,84 @@ def run_train(args, rank, local_rank, world):
         "roofline_pass": "%d eager single-stream replays of the same step after the timed region, CUDA events around every launch" % prof_steps,
         "clocks": clocks,
         "loss": round(loss, 4),
+        "head_check": head_check,
     }
     return res
 
 
+def sampled_index_check(pfc, label_all, rank, dev):
+    """BASELINE config 4: the class indices this rank samples must equal, bit for bit, what ref headers/partial_fc.py:83-94
+    selects from the same torch.rand draw (oracle/partial_fc.py: sample).  -> dict for the JSON line."""
+    import numpy as np
+    import torch
+    from oracle import partial_fc as opfc
+    state = torch.cuda.get_rng_state(dev)
+    tl = label_all.clone()
+    pfc.sample(tl)
+    torch.cuda.synchronize()
+    torch.cuda.set_rng_state(state, dev)
+    perm = torch.rand(size=[pfc.num_local], device=dev).cpu().numpy()          # the draw sample() consumed
+    want_tl, want_index = opfc.sample(label_all.cpu().numpy(), perm, pfc.class_start, pfc.num_local, pfc.num_sample, pfc.sample_rate)
+    ok = bool(np.array_equal(pfc.index.cpu().numpy(), want_index) and np.array_equal(tl.cpu().numpy(), want_tl))
+    return {"rank": rank, "n_index": int(pfc.index.numel()), "bit_exact": ok}
+
+
 def run_head(args, rank, local_rank, world):
-    """BASELINE config 4 style head-only sweep (per-rank shard of `classes`, B=128/GPU)."""
+    """BASELINE config 4: PartialFC head-only step (forward_backward -> optimizer step -> update) on a per-rank shard of
+    `classes`, B = --batch per GPU, sample_rate 0.1 / 1.0, class-sharded over `world` ranks."""
     import torch
     import torch.distributed as dist
     from msml_b200 import _lib, ops
-    from msml_b200.headers import ArcFace, PartialFC
+    from msml_b200.headers import ArcFace, PartialFC, PartialFCSGD
     lib = _lib.load()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     pk = peaks()
     torch.manual_seed(1)
     BATCH = args.batch                                       # per-rank batch (shadows the module constant on purpose)
+    sampled = int(args.sample_rate) != 1
     pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), args.classes, sample_rate=args.sample_rate, embedding_size=512)
-    opt = torch.optim.SGD([{"params": pfc.parameters()}], lr=0.1, momentum=0.9, weight_decay=5e-4)
+    hp = dict(lr=0.1, momentum=0.9, weight_decay=5e-4)
+    opt = PartialFCSGD(pfc, **hp) if args.fused_sgd else torch.optim.SGD([{"params": pfc.parameters()}], **hp)
+    check = None
+    if not sampled and not args.no_head_check:
+        check = head_parity_check(pfc, rank, world, dev, BATCH, args.classes)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     feat = torch.nn.functional.normalize(torch.randn(BATCH, 512, device=dev, generator=g))
     label = torch.randint(0, args.classes, (BATCH,), device=dev, generator=g)
-    for _ in range(args.warmup):
+    if sampled:                                              # bit-exact sampled indices on every rank, before timing
+        label_all = torch.empty(BATCH * world, dtype=torch.int64, device=dev)
+        pfc.comm.all_gather(label_all, label)
+        rec = sampled_index_check(pfc, label_all, rank, dev)
+        recs = [None] * world
+        if world > 1:
+            dist.all_gather_object(recs, rec)
+        else:
+            recs = [rec]
+        check = {"sampled_index_bit_exact_per_rank": [r["bit_exact"] for r in recs], "n_index_per_rank": [r["n_index"] for r in recs]}
+        if rank == 0 and not all(check["sampled_index_bit_exact_per_rank"]):
+            raise SystemExit("bench.py: sampled class indices differ from the oracle: %r" % check)
+
+    def one():
         pfc.forward_backward(label, feat, opt); opt.step(); pfc.update()
+    # warm-up: the caching allocator needs a few steps to settle (the first two sampled steps cudaMalloc ~0.4 GB of gather
+    # buffers each: tens of ms, once), so at least 5 untimed steps whatever --warmup says
+    for _ in range(max(args.warmup, 5)):
+        one()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     lib.msml_profile_enable(1)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        pfc.forward_backward(label, feat, opt); opt.step(); pfc.update()
-    b.record()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        one()
+        ev[i + 1].record()
     torch.cuda.synchronize()
     lib.msml_profile_enable(0)
     prof = collect_profile(lib)
-    ms = a.elapsed_time(b)
+    per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+    ms = ev[0].elapsed_time(ev[-1])
     if world > 1:
         t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     if rank != 0:
@@ -527,12 +636,17 @@ def run_head(args, rank, local_rank, world):
     flops = 6.0 * BATCH * world * n_s * 512
     rl = sorted((roofline_entry(k, v, pk, sustained=False) for k, v in prof.items()), key=lambda r: -r["avg_us"] * r["launches"])
     gemm_ms = sum(v["total_ms"] for k, v in prof.items() if k.endswith("_gemm")) / args.steps
+    own_ms = sum(v["total_ms"] for v in prof.values()) / args.steps
     return {"metric": "PartialFC head step", "value": round(args.steps * BATCH * world / (ms * 1e-3), 1), "unit": "imgs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 5), "ms_per_step": round(ms / args.steps, 4),
+            "ms_per_step_median": round(per_step[len(per_step) // 2], 4), "ms_per_step_max": round(per_step[-1], 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "PartialFC head only, %d classes, sample_rate %g, B=%d/GPU" % (args.classes, args.sample_rate, BATCH),
-                       "n_s_per_rank": n_s},
+            "config": {"workload": "PartialFC head only (forward_backward + SGD + update), %d classes, sample_rate %g, B=%d/GPU, %d rank(s) (BASELINE config 4)"
+                                   % (args.classes, args.sample_rate, BATCH, world),
+                       "n_s_per_rank": n_s, "optimizer": "headers.PartialFCSGD (fused)" if args.fused_sgd else "torch.optim.SGD + update()"},
             "head_algorithmic_tflops_over_gemm_time": round(flops / (gemm_ms * 1e-3) / 1e12, 2),
+            "own_kernel_ms_per_step": round(own_ms, 4), "gemm_ms_per_step": round(gemm_ms, 4),
+            "gpu_launches": int(ops.launch_count()), "head_check": check,
             "rooflines": rl, "roofline": rl[0] if rl else None}
 
 
@@ -593,7 +707,9 @@ def main():
     ap.add_argument("--sample-rate", type=float, default=1.0)
     ap.add_argument("--batch", type=int, default=BATCH, help="head workload only: per-rank batch (1024 on one GPU reproduces the "
                     "per-rank GEMM shapes of the 8-GPU config-4 run: B_tot=1024 rows against a 125,000-class shard)")
-    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-batch", type=int, default=16, help="images per step of the CPU arm (a bounded sample of the 128/GPU workload)")
+    ap.add_argument("--fused-sgd", action="store_true", help="head workload: headers.PartialFCSGD instead of torch.optim.SGD + update()")
+    ap.add_argument("--no-head-check", action="store_true", help="skip the fp64-oracle loss check before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
     args = ap.parse_args()
@@ -606,7 +722,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = min(args.steps, 12)
+        steps = min(args.steps, 8)
         cb = run_cpu(args.cpu_batch, steps, min(args.warmup, 1))
         emit(({
             "impl": "reference", "metric": "train imgs/s ires50-MSML+PartialFC", "value": round(cb["value"], 3), "unit": "imgs/s",
@@ -614,7 +730,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ires50_msml + PartialFC(ArcFace s=64 m=0.5, 93431 classes, sample_rate 1) training step on host CPU "
                                    "cores, 112x112 (BASELINE config 3 shapes; bounded sample: batch %d per step)" % args.cpu_batch},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "head_share", "backbone_share")},
             "e2e": {"value": round(cb["value"], 3), "unit": "imgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -658,8 +774,8 @@ def main():
         res["fusion_microbench"] = fusion_microbench()
         res["head_microbench"] = head_microbench()
         if world == 1 and not args.no_cpu_baseline:
-            cb = run_cpu(args.cpu_batch, 6, 1)
-            res["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cb = run_cpu(args.cpu_batch, 4, 1)
+            res["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "head_share", "backbone_share")}
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -10,6 +10,8 @@
 //     m'  = mu * mom[row] + (1 - dampening) * d      (torch.optim.SGD with an existing momentum buffer: PartialFC always
 //     w'  = w[row] - lr * (nesterov ? d + mu*m' : m')  supplies one, ref partial_fc.py:114)
 //     w[row] = w', mom[row] = m'                     in place in the shard: no gather, no scatter
+//     momentum == 0: w' = w - lr * d and the momentum buffer is left untouched (torch.optim.SGD ignores dampening and
+//     never creates or updates a buffer in that case)
 //     [wn[r] = bf16(w' / max(||w'||, 1e-12)), inv_norm[r] = 1 / max(||w'||, 1e-12)]     (valid for the next step when its
 //                                                                                        sample has the same rows: sample_rate 1)
 // = 3 reads + 2 writes (+ a half-width write).  lr is read from device memory when lr_dev is given (captured graphs
@@ -59,14 +61,14 @@ pfc_sgd_kernel(float* __restrict__ weight, float* __restrict__ weight_mom, const
     for (int i = 0; i < 4; ++i) {
       const float d = fmaf(p.weight_decay, wf[i], gf[i]);
       const float mn = fmaf(p.momentum, mf[i], (1.f - p.dampening) * d);
-      const float upd = p.nesterov ? fmaf(p.momentum, mn, d) : mn;
+      const float upd = p.momentum == 0.f ? d : (p.nesterov ? fmaf(p.momentum, mn, d) : mn);
       const float wnew = fmaf(-lr, upd, wf[i]);
       mf[i] = mn;
       wf[i] = wnew;
       ss = fmaf(wnew, wnew, ss);
     }
     w4[v * 32 + lane] = w[v];
-    m4[v * 32 + lane] = m[v];
+    if (p.momentum != 0.f) m4[v * 32 + lane] = m[v];
   }
   if (wn == nullptr) return;                               // uniform over the grid
 #pragma unroll

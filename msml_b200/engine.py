@@ -223,8 +223,8 @@ class TrainStep:
             if opt is None:
                 continue
             for g in opt.param_groups:
-                if not g.get("fused"):
-                    continue        # only torch's fused kernels take a tensor lr without a host read (illegal while capturing)
+                if not (g.get("fused") or g.get("capturable_lr")):
+                    continue        # only torch's fused kernels and headers.PartialFCSGD take a tensor lr without a host read
                 if not isinstance(g["lr"], torch.Tensor):
                     g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=self.device)
                 elif g["lr"].device != self.device:

@@ -9,8 +9,9 @@ but the work is done by libmsml_b200.so:
                    searchsorted / gather_rows              (ref :77-94; torch.rand stays in torch so
                    the generator is consumed exactly as in the reference)
   prepare          msml_wnorm_cast: fp32 master rows -> unit-norm bf16 + 1/||w||            (ref :115)
-  forward_backward msml_head_fwd (tcgen05 GEMM, margin/scale/online-softmax epilogue; logits are
-                   never materialised) -> ONE all-gather of per-row (max, sum, target) instead of
+  forward_backward msml_head_fwd (tcgen05 GEMM, margin/scale/online-softmax epilogue; the fp32 logits are
+                   never materialised — the backward keeps one bf16 (B_tot x n_s) dcos matrix in the
+                   workspace) -> ONE all-gather of per-row (max, sum, target) instead of
                    the reference's three all-reduces (:136,141,162) -> msml_head_merge_stats ->
                    msml_head_bwd (recompute + dX + dW with the normalise-backward epilogue)
                    -> reduce-scatter of dX (:172-175)
@@ -109,13 +110,17 @@ class PartialFC(Module):
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, name, shape, dtype):
-        """Persistent scratch (torch-allocated so the caching allocator sees it)."""
-        key = (name, tuple(shape), dtype)
-        t = self._ws.get(key)
-        if t is None:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
-            self._ws[key] = t
-        return t
+        """Persistent scratch (torch-allocated so the caching allocator sees it): one buffer per name, grown to the
+        largest size seen (n_s changes from step to step when the positives outnumber num_sample, ref :89-90) and
+        handed out as a view of the requested shape."""
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        t = self._ws.get(name)
+        if t is None or t.dtype != dtype or t.numel() < numel:
+            t = torch.empty((max(numel, 1),), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:numel].view(tuple(shape))
 
     def save_params(self):
         torch.save(self.weight.data, self.weight_name)
@@ -177,8 +182,11 @@ class PartialFC(Module):
     @torch.no_grad()
     def update(self):
         """Scatter the sampled rows back into the shard (ref :101-104)."""
-        if getattr(self, "_fused_sgd", None) is not None:
-            return          # headers.PartialFCSGD updates the shard rows in place: the gathered copies are stale, not newer
+        if getattr(self, "_fused_step_done", False):
+            # headers.PartialFCSGD.step() just updated the shard rows in place: the gathered copies are stale, not newer.
+            # The flag covers that one step only — a stock optimizer stepping this module later scatters as usual.
+            self._fused_step_done = False
+            return
         lib = load()
         rows = self.index.numel()
         check(lib.msml_scatter_rows_f32(_ptr(self.weight_mom), _ptr(self.index), _ptr(self.sub_weight_mom), rows,

@@ -11,7 +11,11 @@ gather, :112-114 optimizer-state surgery, :101-104 scatter back):
 hyper-parameters, same ``param_groups`` (LR schedulers work), same ``step()`` / ``zero_grad()``.  Its step is ONE kernel
 (msml_pfc_sgd_update, csrc/pfc_sgd_kernels.cuh) that applies momentum SGD with weight decay to the sampled rows
 in place in the shard (``weight`` / ``weight_mom``), so ``module_partial_fc.update()`` has nothing left to scatter and
-becomes a no-op.  Arithmetic is torch.optim.SGD's with an existing momentum buffer (PartialFC always supplies one).
+becomes a no-op FOR THAT STEP: ``step()`` raises a flag on the module that ``update()`` consumes, so a module that is later
+stepped by a stock optimizer again scatters its gathered rows back as the reference does.  Arithmetic is
+torch.optim.SGD's with an existing momentum buffer (PartialFC always supplies one); momentum == 0 ignores dampening and
+leaves the buffer untouched, as torch does.  ``capturable_lr`` in the defaults tells ``engine.TrainStep`` to turn the
+learning rate into a device tensor at capture time (the kernel reads it from memory), so LR schedules survive graph replays.
 """
 import ctypes
 
@@ -40,10 +44,10 @@ class PartialFCSGD(torch.optim.Optimizer):
             if not hasattr(module, attr):
                 raise TypeError("PartialFCSGD drives a PartialFC module (missing attribute %r)" % attr)
         load()
-        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov)
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov,
+                        capturable_lr=True)
         super().__init__([{"params": list(module.parameters())}], defaults)
         self.module = module
-        module._fused_sgd = self            # PartialFC.update() has nothing to scatter once this optimizer owns the update
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -70,4 +74,5 @@ class PartialFCSGD(torch.optim.Optimizer):
                                          _ptr(lr_dev), 0.0 if lr_dev is not None else float(lr), float(g["momentum"]),
                                          float(g["weight_decay"]), float(g["dampening"]), int(bool(g["nesterov"])), None, None,
                                          stream_ptr()))
+        m._fused_step_done = True           # this step's rows are already in the shard: the next update() has nothing to scatter
         return loss

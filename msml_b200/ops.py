@@ -146,14 +146,15 @@ class _FMCat(torch.autograd.Function):
 def fm_cat(yf, yo, multiple=8):
     """-> (x, pad, yf_tail): x = cat((yf, yo), dim=1) with `pad` zero channels appended up to a multiple of ``multiple``
     (cuDNN's bf16 tensor-core kernels need C % 8 == 0), one kernel each way; yf_tail is yf for the operator's fused tail
-    (see _FMCat).  Channel counts the vector kernel does not take go through cat_channels_padded."""
+    (see _FMCat).  Like every operator of this package it has only the CUDA implementation: CPU tensors and feature
+    channel counts that are not whole 16-byte vectors raise (every iResNet stage has C % 8 == 0)."""
     if yf.dim() != 4 or yo.dim() != 4 or yf.shape[0] != yo.shape[0] or yf.shape[2:] != yo.shape[2:]:
         raise ValueError("fm_cat: yf %s and yo %s must agree in batch and spatial size" % (tuple(yf.shape), tuple(yo.shape)))
-    vn = 4 if yf.dtype == torch.float32 else 8
-    if not yf.is_cuda or yf.shape[1] % vn or multiple % vn:
-        x, pad = cat_channels_padded((yf, yo.to(yf.dtype)), multiple)
-        return x, pad, yf
     require_cuda(yf, yo)
+    vn = 4 if yf.dtype == torch.float32 else 8
+    if yf.shape[1] % vn or multiple % vn:
+        raise ValueError("fm_cat: feature channels (%d) and the padding multiple (%d) must be multiples of %d (16-byte vectors)"
+                         % (yf.shape[1], multiple, vn))
     C, Co = yf.shape[1], yo.shape[1]
     pad = (-(C + Co)) % multiple
     if torch.is_grad_enabled() and (yf.requires_grad or yo.requires_grad):

@@ -133,3 +133,28 @@ def step(features_per_rank, labels_per_rank, weights_per_rank, num_classes, kind
     return dict(x_grad=x_grad, w_grad=w_grads, index=idxs, total_label=tls, loss=loss,
                 rowmax=gmax, rowsum=gsum, target_prob=tgt,
                 logits=[f["logits"] for f in fw], dx_full=x_grads_full)
+
+
+def forward_loss(features_per_rank, labels_per_rank, weights_per_rank, num_classes, kind, s, m, a=0.0, k=0.0, chunk=256):
+    """Loss of the full-class step only (ref :132-163), evaluated in row chunks so that BASELINE-size problems
+    (B_tot = 1024 x 93,431 classes) fit in a few hundred MB: used by bench.py to check the loss its first step reports
+    on N ranks.  -> (loss, rowmax (B_tot,), rowsum (B_tot,))."""
+    W = len(features_per_rank)
+    X = np.concatenate([np.asarray(f, np.float64) for f in features_per_rank], 0)
+    L = np.concatenate([np.asarray(l, np.int64) for l in labels_per_rank], 0)
+    B_tot = X.shape[0]
+    geo = [shard_geometry(num_classes, W, r) for r in range(W)]
+    wns = [l2_normalize(np.asarray(w, np.float64)) for w in weights_per_rank]
+    tls = [remap_labels(L, g[1], g[0]) for g in geo]
+    gmax, gsum, tgt = np.empty(B_tot), np.empty(B_tot), np.zeros(B_tot)
+    for lo in range(0, B_tot, chunk):
+        hi = min(lo + chunk, B_tot)
+        logits = [margin_apply(X[lo:hi] @ wns[r].T, tls[r][lo:hi], kind, s, m, a, k) for r in range(W)]
+        mx = np.max(np.stack([l.max(axis=1) for l in logits], 0), axis=0)                      # all_reduce MAX (:136)
+        exps = [np.exp(l - mx[:, None]) for l in logits]
+        sm = np.sum(np.stack([e.sum(axis=1) for e in exps], 0), axis=0)                        # all_reduce SUM (:141)
+        for r in range(W):
+            rows = np.nonzero(tls[r][lo:hi] != -1)[0]
+            tgt[lo + rows] += exps[r][rows, tls[r][lo:hi][rows]] / sm[rows]                   # all_reduce SUM (:162)
+        gmax[lo:hi], gsum[lo:hi] = mx, sm
+    return -np.mean(np.log(np.maximum(tgt, 1e-30))), gmax, gsum

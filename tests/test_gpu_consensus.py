@@ -1,24 +1,16 @@
-"""GPU parity checks of the consensus-loss kernels (csrc/seg_loss.cu) against the reference goldens and the oracle.
-
-NOT collected by the default test run: these kernels were written after the round's GPU budget was spent and have never
-executed on a GPU.  tests/test_gpu_unverified.py runs this file in a subprocess (a faulting kernel must not take the
-CUDA context of the main test process with it) and reports the outcome as xfail / xpass.  Move the tests into
-tests/test_gpu_fusion.py once they have passed on a B200.
-"""
-import os
-import sys
+"""GPU parity of the consensus-loss kernels (csrc/seg_loss.cu) against the reference goldens
+(tests/golden/consensus.npz, ref tricks/consensus_loss.py:63-178) and the oracle.  First passed on a B200 in round 2
+(gpurun_out/r02_check_consensus.log: 15 passed)."""
 
 import numpy as np
 import pytest
 import torch
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(HERE))
-sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from conftest import load_golden
+from gpu_util import assert_close, dev, host, need_gpu
+from oracle import consensus
 
-from conftest import load_golden  # noqa: E402
-from gpu_util import assert_close, dev, host, need_gpu  # noqa: E402
-from oracle import consensus  # noqa: E402
+pytestmark = pytest.mark.gpu
 
 CASES = ["binary_missing", "four_blobs", "four_blobs_all_all", "four_blobs_idx_all", "underflow", "seg_shape"]
 

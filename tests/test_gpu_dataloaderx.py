@@ -1,16 +1,12 @@
-"""GPU check of msml_b200.datasets.DataLoaderX (drop-in for ref datasets/dataloaderx.py).  NOT collected by the default
-run (never executed on a GPU yet); tests/test_gpu_unverified.py runs it in a subprocess and reports xfail / xpass."""
-import os
-import sys
+"""GPU check of msml_b200.datasets.DataLoaderX (drop-in for ref datasets/dataloaderx.py:40-67)."""
 
+import pytest
 import torch
 from torch.utils.data import TensorDataset
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(HERE))
-sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from gpu_util import need_gpu
 
-from gpu_util import need_gpu  # noqa: E402
+pytestmark = pytest.mark.gpu
 
 
 def test_dataloaderx_delivers_every_batch_on_the_device():

@@ -155,6 +155,10 @@ def test_fm_cat_full_size_and_argument_errors():
     assert torch.equal(x[:, :64], yf) and torch.equal(x[:, 64:82], yo) and not x[:, 82:].any()
     with pytest.raises(ValueError):
         ops.fm_cat(yf, yo[:, :, :28])
+    with pytest.raises(ValueError):                      # no torch.cat fallback for channel counts the kernel does not take
+        ops.fm_cat(yf[:, :60], yo)
+    with pytest.raises(RuntimeError):                    # ... nor for CPU tensors
+        ops.fm_cat(yf.cpu(), yo.cpu())
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
     assert lib.msml_fm_cat_fwd(yf.data_ptr(), yo.data_ptr(), x.data_ptr(), 10, 64, 18, 80, _lib.BF16, st) != 0    # Ct < C + Co

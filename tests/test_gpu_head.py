@@ -119,6 +119,35 @@ def test_sample_ties_at_threshold_take_lowest_index():
     assert np.array_equal(index.cpu().numpy(), want)
 
 
+def assert_rows_close(actual, desired, rtol, floor_frac=1e-3, what=""):
+    """Per-ROW relative error: ||a_r - d_r||_2 <= rtol * ||d_r||_2 + floor_frac * median_r ||d_r||_2.
+    assert_close's absolute floor is a fraction of the matrix maximum; in w_grad the target rows are 100-1000x larger
+    than the rest, so that floor leaves the eps/(n_s - 1) label-smoothing rows (ref partial_fc.py:152-156) unchecked.
+    Here every row is measured against its own norm."""
+    a = np.asarray(actual, np.float64)
+    d = np.asarray(desired, np.float64)
+    assert a.shape == d.shape and np.isfinite(a).all(), what
+    dn = np.linalg.norm(d, axis=1)
+    err = np.linalg.norm(a - d, axis=1)
+    tol = rtol * dn + floor_frac * np.median(dn)
+    bad = err > tol
+    if bad.any():
+        i = int(np.argmax(err / np.maximum(tol, 1e-300)))
+        raise AssertionError("%s: %d / %d rows out of tolerance; worst row %d: |err| %g, |want| %g (tol %g), median |want| %g" % (
+            what, bad.sum(), bad.size, i, err[i], dn[i], tol[i], np.median(dn)))
+
+
+def check_w_grad_rows(w_grad, want, labels_local, what):
+    """Target rows and non-target rows of the class-centre gradient, each against its own scale."""
+    n_s = want.shape[0]
+    is_t = np.zeros(n_s, bool)
+    lab = np.asarray(labels_local)
+    is_t[lab[lab >= 0]] = True
+    assert_rows_close(w_grad[is_t], want[is_t], 2e-2, what=what + " target rows")
+    assert (~is_t).sum() > 0
+    assert_rows_close(w_grad[~is_t], want[~is_t], 2e-2, what=what + " non-target rows (softmax + local label smoothing)")
+
+
 # ------------------------------------------------------------------------------- PartialFC step
 PFC = ["pfc_w1_full", "pfc_w1_sample", "pfc_w1_d512", "pfc_w1_overflow", "pfc_w2_full", "pfc_w2_sample", "pfc_w2_am"]
 
@@ -217,6 +246,55 @@ def test_head_step_vs_oracle_fp64(B_tot, C, kind, smak):
     assert abs(float(loss) - res["loss"]) <= 1e-3 * abs(res["loss"])
     assert_close(host(x_grad), res["x_grad"][0], 2e-2, atol_frac=1e-2, what="x_grad")
     assert_close(host(pfc.sub_weight.grad), res["w_grad"][0], 2e-2, atol_frac=1e-2, what="w_grad")
+    assert_rows_close(host(x_grad), res["x_grad"][0], 2e-2, what="x_grad rows")
+    check_w_grad_rows(host(pfc.sub_weight.grad), res["w_grad"][0], res["total_label"][0], "w_grad")
+
+
+def test_label_smoothing_term_is_visible_in_non_target_rows():
+    """The eps/(n_s - 1) local label smoothing (ref partial_fc.py:152-156) must be IN the gradient: the oracle
+    evaluated without it (EPSILON = 0) has to FAIL the same row check the kernel passes."""
+    need_gpu()
+    torch.manual_seed(31)
+    B_tot, C, D = 128, 3000, 512
+    pfc = _pfc(0, 1, B_tot, C, 1.0, D)
+    feat = torch.nn.functional.normalize(torch.randn(B_tot, D, device="cuda"))
+    label = torch.randint(0, C, (B_tot,), device="cuda")
+    pfc.forward_backward(label, feat, None)
+    xb = feat.to(torch.bfloat16).double().cpu().numpy()
+    w = pfc.weight.double().cpu().numpy()
+    res = opfc.step([xb], [label.cpu().numpy()], [w], C, "arc", 64.0, 0.5)
+    got = host(pfc.sub_weight.grad)
+    check_w_grad_rows(got, res["w_grad"][0], res["total_label"][0], "w_grad")
+    saved = opfc.EPSILON
+    opfc.EPSILON = 0.0
+    try:
+        res0 = opfc.step([xb], [label.cpu().numpy()], [w], C, "arc", 64.0, 0.5)
+    finally:
+        opfc.EPSILON = saved
+    with pytest.raises(AssertionError):
+        check_w_grad_rows(got, res0["w_grad"][0], res["total_label"][0], "w_grad without smoothing")
+
+
+@pytest.mark.parametrize("B_tot,n_s", [(1024, 11679), (1024, 11678)])
+def test_head_step_at_config3_w8_rank_shape_vs_oracle(B_tot, n_s):
+    """The GEMM shapes one rank of the 8-GPU BASELINE config-3 run sees (B_tot = 8 x 128 gathered rows against an
+    11,679 / 11,678-class shard; 8 M-blocks, ragged last class tile) against the fp64 oracle."""
+    need_gpu()
+    torch.manual_seed(n_s)
+    D = 512
+    pfc = _pfc(0, 1, B_tot, n_s, 1.0, D)
+    feat = torch.nn.functional.normalize(torch.randn(B_tot, D, device="cuda"))
+    label = torch.randint(0, n_s, (B_tot,), device="cuda")
+    label[::3] = torch.randint(n_s - 40, n_s, (label[::3].numel(),), device="cuda")      # load the ragged last tile
+    with torch.no_grad():
+        pfc.weight[label[:64]] = feat[:64] * 0.01 + pfc.weight[label[:64]] * 0.2
+    x_grad, loss = pfc.forward_backward(label, feat, None)
+    res = opfc.step([feat.to(torch.bfloat16).double().cpu().numpy()], [label.cpu().numpy()], [pfc.weight.double().cpu().numpy()],
+                    n_s, "arc", 64.0, 0.5)
+    assert abs(float(loss) - res["loss"]) <= 1e-3 * abs(res["loss"])
+    assert_close(host(x_grad), res["x_grad"][0], 2e-2, atol_frac=1e-2, what="x_grad")
+    assert_rows_close(host(x_grad), res["x_grad"][0], 2e-2, what="x_grad rows")
+    check_w_grad_rows(host(pfc.sub_weight.grad), res["w_grad"][0], res["total_label"][0], "w_grad")
 
 
 def test_head_config3_shape_properties():
@@ -244,4 +322,10 @@ def test_head_config3_shape_properties():
     gl = (p - t) / B * 64.0
     gl[torch.arange(B), label] *= (torch.sin(theta + 0.5) / torch.sin(theta)).double()
     assert_close(host(x_grad), (gl @ wn.double()).cpu().numpy(), 2e-2, atol_frac=1e-2, what="x_grad cfg3")
-    assert torch.isfinite(pfc.sub_weight.grad).all()
+    # class-centre gradient through the normalise backward (ref :115,169), every row against its own norm
+    dwn = gl.t() @ xb.double()
+    w64 = pfc.weight.double()
+    nrm = w64.norm(dim=1, keepdim=True)
+    wn64 = w64 / nrm
+    want_dw = ((dwn - wn64 * (wn64 * dwn).sum(1, keepdim=True)) / nrm).cpu().numpy()
+    check_w_grad_rows(host(pfc.sub_weight.grad), want_dw, label.cpu().numpy(), "w_grad cfg3")

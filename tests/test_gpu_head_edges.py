@@ -1,22 +1,16 @@
-"""Edge-case probes of the (GPU-verified) PartialFC head that the regular suite does not hit: a rank none of whose
-rows has its class on the shard, a batch of one, one class repeated through the whole batch, a two-class shard.
-Written after the round's GPU budget was spent, so they run through tests/test_gpu_unverified.py (subprocess,
-xfail / xpass) until they have been seen to pass on a B200.  Checker: the fp64 oracle on the same bf16-rounded inputs
-(oracle/partial_fc.py follows ref headers/partial_fc.py:118-177)."""
-import os
-import sys
+"""Edge cases of the PartialFC head: a rank none of whose rows has its class on the shard, a batch of one, one class
+repeated through the whole batch, shard boundaries with an odd class count, a two-class shard.  Checker: the fp64 oracle
+on the same bf16-rounded inputs (oracle/partial_fc.py follows ref headers/partial_fc.py:118-177)."""
 import threading
 
 import numpy as np
 import pytest
 import torch
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.dirname(HERE))
-sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from gpu_util import assert_close, host, need_gpu
+from oracle import partial_fc as opfc
 
-from gpu_util import assert_close, host, need_gpu  # noqa: E402
-from oracle import partial_fc as opfc  # noqa: E402
+pytestmark = pytest.mark.gpu
 
 
 def run_ranks(W, B, C, D, labels, feats, weights, kind="arc", smak=(64.0, 0.5, 0.0, 0.0)):

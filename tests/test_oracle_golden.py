@@ -90,6 +90,28 @@ def test_partial_fc_step_matches_reference(name):
         weights = [g[f"r{r}.{p}weight_after"] for r in range(W)]
 
 
+@pytest.mark.parametrize("name", ["pfc_w1_full", "pfc_w1_d512"])
+def test_torch_port_of_the_head_matches_reference(name):
+    """oracle/partial_fc_torch.py (the timed CPU port of bench.py's reference arm) against the reference's own outputs."""
+    import torch
+    from oracle import partial_fc_torch as pt
+    g = load_golden(name)
+    assert int(g["W"]) == 1 and int(float(g["sample_rate"])) == 1
+    s, m, a, k = (float(v) for v in g["smak"])
+    assert a == 0.0 and k == 0.0
+    w = torch.from_numpy(g["r0.w0"]).clone()
+    mom = torch.zeros_like(w)
+    for step in range(int(g["steps"])):
+        p = f"r0.s{step}."
+        x_grad, w_grad, loss = pt.head_step(torch.from_numpy(g[p + "feat"]), torch.from_numpy(g[p + "label"]), w, str(g["kind"]), s, m)
+        close(x_grad.numpy(), g[p + "x_grad"], 1e-4, 1e-6)
+        close(w_grad.numpy(), g[p + "w_grad"], 1e-4, 1e-6)
+        assert abs(float(loss) - float(g[p + "loss"])) <= 1e-5 * abs(float(loss))
+        pt.sgd_update(w, mom, w_grad)
+        close(w.numpy(), g[p + "weight_after"], 1e-5, 1e-7)
+        close(mom.numpy(), g[p + "mom_after"], 1e-5, 1e-7)
+
+
 def test_shard_geometry():
     # ref partial_fc.py:34-36 at BASELINE config 3 (93,431 classes over 8 ranks)
     geo = [partial_fc.shard_geometry(93431, 8, r) for r in range(8)]
