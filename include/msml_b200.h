@@ -256,6 +256,10 @@ int msml_gemm_bf16_tn(const void* a, int64_t lda, const void* b, int64_t ldb, fl
  * b_mn != 0 => B stored (K, N) row-major.  block_n in {256, 512} selects the accumulator tile. */
 int msml_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, float* c,
                    int64_t ldc, int64_t M, int64_t N, int64_t K, int block_n, void* stream);
+/* Same contract on the CTA-pair mainloop (clusters of two CTAs, tcgen05.mma.cta_group::2, 256 x block_n tiles;
+ * block_n in {128, 256}): the mainloop of the head's three tensor-bound GEMMs, exposed for the exact-integer tests. */
+int msml_gemm_bf16_pair(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, float* c,
+                        int64_t ldc, int64_t M, int64_t N, int64_t K, int block_n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,7 @@ SIGNATURES = {
     "msml_margin_fwd": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p]),
     "msml_margin_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p]),
     "msml_gemm_bf16": (c_int, [c_p, c_i64, c_int, c_p, c_i64, c_int, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
+    "msml_gemm_bf16_pair": (c_int, [c_p, c_i64, c_int, c_p, c_i64, c_int, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
     "msml_gemm_bf16_tn": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_i64, c_i64, c_i64, c_p]),
 }
 

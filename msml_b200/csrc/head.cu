@@ -16,6 +16,7 @@
 //                 epilogue applies (dWn - Wn * rdot) / ||W|| and streams fp32 rows out through TMA.
 // Everything runs on the caller's stream; no allocation, no host sync.
 #include <cmath>
+#include <cstdlib>
 
 #include "tc_gemm.cuh"
 #include "head_small_kernels.cuh"
@@ -212,6 +213,7 @@ struct EpiBwdDcos {
   const float* gsum;   // [B_tot] global row sum of exp(logit - max)
   float* rdot;         // [n_s] zero-initialised; <Wn[n], dWn[n]> for the normalise backward
   float smooth_on, smooth_off, inv_btot;
+  int blk_pitch;       // > 0: dcos is tile-blocked [n_s/64][blk_pitch rows][64] (tc_gemm.cuh); 0: row-major (B_tot x ld)
   __device__ void prefetch(int, int, int, int, uint8_t*) const {}
   __device__ void finish(int, int lane) const { StageOut::drain(lane); }
   __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int half, int nh) const {
@@ -285,7 +287,8 @@ struct EpiBwdDcos {
           for (int q = 0; q < 4; ++q) packed[h * 4 + q] = make_uint4(0, 0, 0, 0);
         }
       }
-      StageOut::put_and_store(wscr, (c >> 1) & 1, lane, packed, &map_dcos, tile_col0 + c * 32, row0);
+      if (blk_pitch) StageOut::put_and_store(wscr, (c >> 1) & 1, lane, packed, &map_dcos, 0, ((tile_col0 + c * 32) >> 6) * blk_pitch + row0);
+      else StageOut::put_and_store(wscr, (c >> 1) & 1, lane, packed, &map_dcos, tile_col0 + c * 32, row0);
     }
   }
 };
@@ -404,10 +407,25 @@ static int to_margin(const msml_margin_params* p, Margin* out) {
 struct HeadWs {
   float* part_max; float* part_sum; float* tgt; float* rdot;
   __nv_bfloat16* dcos;
-  int64_t ld_dc;
+  int64_t ld_dc;          // row-major layout: row pitch in elements
+  int64_t blk_pitch;      // tile-blocked layout: rows per 64-class block (B_tot rounded up to 128)
+  int64_t n_cb;           // tile-blocked layout: number of 64-class blocks
   int n_blocks;
   size_t bytes;
 };
+
+// MSML_HEAD_DCOS_ROWMAJOR=1 keeps round 1's row-major dcos (A/B measurements); default: tile-blocked
+static bool dcos_blocked() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSML_HEAD_DCOS_ROWMAJOR"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+// MSML_HEAD_PAIR=0 selects the single-CTA kernels for the three tensor-bound GEMMs (A/B measurements); default: CTA pairs
+static bool head_pairs() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MSML_HEAD_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 constexpr int kFwdBlockN = 128;   // smallest class tile; each tile yields two softmax partials (one per epilogue half)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -416,13 +434,18 @@ static HeadWs carve(void* ws, int64_t B_tot, int64_t n_s) {
   HeadWs h;
   h.n_blocks = 2 * (int)((n_s + kFwdBlockN - 1) / kFwdBlockN);
   h.ld_dc = (n_s + 7) / 8 * 8;
+  h.blk_pitch = (B_tot + kBlockM - 1) / kBlockM * kBlockM;
+  h.n_cb = (n_s + 63) / 64;
   size_t off = 0;
   char* base = static_cast<char*>(ws);
   h.part_max = reinterpret_cast<float*>(base + off); off = align_up(off + sizeof(float) * h.n_blocks * B_tot, 256);
   h.part_sum = reinterpret_cast<float*>(base + off); off = align_up(off + sizeof(float) * h.n_blocks * B_tot, 256);
   h.tgt = reinterpret_cast<float*>(base + off); off = align_up(off + sizeof(float) * B_tot, 256);
   h.rdot = reinterpret_cast<float*>(base + off); off = align_up(off + sizeof(float) * n_s, 256);
-  h.dcos = reinterpret_cast<__nv_bfloat16*>(base + off); off = align_up(off + 2 * (size_t)B_tot * h.ld_dc, 256);
+  {   // either layout fits (the blocked one pads rows to 128 and classes to 64)
+    const size_t rowmajor = 2 * (size_t)B_tot * h.ld_dc, blocked = 2 * (size_t)h.n_cb * h.blk_pitch * 64;
+    h.dcos = reinterpret_cast<__nv_bfloat16*>(base + off); off = align_up(off + (rowmajor > blocked ? rowmajor : blocked), 256);
+  }
   h.bytes = off;
   return h;
 }
@@ -467,6 +490,32 @@ extern "C" int msml_gemm_bf16(const void* a, int64_t lda, int a_mn, const void* 
     case 5: return launch_gemm<512, 1, 2, false, true>("gemm_bf16", ma, mb, sh, epi, st);
     case 6: return launch_gemm<512, 1, 2, true, false>("gemm_bf16", ma, mb, sh, epi, st);
     default: return launch_gemm<512, 1, 2, true, true>("gemm_bf16", ma, mb, sh, epi, st);
+  }
+}
+
+// The CTA-pair kernel with the plain fp32-store epilogue (bring-up / tests): same contract as msml_gemm_bf16, block_n in
+// {128, 256}; both operand majors.
+extern "C" int msml_gemm_bf16_pair(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, float* c,
+                                   int64_t ldc, int64_t M, int64_t N, int64_t K, int block_n, void* stream) {
+  MSML_REQUIRE(a && b && c && M > 0 && N > 0 && K > 0, MSML_EINVAL, "bad GEMM arguments");
+  MSML_REQUIRE(block_n == 128 || block_n == 256, MSML_EINVAL, "block_n must be 128 or 256");
+  CUtensorMap ma, mb;
+  if (int e = a_mn ? encode_tmap_bf16_mnmajor(&ma, a, M, K, lda) : encode_tmap_bf16_kmajor(&ma, a, M, K, lda, kBlockM)) return e;
+  if (int e = b_mn ? encode_tmap_bf16_mnmajor(&mb, b, N, K, ldb) : encode_tmap_bf16_kmajor(&mb, b, N, K, ldb, block_n / 2)) return e;
+  EpiStore epi;
+  epi.c = c; epi.ldc = ldc; epi.M = (int)M; epi.N = (int)N; epi.block_n = block_n;
+  cudaStream_t st = (cudaStream_t)stream;
+  const GemmShape sh = make_shape(M, N, K, block_n);
+  const int sel = (block_n == 128 ? 4 : 0) + (a_mn ? 2 : 0) + (b_mn ? 1 : 0);
+  switch (sel) {
+    case 0: return launch_gemm_pair<256, 2, 6, false, false>("gemm_bf16_pair", ma, mb, sh, epi, st);
+    case 1: return launch_gemm_pair<256, 2, 6, false, true>("gemm_bf16_pair", ma, mb, sh, epi, st);
+    case 2: return launch_gemm_pair<256, 2, 6, true, false>("gemm_bf16_pair", ma, mb, sh, epi, st);
+    case 3: return launch_gemm_pair<256, 2, 6, true, true>("gemm_bf16_pair", ma, mb, sh, epi, st);
+    case 4: return launch_gemm_pair<128, 4, 8, false, false>("gemm_bf16_pair", ma, mb, sh, epi, st);
+    case 5: return launch_gemm_pair<128, 4, 8, false, true>("gemm_bf16_pair", ma, mb, sh, epi, st);
+    case 6: return launch_gemm_pair<128, 4, 8, true, false>("gemm_bf16_pair", ma, mb, sh, epi, st);
+    default: return launch_gemm_pair<128, 4, 8, true, true>("gemm_bf16_pair", ma, mb, sh, epi, st);
   }
 }
 
@@ -521,8 +570,9 @@ extern "C" size_t msml_head_workspace(int64_t B_tot, int64_t n_s, int64_t D) {
 }
 
 // class-tile width for the logits GEMMs: the one that fills the last wave of the persistent grid best
-static int pick_block_n(int64_t B_tot, int64_t n_s) {
-  const int64_t mb = (B_tot + kBlockM - 1) / kBlockM, sms = num_sms();
+static int pick_block_n(int64_t B_tot, int64_t n_s, bool pair = false) {
+  int64_t mb = (B_tot + kBlockM - 1) / kBlockM, sms = num_sms();
+  if (pair) { mb = (mb + 1) / 2; sms /= 2; }              // work units are 256-row tiles, workers are CTA pairs
   auto eff = [&](int bn) {
     const int64_t tiles = mb * ((n_s + bn - 1) / bn);
     return (double)tiles / (double)(((tiles + sms - 1) / sms) * sms);
@@ -548,15 +598,22 @@ extern "C" int msml_head_fwd(const void* x, const void* wn, const int64_t* tl, i
   if (int e = to_margin(margin, &mg)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   HeadWs h = carve(ws, B_tot, n_s);
-  const int bn = pick_block_n(B_tot, n_s);
+  const bool pair = head_pairs() && B_tot > kBlockM;      // a pair needs two 128-row blocks to be worth it
+  const int bn = pick_block_n(B_tot, n_s, pair);
   CUtensorMap ma, mb;
   if (int e = encode_tmap_bf16_kmajor(&ma, x, B_tot, D, D, kBlockM)) return e;
-  if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, bn)) return e;     // box rows == UMMA_N of the tile
+  if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, pair ? bn / 2 : bn)) return e;     // box rows: the B rows ONE CTA loads
   EpiFwdStats epi;
   epi.tl = tl; epi.mg = mg; epi.B_tot = (int)B_tot; epi.n_s = (int)n_s; epi.block_n = bn;
   epi.part_max = h.part_max; epi.part_sum = h.part_sum; epi.tgt = h.tgt;
   const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D;      // stream Wn + X once (bf16)
-  if (bn == 256) {
+  if (pair) {
+    if (bn == 256) {
+      if (int e = launch_gemm_pair<256, 2, 6, false, false, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
+    } else {
+      if (int e = launch_gemm_pair<128, 4, 8, false, false, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
+    }
+  } else if (bn == 256) {
     if (int e = launch_gemm<256, 2, 4, false, false, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
   } else {
     if (int e = launch_gemm<128, 4, 6, false, false, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
@@ -585,21 +642,34 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
   cudaStream_t st = (cudaStream_t)stream;
   HeadWs h = carve(ws, B_tot, n_s);
 
-  // 1. recompute logits -> dcos (bf16, row-major) + rdot[n] = <Wn[n], dWn[n]>
+  const bool blocked = dcos_blocked();
+  const bool pair = head_pairs() && B_tot > kBlockM;
+  // 1. recompute logits -> dcos (bf16; tile-blocked, see tc_gemm.cuh) + rdot[n] = <Wn[n], dWn[n]>
   {
     MSML_CUDA(cudaMemsetAsync(h.rdot, 0, sizeof(float) * (size_t)n_s, st));
-    const int bn = pick_block_n(B_tot, n_s);
+    const int bn = pick_block_n(B_tot, n_s, pair);
     CUtensorMap ma, mb;
     if (int e = encode_tmap_bf16_kmajor(&ma, x, B_tot, D, D, kBlockM)) return e;
-    if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, bn)) return e;   // box rows == UMMA_N of the tile
+    if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, pair ? bn / 2 : bn)) return e;   // box rows: the B rows ONE CTA loads
     const float eps = 0.1f;   // ref partial_fc.py:154
     EpiBwdDcos epi;
-    if (int e = encode_tmap_2d(&epi.map_dcos, h.dcos, 2, n_s, B_tot, h.ld_dc, 64, 32)) return e;
+    if (blocked) {
+      if (int e = encode_tmap_2d(&epi.map_dcos, h.dcos, 2, 64, h.n_cb * h.blk_pitch, 64, 64, 32)) return e;
+    } else {
+      if (int e = encode_tmap_2d(&epi.map_dcos, h.dcos, 2, n_s, B_tot, h.ld_dc, 64, 32)) return e;
+    }
+    epi.blk_pitch = blocked ? (int)h.blk_pitch : 0;
     epi.tl = tl; epi.mg = mg; epi.B_tot = (int)B_tot; epi.n_s = (int)n_s; epi.block_n = bn;
     epi.gmax = gstats; epi.gsum = gstats + B_tot; epi.rdot = h.rdot;
     epi.smooth_on = 1.0f - eps; epi.smooth_off = eps / (float)(n_s - 1); epi.inv_btot = 1.0f / (float)B_tot;
     const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D + 2.0 * (double)B_tot * n_s;   // + dcos out
-    if (bn == 256) {
+    if (pair) {
+      if (bn == 256) {
+        if (int e = launch_gemm_pair<256, 2, 4, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
+      } else {
+        if (int e = launch_gemm_pair<128, 4, 6, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
+      }
+    } else if (bn == 256) {
       if (int e = launch_gemm<256, 2, 3, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
     } else {
       if (int e = launch_gemm<128, 4, 4, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
@@ -609,28 +679,48 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
   {
     MSML_CUDA(cudaMemsetAsync(dx_full, 0, sizeof(float) * (size_t)B_tot * D, st));
     CUtensorMap ma, mb;
-    if (int e = encode_tmap_bf16_kmajor(&ma, h.dcos, B_tot, n_s, h.ld_dc, kBlockM)) return e;
+    if (blocked) {
+      if (int e = encode_tmap_2d(&ma, h.dcos, 2, 64, h.n_cb * h.blk_pitch, 64, 64, kBlockM)) return e;      // 128 rows x 64 classes: 16 KB contiguous
+    } else {
+      if (int e = encode_tmap_bf16_kmajor(&ma, h.dcos, B_tot, n_s, h.ld_dc, kBlockM)) return e;
+    }
     if (int e = encode_tmap_bf16_mnmajor(&mb, wn, D, n_s, D)) return e;
-    const int tiles = (int)((B_tot + kBlockM - 1) / kBlockM) * (int)((D + 255) / 256);
+    const int m_units = pair ? (int)((B_tot + 2 * kBlockM - 1) / (2 * kBlockM)) : (int)((B_tot + kBlockM - 1) / kBlockM);
+    const int tiles = m_units * (int)((D + 255) / 256);
     // as many split-K units as fit in ONE wave of the persistent grid (rounding up would leave a second, almost
     // empty wave: 16 tiles x 10 splits = 160 units on 148 SMs ran at 54 % occupancy)
-    int splits = num_sms() / tiles;
+    int splits = (pair ? num_sms() / 2 : num_sms()) / tiles;
     if (splits < 1) splits = 1;
     EpiDxAccum epi;
     epi.dx = dx_full; epi.B_tot = (int)B_tot; epi.D = (int)D; epi.block_n = 256;
     const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 4.0 * (double)B_tot * D;
-    if (int e = launch_gemm<256, 2, 4, false, true, 8>("head_bwd_dx_gemm", ma, mb, make_shape(B_tot, D, n_s, 256, splits), epi, st, min_bytes)) return e;
+    GemmShape sh = make_shape(B_tot, D, n_s, 256, splits);
+    sh.a_blk_pitch = (int)h.blk_pitch;
+    if (pair) {
+      if (blocked) { if (int e = launch_gemm_pair<256, 2, 6, false, true, 8, true>("head_bwd_dx_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
+      else { if (int e = launch_gemm_pair<256, 2, 6, false, true, 8, false>("head_bwd_dx_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
+    } else {
+      if (blocked) { if (int e = launch_gemm<256, 2, 4, false, true, 8, true>("head_bwd_dx_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
+      else { if (int e = launch_gemm<256, 2, 4, false, true, 8, false>("head_bwd_dx_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
+    }
   }
   // 3. dW = normalize_bwd(dcos^T X): A = dcos read in place (MN-major over classes), B = X in place (MN-major), K = B_tot
   {
     CUtensorMap ma, mb;
-    if (int e = encode_tmap_bf16_mnmajor(&ma, h.dcos, n_s, B_tot, h.ld_dc)) return e;
+    if (blocked) {
+      if (int e = encode_tmap_2d(&ma, h.dcos, 2, 64, h.n_cb * h.blk_pitch, 64, 64, 64)) return e;           // 64 classes x 64 rows: 8 KB contiguous
+    } else {
+      if (int e = encode_tmap_bf16_mnmajor(&ma, h.dcos, n_s, B_tot, h.ld_dc)) return e;
+    }
     if (int e = encode_tmap_bf16_mnmajor(&mb, x, D, B_tot, D)) return e;
     EpiDwNormBwd epi;
     if (int e = encode_tmap_2d(&epi.map_dw, dw, 4, D, n_s, D, 32, 32)) return e;
     epi.wn = static_cast<const __nv_bfloat16*>(wn); epi.inv_norm = inv_norm; epi.rdot = h.rdot; epi.n_s = (int)n_s; epi.D = (int)D;
     const double min_bytes = 4.0 * (double)n_s * D + 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 2.0 * (double)B_tot * D;
-    if (int e = launch_gemm<256, 2, 3, true, true>("head_bwd_dw_gemm", ma, mb, make_shape(n_s, D, B_tot, 256, 1, /*n_fastest=*/true), epi, st, min_bytes)) return e;
+    GemmShape sh = make_shape(n_s, D, B_tot, 256, 1, /*n_fastest=*/true);
+    sh.a_blk_pitch = (int)h.blk_pitch;
+    if (blocked) { if (int e = launch_gemm<256, 2, 3, true, true, 4, true>("head_bwd_dw_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
+    else { if (int e = launch_gemm<256, 2, 3, true, true, 4, false>("head_bwd_dw_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
   }
   return 0;
 }

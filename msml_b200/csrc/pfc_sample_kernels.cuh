@@ -15,7 +15,9 @@
 // :89-90 branch because positives are the only keys equal to 2.0 and rand() < 1.  Ties at the
 // k-th value go to the lowest class index.  Everything is integer/compare work: bit-exact.
 // Kernels are small multi-CTA passes; the digit pick / block-offset scan runs in the last CTA to
-// finish (threadfence + ticket), so no kernel ever waits on another CTA.
+// finish (threadfence + ticket), so no kernel ever waits on another CTA.  Both are block-wide scans over all 512 threads:
+// round 1 walked the 2048 bins (and the per-CTA counts) from ONE thread with dependent global loads, ~0.6 us each —
+// 477 us of a 0.84 ms sampled step at 125,000 classes (gpurun r02_head_125k_sr0.1.json), the whole "sampled-path cliff".
 #pragma once
 #include "common.cuh"
 
@@ -41,6 +43,22 @@ __device__ __forceinline__ unsigned int f2key(float f) {
   const unsigned int u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+// inclusive block scan of one long long per thread (Hillis-Steele in shared memory; every thread of the CTA must call it)
+__device__ __forceinline__ long long block_incl_scan(long long v, long long* sh) {
+  const int t = threadIdx.x;
+  sh[t] = v;
+  __syncthreads();
+  for (int o = 1; o < kSelThreads; o <<= 1) {
+    const long long add = t >= o ? sh[t - o] : 0;
+    __syncthreads();
+    sh[t] += add;
+    __syncthreads();
+  }
+  const long long r = sh[t];
+  __syncthreads();
+  return r;
+}
+
 __device__ __forceinline__ int digit_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
 __device__ __forceinline__ int digit_bits(int pass) { return pass == 2 ? 10 : 11; }
 
@@ -94,9 +112,14 @@ pfc_hist_kernel(const float* __restrict__ perm, int64_t n, int64_t num_sample, S
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // last CTA: pick the digit that contains the k_rem-th largest key (thread 0; 2048 bins)
+  // last CTA: pick the digit d that contains the k_rem-th largest key = the first d, walking down from the top bin, with
+  // (#keys in bins above d) + hist[d] >= k_rem; d = 0 if no bin above 0 gets there.  Thread t owns `per` consecutive bins,
+  // descending from nb - 1 - t * per; a block scan gives every thread the count above its range.
+  __shared__ long long s_scan[kSelThreads];
+  __shared__ long long s_krem;
+  __shared__ int s_found;
+  volatile SelState* v = st;
   if (threadIdx.x == 0) {
-    volatile SelState* v = st;
     long long k_rem;
     if (PASS == 0) {
       long long k = num_sample;
@@ -107,19 +130,34 @@ pfc_hist_kernel(const float* __restrict__ perm, int64_t n, int64_t num_sample, S
     } else {
       k_rem = v->k_rem;
     }
-    const int nb = 1 << digit_bits(PASS);
-    int d = nb - 1;
-    long long above = 0;
-    for (; d > 0; --d) {
-      const long long c = v->hist[PASS][d];
-      if (above + c >= k_rem) break;
-      above += c;
+    s_krem = k_rem;
+    s_found = 0;
+  }
+  constexpr int nb = 1 << (PASS == 2 ? 10 : 11);
+  constexpr int per = nb / kSelThreads;
+  const int top = nb - 1 - (int)threadIdx.x * per;
+  long long c[per], loc = 0;
+#pragma unroll
+  for (int j = 0; j < per; ++j) { c[j] = v->hist[PASS][top - j]; loc += c[j]; }
+  long long above = block_incl_scan(loc, s_scan) - loc;       // keys in the bins above this thread's range (syncs: s_krem visible)
+  const long long k_rem = s_krem;
+#pragma unroll
+  for (int j = 0; j < per; ++j) {
+    const int d = top - j;
+    if (d > 0 && above + c[j] >= k_rem && (d == nb - 1 || above < k_rem)) {      // exactly one (thread, j) can satisfy this
+      s_found = 1;
+      const unsigned int p = prefix | ((unsigned int)d << shift);
+      v->prefix = p;
+      v->k_rem = k_rem - above;
+      if (PASS == 2) { v->threshold = p; v->need_eq = k_rem - above; }
     }
-    k_rem -= above;
-    const unsigned int p = prefix | ((unsigned int)d << shift);
-    v->prefix = p;
-    v->k_rem = k_rem;
-    if (PASS == 2) { v->threshold = p; v->need_eq = k_rem; }
+    if (d > 0) above += c[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == kSelThreads - 1 && !s_found) {            // owner of bin 0; `above` = all keys in bins 1 .. nb-1
+    v->prefix = prefix;
+    v->k_rem = k_rem - above;
+    if (PASS == 2) { v->threshold = prefix; v->need_eq = k_rem - above; }
   }
 }
 
@@ -154,15 +192,24 @@ pfc_count_kernel(const float* __restrict__ perm, int64_t n, SelState* st, long l
     s_last = (atomicAdd(&st->ticket[3], 1u) == gridDim.x - 1);
   }
   __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
+  if (!s_last) return;
   __threadfence();
+  // exclusive scan of the per-CTA counts (31 CTAs at 125,000 classes, 245 at 1,000,000), 512 at a time
+  __shared__ long long s_scan[kSelThreads];
+  __shared__ long long s_tot[2];
   volatile long long* g = blk_gt;
   volatile long long* e = blk_eq;
-  long long ag = 0, ae = 0;
-  for (unsigned int b = 0; b < gridDim.x; ++b) {   // exclusive scan (<= a few thousand CTAs)
-    const long long cg = g[b], ce = e[b];
-    g[b] = ag; e[b] = ae;
-    ag += cg; ae += ce;
+  long long carry_g = 0, carry_e = 0;
+  for (unsigned int b0 = 0; b0 < gridDim.x; b0 += kSelThreads) {
+    const unsigned int b = b0 + threadIdx.x;
+    const long long cg = b < gridDim.x ? g[b] : 0, ce = b < gridDim.x ? e[b] : 0;
+    const long long ig = block_incl_scan(cg, s_scan), ie = block_incl_scan(ce, s_scan);
+    if (b < gridDim.x) { g[b] = carry_g + ig - cg; e[b] = carry_e + ie - ce; }
+    if (threadIdx.x == kSelThreads - 1) { s_tot[0] = ig; s_tot[1] = ie; }     // chunk totals
+    __syncthreads();
+    carry_g += s_tot[0];
+    carry_e += s_tot[1];
+    __syncthreads();
   }
 }
 

@@ -203,7 +203,18 @@ struct GemmShape {
   int k_splits;          // split-K work units
   int k_blocks_per_split;
   int n_fastest;         // unit order: 0 = m fastest (CTAs running together share the B tile in L2), 1 = n fastest (share A)
+  int a_blk_pitch;       // A_BLOCKED only: rows per 64-column block of the tile-blocked A matrix (see below)
 };
+
+// Tile-blocked A operand (the head's dcos matrix, written by one GEMM epilogue and read by two other GEMMs, once
+// along each of its axes): a logical (R x C) bf16 matrix stored as [C/64][R_pad][64] — for every block of 64 columns,
+// all rows back to back, 128 bytes each.  Seen by TMA as a 2-D array (inner 64, outer C/64 * R_pad), so that
+//   * the K-major reader  (M = rows,    K = columns): 128 rows x 64 k   = ONE contiguous 16 KB box at (0, kb * R_pad + m0)
+//   * the MN-major reader (M = columns, K = rows):    64 mn x 64 k      = ONE contiguous  8 KB box at (0, cb * R_pad + k0)
+//   * the writer (32 rows x 64 columns per warp)                        = ONE contiguous  4 KB box
+// and every DRAM access of all three kernels is a whole multi-KB burst, where the row-major layout gave the MN-major
+// reader (and the writer) 128-byte pieces a full row pitch (250 KB at 125,000 classes) apart.  The shared-memory images
+// are exactly the canonical SW128 K-major / MN-major layouts, so the UMMA descriptors do not change.
 
 template <int BLOCK_N, int STAGES, int EPI_BYTES>
 struct SmemLayout {
@@ -230,7 +241,7 @@ struct SmemLayout {
 // ((quarter*32) << 16) + column.  Called by all epilogue threads (warp-convergent); with 8 epilogue warps
 // (n_halves == 2) warp `half` of a quarter owns columns [half, half+1) * BLOCK_N / 2 of the tile.
 
-template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, class Epi, int EW = 4>
+template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, class Epi, int EW = 4, bool A_BLOCKED = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const GemmShape shape, const __grid_constant__ Epi epi) {
@@ -285,10 +296,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           if (A_MN) {   // 64(m) x 64(k) boxes, one per 64-wide M block
 #pragma unroll
-            for (int j = 0; j < kBlockM / 64; ++j)
-              tma_load_2d(sa + j * 8192, &map_a, &full_bar[stage], m_blk * kBlockM + j * 64, kb * kBlockK);
+            for (int j = 0; j < kBlockM / 64; ++j) {
+              if (A_BLOCKED) tma_load_2d(sa + j * 8192, &map_a, &full_bar[stage], 0, (m_blk * (kBlockM / 64) + j) * shape.a_blk_pitch + kb * kBlockK);
+              else tma_load_2d(sa + j * 8192, &map_a, &full_bar[stage], m_blk * kBlockM + j * 64, kb * kBlockK);
+            }
           } else {
-            tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+            if (A_BLOCKED) tma_load_2d(sa, &map_a, &full_bar[stage], 0, kb * shape.a_blk_pitch + m_blk * kBlockM);
+            else tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
           }
           if (B_MN) {
 #pragma unroll
@@ -369,6 +383,230 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of one cluster (the two SMs of a TPC) own ONE 256 x BLOCK_N tile: rank r holds rows [128 r, 128 r + 128) of A
+// and rows [BLOCK_N/2 r, BLOCK_N/2 (r + 1)) of B in ITS shared memory, `tcgen05.mma.cta_group::2` (M = 256, issued by
+// rank 0 only) reads both halves of B from the two shared memories, and each CTA's TMEM receives its own 128 rows x BLOCK_N
+// columns.  Per k-block a CTA therefore pulls (128 + BLOCK_N/2) x 128 bytes through its L2 -> SM port instead of
+// (128 + BLOCK_N) x 128 (-33 % at BLOCK_N = 256) and its tensor core reads half the B bytes from shared memory per flop:
+// the two limits measured on the single-CTA kernels (0.70-0.73 of peak).  The epilogues are unchanged: a thread still owns
+// one accumulator row of its CTA's 128.
+//   full_bar[s]   lives in rank 0: its producer arms it with the bytes of BOTH CTAs, both producers' TMA loads complete on it
+//                 (cp.async.bulk.tensor ... .cta_group::2 with the barrier address mapped into rank 0)
+//   empty_bar[s]  one per CTA; `tcgen05.commit.cta_group::2 ... multicast::cluster` (mask 0b11) arrives on both
+//   tmem_full[a]  one per CTA, same multicast commit;   tmem_empty[a] in rank 0, counts the epilogue warps of both CTAs
+//                 (rank 1 arrives remotely)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs when every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+template <int BLOCK_N, int STAGES, int EPI_BYTES>
+struct SmemLayoutPair {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;            // this CTA's 128 rows of A
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;      // this CTA's half of B
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiOffset = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kEpiOffset + EPI_BYTES;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;
+  static_assert(EPI_BYTES % 1024 == 0, "epilogue scratch must keep 1024-byte alignment");
+  static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
+};
+
+// shape.m_blocks counts 128-row blocks as in the single-CTA kernel; a pair owns blocks (2 p, 2 p + 1).
+template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, class Epi, int EW = 4, bool A_BLOCKED = false>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmShape shape, const __grid_constant__ Epi epi) {
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N in {128,256} (cta_group::2: N <= 256)");
+  static_assert(BLOCK_N * ACC_STAGES <= kTmemCols, "accumulators exceed TMEM");
+  constexpr int HALF_N = BLOCK_N / 2;
+  using L = SmemLayoutPair<BLOCK_N, STAGES, Epi::kSmemBytes>;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m_pairs = (shape.m_blocks + 1) / 2;
+  const int num_units = m_pairs * shape.n_blocks * shape.k_splits;
+  const int total_k_blocks = (shape.K + kBlockK - 1) / kBlockK;
+  const int first_unit = (int)cluster_id_x(), unit_step = (int)cluster_count_x();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EW); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = first_unit; u < num_units; u += unit_step) {
+        const int mn = u % (m_pairs * shape.n_blocks);
+        const int pair = shape.n_fastest ? mn / shape.n_blocks : mn % m_pairs;
+        const int n_blk = shape.n_fastest ? mn % shape.n_blocks : mn / m_pairs;
+        const int m_blk = pair * 2 + (int)rank;
+        const int ks = u / (m_pairs * shape.n_blocks);
+        const int kb0 = ks * shape.k_blocks_per_split;
+        int kb1 = kb0 + shape.k_blocks_per_split;
+        if (kb1 > total_k_blocks) kb1 = total_k_blocks;
+        const int n0 = n_blk * BLOCK_N + (int)rank * HALF_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j) {
+              if (A_BLOCKED) tma_load_2d_pair(sa + j * 8192, &map_a, bar, 0, (m_blk * (kBlockM / 64) + j) * shape.a_blk_pitch + kb * kBlockK);
+              else tma_load_2d_pair(sa + j * 8192, &map_a, bar, m_blk * kBlockM + j * 64, kb * kBlockK);
+            }
+          } else {
+            if (A_BLOCKED) tma_load_2d_pair(sa, &map_a, bar, 0, kb * shape.a_blk_pitch + m_blk * kBlockM);
+            else tma_load_2d_pair(sa, &map_a, bar, kb * kBlockK, m_blk * kBlockM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < HALF_N / 64; ++j) tma_load_2d_pair(sb + j * 8192, &map_b, bar, n0 + j * 64, kb * kBlockK);
+          } else {
+            tma_load_2d_pair(sb, &map_b, bar, kb * kBlockK, n0);        // box = HALF_N rows x 64 k
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (rank 0 only) =====================
+      constexpr uint32_t idesc = make_idesc(2 * kBlockM, BLOCK_N, A_MN, B_MN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int u = first_unit; u < num_units; u += unit_step) {
+        const int ks = u / (m_pairs * shape.n_blocks);
+        const int kb0 = ks * shape.k_blocks_per_split;
+        int kb1 = kb0 + shape.k_blocks_per_split;
+        if (kb1 > total_k_blocks) kb1 = total_k_blocks;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc_mn(sa + k * 2048) : make_smem_desc(sa + k * kUmmaK * 2);
+            const uint64_t db = B_MN ? make_smem_desc_mn(sb + k * 2048) : make_smem_desc(sb + k * kUmmaK * 2);
+            umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = first_unit; u < num_units; u += unit_step) {
+      const int mn = u % (m_pairs * shape.n_blocks);
+      const int pair = shape.n_fastest ? mn / shape.n_blocks : mn % m_pairs;
+      const int n_blk = shape.n_fastest ? mn % shape.n_blocks : mn / m_pairs;
+      const int m_blk = pair * 2 + (int)rank;
+      const int ks = u / (m_pairs * shape.n_blocks);
+      const bool live = m_blk < shape.m_blocks;          // odd number of 128-row blocks: the last pair's second half is empty
+      if (live) epi.prefetch(m_blk, n_blk, quarter, lane, smem + L::kEpiOffset);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (live) epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane, smem + L::kEpiOffset, half, EW / 4);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[acc]), 0));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    epi.finish(quarter, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // nobody leaves (or frees TMEM) while the peer may still signal / read this CTA
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
 // ------------------------------------------------------------------------------- host side
 // cuTensorMapEncodeTiled is fetched through the runtime (no link-time libcuda dependency).
 // 2-D tensor map over a row-major (outer x inner) array: inner contiguous, row pitch ld_elems, 128-byte
@@ -384,11 +622,11 @@ inline int encode_tmap_bf16_mnmajor(CUtensorMap* out, const void* base, int64_t 
   return encode_tmap_2d(out, base, 2, mn, k, ld_elems, 64, kBlockK);
 }
 
-template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, int EW = 4, class Epi>
+template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, int EW = 4, bool A_BLOCKED = false, class Epi>
 int launch_gemm(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& shape, const Epi& epi,
                 cudaStream_t st, double min_bytes = 0.0) {
   using L = SmemLayout<BLOCK_N, STAGES, Epi::kSmemBytes>;
-  auto kern = gemm_kernel<BLOCK_N, ACC_STAGES, STAGES, A_MN, B_MN, Epi, EW>;
+  auto kern = gemm_kernel<BLOCK_N, ACC_STAGES, STAGES, A_MN, B_MN, Epi, EW, A_BLOCKED>;
   static thread_local bool configured = false;   // per template instantiation
   if (!configured) {
     MSML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -404,9 +642,42 @@ int launch_gemm(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, 
   return 0;
 }
 
+template <int BLOCK_N, int ACC_STAGES, int STAGES, bool A_MN, bool B_MN, int EW = 4, bool A_BLOCKED = false, class Epi>
+int launch_gemm_pair(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& shape, const Epi& epi,
+                     cudaStream_t st, double min_bytes = 0.0) {
+  using L = SmemLayoutPair<BLOCK_N, STAGES, Epi::kSmemBytes>;
+  auto kern = gemm_pair_kernel<BLOCK_N, ACC_STAGES, STAGES, A_MN, B_MN, Epi, EW, A_BLOCKED>;
+  static thread_local bool configured = false;   // per template instantiation
+  if (!configured) {
+    MSML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int units = ((shape.m_blocks + 1) / 2) * shape.n_blocks * shape.k_splits;
+  int pairs = num_sms() / 2;
+  if (units < pairs) pairs = units;
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(64 + 32 * EW);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MSML_PROF2(name, 2.0 * shape.M * shape.N * shape.K, min_bytes, st);
+  MSML_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, shape, epi));
+  MSML_LAUNCH_CHECK();
+  return 0;
+}
+
 inline GemmShape make_shape(int64_t M, int64_t N, int64_t K, int block_n, int k_splits = 1, bool n_fastest = false) {
   GemmShape s;
   s.M = (int)M; s.N = (int)N; s.K = (int)K;
+  s.a_blk_pitch = 0;
   s.n_fastest = n_fastest ? 1 : 0;
   s.m_blocks = (int)((M + kBlockM - 1) / kBlockM);
   s.n_blocks = (int)((N + block_n - 1) / block_n);

@@ -19,8 +19,9 @@ and runs it the B200 way:
     SGD updates, the stream forks and joins — is captured into a CUDA graph and replayed with no Python or launch
     overhead; the next batch's host-to-device copy runs under the current step (``prefetch``).
 
-Limits of the captured mode (documented, checked): PartialFC sample_rate must be 1 (sampling needs
-a data-dependent allocation).  With ``fused=True`` optimizers the learning rates are turned into device tensors
+Limits of the captured mode (documented, checked): with a sampled PartialFC (sample_rate < 1) the gathered batch must
+not exceed num_sample (the positives-outnumber-the-sample branch has a data-dependent size); the sampling itself —
+torch.rand through the graph-registered generator, radix select, gathers into fixed-capacity buffers — is captured.  With ``fused=True`` optimizers the learning rates are turned into device tensors
 at capture time, so torch LR schedulers keep working across replays; with other optimizers, and for momentum /
 weight decay, the values are baked in (call ``recapture()`` after changing them).  ``use_graph=False`` runs the identical step eagerly.
 """
@@ -50,8 +51,9 @@ class TrainStep:
         self._copy_stream, self._has_staged = None, False
         # convolution weight gradients run on a second stream and fill the idle SMs under the latency-bound BN kernels
         self.wgrad_side_stream = wgrad_side_stream
-        if use_graph and int(pfc.sample_rate) != 1:
-            raise ValueError("captured TrainStep needs PartialFC sample_rate == 1; use use_graph=False for sampled heads")
+        if use_graph and int(pfc.sample_rate) != 1 and batch_shape[0] * world_size > pfc.num_sample:
+            raise ValueError("captured TrainStep with a sampled PartialFC needs batch * world_size <= num_sample (the branch of "
+                             "ref partial_fc.py:89-90 has a data-dependent size); use use_graph=False")
 
     # ------------------------------------------------------------------ one eager step
     def _discover_used_params(self):

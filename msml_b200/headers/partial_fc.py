@@ -131,7 +131,7 @@ class PartialFC(Module):
         lib = load()
         ws_bytes = lib.msml_pfc_select_workspace(self.num_local)
         ws = self._buf("select_ws", (ws_bytes,), torch.uint8)
-        index = torch.empty((capacity,), dtype=torch.int64, device=self.device)
+        index = self._buf("index", (capacity,), torch.int64)
         n_index = self._buf("n_index", (1,), torch.int64)
         check(lib.msml_pfc_select(_ptr(perm), self.num_local, num_sample, _ptr(index), _ptr(n_index),
                                   _ptr(ws), ws_bytes, stream_ptr()))
@@ -139,6 +139,9 @@ class PartialFC(Module):
 
     @torch.no_grad()
     def sample(self, total_label):
+        """ref :77-94.  All per-step tensors (index, gathered rows, their momentum) are views of persistent scratch: a
+        sampled step allocates nothing once warm (the caching allocator otherwise recycles ~0.6 GB per step at 1M classes
+        through cudaMalloc / cudaFree stalls of tens of ms), and the step can be captured into a CUDA graph."""
         lib = load()
         n = total_label.numel()
         check(lib.msml_pfc_remap(_ptr(total_label), n, self.class_start, self.num_local, stream_ptr()))
@@ -147,28 +150,27 @@ class PartialFC(Module):
             if n > self.num_sample:
                 # the positives may outnumber num_sample (ref :89-90): count them first, without
                 # touching the generator, exactly as the reference does
-                probe = torch.zeros((self.num_local,), dtype=torch.float32, device=self.device)
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("PartialFC: a captured step needs batch_size * world_size <= num_sample (%d > %d): the "
+                                       "positives-outnumber-the-sample branch (ref :89-90) has a data-dependent size" % (n, self.num_sample))
+                probe = self._buf("probe", (self.num_local,), torch.float32).zero_()
                 check(lib.msml_pfc_mark_positive(_ptr(probe), _ptr(total_label), n, self.num_local, stream_ptr()))
-                pos_index, n_pos = self._select(probe, 0, n)
+                pos_index, n_pos = self._select(probe, 0, max(n, self.num_sample, 1))
                 n_pos_host = int(n_pos.item())
                 if n_pos_host > self.num_sample:
-                    index, n_index = pos_index[:n_pos_host], n_pos.clone()
+                    index, n_index = pos_index[:n_pos_host], n_pos
             if index is None:
                 perm = torch.rand(size=[self.num_local], device=self.device)
                 check(lib.msml_pfc_mark_positive(_ptr(perm), _ptr(total_label), n, self.num_local, stream_ptr()))
-                index, n_index = self._select(perm, self.num_sample, max(self.num_sample, 1))
+                index, n_index = self._select(perm, self.num_sample, max(n, self.num_sample, 1))
                 index = index[:self.num_sample]
             self.index = index
             check(lib.msml_pfc_searchsorted(_ptr(total_label), n, _ptr(index), _ptr(n_index), stream_ptr()))
             rows = index.numel()
-            sub_w = torch.empty((rows, self.embedding_size), dtype=torch.float32, device=self.device)
-            sub_m = torch.empty_like(sub_w)
+            sub_w = self._buf("sub_w", (rows, self.embedding_size), torch.float32)
+            sub_m = self._buf("sub_m", (rows, self.embedding_size), torch.float32)
             check(lib.msml_gather_rows_f32(_ptr(self.weight), _ptr(index), _ptr(sub_w), rows, self.embedding_size, stream_ptr()))
             check(lib.msml_gather_rows_f32(_ptr(self.weight_mom), _ptr(index), _ptr(sub_m), rows, self.embedding_size, stream_ptr()))
-            if not torch.cuda.is_current_stream_capturing():
-                main = torch.cuda.default_stream(self.device)
-                for t in (index, sub_w, sub_m):  # produced on the side stream, consumed on the main one
-                    t.record_stream(main)
             self.sub_weight = Parameter(sub_w)
             self.sub_weight_mom = sub_m
 
@@ -261,7 +263,9 @@ class PartialFC(Module):
             check(lib.msml_head_merge_stats(_ptr(gathered), W, B_tot, _ptr(gstats), _ptr(loss_v), stream_ptr()))
 
             dx_full = self._buf("dx_full", (B_tot, D), torch.float32)
-            dw = torch.empty((n_s, D), dtype=torch.float32, device=self.device)
+            # sample_rate 1: a fresh tensor per step as autograd would produce; sampled: persistent scratch (see sample())
+            dw = (torch.empty((n_s, D), dtype=torch.float32, device=self.device) if int(self.sample_rate) == 1
+                  else self._buf("dw", (n_s, D), torch.float32))
             check(lib.msml_head_bwd(_ptr(x), _ptr(wn), _ptr(inv_norm), _ptr(total_label), B_tot, n_s, D, mp,
                                     _ptr(gstats), _ptr(dx_full), _ptr(dw), _ptr(ws), ws_bytes, stream_ptr()))
             self.sub_weight.grad = dw

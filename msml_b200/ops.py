@@ -436,9 +436,10 @@ def gemm_tn(a, b):
     return c
 
 
-def gemm(a, b, a_mn=False, b_mn=False, block_n=256):
+def gemm(a, b, a_mn=False, b_mn=False, block_n=256, pair=False):
     """fp32 (M, N) = op(a) @ op(b)^T; a_mn / b_mn: the operand is stored (K, M) / (K, N) row-major and read in
-    place through MN-major UMMA descriptors (no transposed copy)."""
+    place through MN-major UMMA descriptors (no transposed copy).  pair=True runs the CTA-pair mainloop
+    (tcgen05.mma.cta_group::2, 256 x block_n tiles, block_n in {128, 256})."""
     require_cuda(a, b)
     lib = load()
     a = a.to(torch.bfloat16).contiguous()
@@ -448,8 +449,8 @@ def gemm(a, b, a_mn=False, b_mn=False, block_n=256):
     if K != K2:
         raise ValueError("gemm: K mismatch %d vs %d" % (K, K2))
     c = torch.empty((M, N), dtype=torch.float32, device=a.device)
-    check(lib.msml_gemm_bf16(_ptr(a), a.shape[1], int(a_mn), _ptr(b), b.shape[1], int(b_mn), _ptr(c), N, M, N, K,
-                             block_n, stream_ptr()))
+    fn = lib.msml_gemm_bf16_pair if pair else lib.msml_gemm_bf16
+    check(fn(_ptr(a), a.shape[1], int(a_mn), _ptr(b), b.shape[1], int(b_mn), _ptr(c), N, M, N, K, block_n, stream_ptr()))
     return c
 
 

@@ -246,3 +246,47 @@ def test_lr_schedule_is_honoured_by_the_captured_graph():
     step(img, label)
     w3 = w()
     assert not torch.equal(w2[0], w3[0]) and not torch.equal(w2[1], w3[1])
+
+
+@pytest.mark.parametrize("fused_head", [False, True])
+def test_captured_step_with_a_sampled_head(fused_head):
+    """sample_rate < 1 inside the CUDA graph: torch.rand through the graph-registered generator, radix
+    select and the row gathers into fixed-capacity buffers are all captured.  Every replay must draw a NEW sample that
+    contains the positives of ITS batch (ref partial_fc.py:84-88), train (loss finite, class centres of sampled rows move,
+    rows outside every sample stay bit-identical) — with the stock optimizer + update() and with headers.PartialFCSGD."""
+    need_gpu()
+    from msml_b200.backbones import MSML
+    from msml_b200.engine import TrainStep
+    from msml_b200.headers import ArcFace, PartialFC, PartialFCSGD
+    from oracle.detfill import fill_state_dict_
+    torch.manual_seed(3)
+    B, C = 8, 1000
+    net = MSML("iresnet18", "unet", (1, 1, 1, 1), C, fp16=False, header_type=None, fm_params=(3, 2, "sigmoid", "mul"))
+    fill_state_dict_(net)
+    net = net.cuda().train()
+    pfc = PartialFC(0, 0, 1, B, False, ArcFace(64.0, 0.5), C, sample_rate=0.2)
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
+    hp = dict(lr=0.01, momentum=0.9, weight_decay=5e-4)
+    opt_pfc = PartialFCSGD(pfc, **hp) if fused_head else torch.optim.SGD([{"params": pfc.parameters()}], fused=True, **hp)
+    step = TrainStep(net, pfc, opt, opt_pfc, (B, 3, 112, 112), use_graph=True)
+    step.recapture()
+    w0 = pfc.weight.clone()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    touched = torch.zeros(C, dtype=torch.bool, device="cuda")
+    seen = []
+    for _ in range(3):
+        img = torch.randn(B, 3, 112, 112, device="cuda", generator=g)
+        label = torch.randint(0, C, (B,), device="cuda", generator=g)
+        loss = step(img, label)
+        torch.cuda.synchronize()
+        assert torch.isfinite(loss)
+        idx = pfc.index.clone()
+        assert idx.numel() == pfc.num_sample == 200 and bool((idx[1:] > idx[:-1]).all())
+        assert bool(torch.isin(label, idx).all())                        # this batch's positives are in this replay's sample
+        touched[idx] = True
+        seen.append(idx)
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])     # a new draw every replay
+    moved = (pfc.weight != w0).any(dim=1)
+    assert bool(moved[touched].all()) and not bool(moved[~touched].any())
+    with pytest.raises(ValueError):                                                    # gathered batch > num_sample: refused up front
+        TrainStep(net, PartialFC(0, 0, 1, B, False, ArcFace(64.0, 0.5), 70, sample_rate=0.1), opt, opt_pfc, (B, 3, 112, 112), use_graph=True)

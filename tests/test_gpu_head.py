@@ -59,6 +59,27 @@ def test_gemm_operand_layouts_exact(a_mn, b_mn, block_n, M, N, K):
     assert torch.equal(c, a @ b.t())
 
 
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 128), (384, 520, 320), (200, 96, 1000), (1000, 512, 136), (1024, 2048, 512), (128, 256, 64)])
+def test_gemm_cta_pair_exact(a_mn, b_mn, block_n, M, N, K):
+    """The CTA-pair mainloop (clusters of two CTAs, tcgen05.mma.cta_group::2 with M = 256, each CTA staging its 128 rows
+    of A and half of the B tile): every operand-major combination on integer-valued operands, bit-exact — including an
+    odd number of 128-row blocks (the last pair's second CTA has no rows) and ragged N / K."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(M * 7 + N * 3 + K + block_n)
+    a = torch.randint(-4, 5, (M, K), device="cuda").float()
+    b = torch.randint(-4, 5, (N, K), device="cuda").float()
+    a_store = a.t().contiguous() if a_mn else a
+    b_store = b.t().contiguous() if b_mn else b
+    if (a_store.shape[1] % 8) or (b_store.shape[1] % 8):
+        pytest.skip("pitch must be a multiple of 8 elements")
+    c = ops.gemm(a_store, b_store, a_mn=a_mn, b_mn=b_mn, block_n=block_n, pair=True)
+    assert torch.equal(c, a @ b.t())
+
+
 # ------------------------------------------------------------------------------- sampling
 def _pfc(rank, W, B, C, sr, D, kind="arc", smak=(64.0, 0.5, 0.0, 0.0), comm=None):
     from msml_b200.headers import MarginSoftmax, PartialFC

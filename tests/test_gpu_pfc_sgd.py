@@ -60,7 +60,8 @@ def test_fused_update_equals_stock_step_plus_update_every_step(sample_rate, nest
         _fused_update(w0, m0, dw, index, nesterov=nesterov, **HP)
         torch.cuda.synchronize()
         # the only differences are fused multiply-adds against torch's separately rounded mul / add
-        assert_close(host(w0), host(pfc.weight), 2e-6, atol=2e-9, what="weight")
+        # (w' = w - lr * m' cancels where w ~ lr * m': the floor is an ulp of the operands, |w| ~ 1e-2 .. 1, not of the result)
+        assert_close(host(w0), host(pfc.weight), 2e-6, atol=5e-8, what="weight")
         assert_close(host(m0), host(pfc.weight_mom), 2e-6, atol=1e-6 * float(pfc.weight_mom.abs().max()), what="weight_mom")
         if index is not None:                   # rows outside the sample are untouched, bit for bit
             rest = torch.ones(pfc.num_local, dtype=torch.bool, device="cuda")
@@ -151,7 +152,7 @@ def test_fused_pfc_sgd_tensor_lr_emit_momentum_zero_and_errors():
     ref = torch.nn.Parameter(w.clone())
     ref.grad = dw.clone()
     torch.optim.SGD([ref], lr=0.1, momentum=0.0, dampening=0.5, weight_decay=5e-4).step()
-    assert_close(host(w1), host(ref.data), 2e-6, atol=2e-9, what="w momentum 0")
+    assert_close(host(w1), host(ref.data), 2e-6, atol=5e-8, what="w momentum 0")
     assert torch.equal(m1, mom)
     assert lib.msml_pfc_sgd_update(w.data_ptr(), mom.data_ptr(), dw.data_ptr(), None, n, n, 100, None, 0.1, 0.9, 0.0, 0.0, 0, None, None, st) != 0
     assert lib.msml_pfc_sgd_update(w.data_ptr(), mom.data_ptr(), dw.data_ptr(), None, n, n, D, None, 0.1, 0.0, 0.0, 0.0, 1, None, None, st) != 0
