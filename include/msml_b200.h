@@ -28,7 +28,7 @@ extern "C" {
 
 #define MSML_B200_ABI_VERSION 1
 
-typedef enum { MSML_OK = 0, MSML_EINVAL = -1, MSML_EALIGN = -2, MSML_EWORKSPACE = -3, MSML_EUNSUPPORTED = -4 } msml_status;
+typedef enum { MSML_OK = 0, MSML_EINVAL = -1, MSML_EALIGN = -2, MSML_EWORKSPACE = -3, MSML_EUNSUPPORTED = -4, MSML_ENCCL = -5 } msml_status;
 typedef enum { MSML_F32 = 0, MSML_BF16 = 1, MSML_F16 = 2 } msml_dtype;
 typedef enum { MSML_ACT_TANH = 0, MSML_ACT_SIGMOID = 1 } msml_act;       /* ref fmoperator.py:113-117 */
 typedef enum { MSML_ARITH_ADD = 0, MSML_ARITH_SUB = 1, MSML_ARITH_DIV = 2, MSML_ARITH_MUL = 3 } msml_arith; /* :71-81 */
@@ -239,6 +239,34 @@ int msml_head_bwd(const void* x_bf16, const void* wn_bf16, const float* inv_norm
                   int64_t B_tot, int64_t n_s, int64_t D, const msml_margin_params* margin_host,
                   const float* gstats, float* dx_full, float* dw,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The class-sharded step over NCCL, owned by the library.
+ * ref headers/partial_fc.py:110,126,136,141,162,174 issues six collectives per step; here three, enqueued from C on
+ * the caller's stream between the kernels.  NCCL is bound at run time (dlopen "libnccl.so.2": inside a PyTorch process
+ * that is the copy torch loaded).  comm == NULL means world size 1: same calls, no collective.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct msml_comm msml_comm;
+/* rank 0: a fresh 128-byte ncclUniqueId to broadcast to the other ranks by any means */
+int msml_nccl_unique_id(void* out128);
+/* every rank, with its CUDA device current: ncclCommInitRank (blocking; the only synchronous call of the library) */
+int msml_nccl_init(const void* unique_id128, int rank, int world, msml_comm** out);
+int msml_nccl_destroy(msml_comm* comm);
+int msml_comm_world(const msml_comm* comm);
+int msml_comm_rank(const msml_comm* comm);
+/* :110 + :126 + :79-81 in ONE all-gather: this rank's (B, D) fp32 embeddings are cast to bf16 and packed with its B int64
+ * labels into one message; after the gather, x_bf16 (B*W, D) is the contiguous GEMM operand and total_label (B*W) holds
+ * the labels remapped to this rank's shard (off-shard -> -1). */
+size_t msml_head_gather_workspace(int64_t B, int64_t W, int64_t D);
+int msml_head_gather(msml_comm* comm, const float* feat, const int64_t* label, int64_t B, int64_t D, int64_t class_start,
+                     int64_t num_local, void* x_bf16, int64_t* total_label, void* workspace, size_t workspace_bytes, void* stream);
+/* :132-175 on one stream: msml_head_fwd -> all-gather of the per-row (max, sum-exp, target logit) [replaces the MAX, SUM
+ * and loss all-reduces] -> msml_head_merge_stats -> msml_head_bwd -> reduce-scatter(dX) -> x world_size.
+ * x_grad (B, D) fp32, dw (n_s, D) fp32, loss: device scalar (identical on every rank). */
+size_t msml_head_step_workspace(int64_t B, int64_t W, int64_t n_s, int64_t D);
+int msml_head_step(msml_comm* comm, const void* x_bf16, const void* wn_bf16, const float* inv_norm, const int64_t* tl,
+                   int64_t B, int64_t n_s, int64_t D, const msml_margin_params* margin_host, float* x_grad, float* dw,
+                   float* loss, void* workspace, size_t workspace_bytes, void* stream);
 
 /* In-model full-FC margin heads (ref headers/margin_losses.py:275-303, 390-418) on a
  * materialised cosine matrix (B, C) fp32, in place:  fwd applies margin + scale, bwd multiplies

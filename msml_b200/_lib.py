@@ -69,6 +69,15 @@ SIGNATURES = {
     "msml_head_merge_stats": (c_int, [c_p, c_i64, c_i64, c_p, c_p, c_p]),
     "msml_head_bwd": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64,
                               ctypes.POINTER(MarginParams), c_p, c_p, c_p, c_p, c_size, c_p]),
+    "msml_nccl_unique_id": (c_int, [c_p]),
+    "msml_nccl_init": (c_int, [c_p, c_int, c_int, ctypes.POINTER(c_p)]),
+    "msml_nccl_destroy": (c_int, [c_p]),
+    "msml_comm_world": (c_int, [c_p]),
+    "msml_comm_rank": (c_int, [c_p]),
+    "msml_head_gather_workspace": (c_size, [c_i64, c_i64, c_i64]),
+    "msml_head_gather": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_size, c_p]),
+    "msml_head_step_workspace": (c_size, [c_i64, c_i64, c_i64, c_i64]),
+    "msml_head_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p, c_p, c_p, c_p, c_size, c_p]),
     "msml_margin_fwd": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p]),
     "msml_margin_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p]),
     "msml_gemm_bf16": (c_int, [c_p, c_i64, c_int, c_p, c_i64, c_int, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),

@@ -16,8 +16,8 @@ but the work is done by libmsml_b200.so:
                    msml_head_bwd (recompute + dX + dW with the normalise-backward epilogue)
                    -> reduce-scatter of dX (:172-175)
 
-Class shards exchange data through torch.distributed (NCCL over NVLink); with world_size == 1 no
-process group is needed.  ``margin_softmax`` must carry (kind, s, m, a, k): a
+Class shards exchange data through an ncclComm_t owned by the library (headers/_comm.NativeComm: three collectives
+per step, enqueued from C between the kernels); with world_size == 1 no process group is needed.  ``margin_softmax`` must carry (kind, s, m, a, k): a
 ``msml_b200.headers.MarginSoftmax`` (ArcFace()/CosFace()) or an AMArcFace/AMCosFace module.
 """
 import contextlib
@@ -31,7 +31,7 @@ from torch.nn.parameter import Parameter
 
 from .. import _lib
 from .._lib import check, load, stream_ptr
-from ._comm import TorchDistComm
+from ._comm import NativeComm, TorchDistComm
 
 EPSILON = 0.1  # label smoothing baked into the gradient (ref :154)
 
@@ -45,7 +45,6 @@ class PartialFC(Module):
     def __init__(self, rank, local_rank, world_size, batch_size, resume,
                  margin_softmax, num_classes, sample_rate=1.0, embedding_size=512, prefix="./", comm=None):
         super().__init__()
-        self.comm = comm if comm is not None else TorchDistComm(world_size, rank)
         self.num_classes = num_classes
         self.rank = rank
         self.local_rank = local_rank
@@ -69,6 +68,10 @@ class PartialFC(Module):
         self._margin = _lib.margin_params(margin_softmax.kind, margin_softmax.s, margin_softmax.m,
                                           margin_softmax.a, margin_softmax.k)
         load()  # fail loudly right here if the CUDA library is missing
+        # default: the library-owned communicator (three collectives per step enqueued from C); pass a TorchDistComm /
+        # LockstepComm to keep the collectives in Python
+        with torch.cuda.device(self.device):
+            self.comm = comm if comm is not None else NativeComm(world_size, rank, device=self.device)
 
         self.weight_name = os.path.join(self.prefix, "rank:{}_softmax_weight.pt".format(self.rank))
         self.weight_mom_name = os.path.join(self.prefix, "rank:{}_softmax_weight_mom.pt".format(self.rank))
@@ -138,13 +141,14 @@ class PartialFC(Module):
         return index, n_index
 
     @torch.no_grad()
-    def sample(self, total_label):
-        """ref :77-94.  All per-step tensors (index, gathered rows, their momentum) are views of persistent scratch: a
+    def sample(self, total_label, remapped=False):
+        """ref :77-94 (remapped=True: total_label already holds shard-local labels, msml_head_gather did :79-81).  All per-step tensors (index, gathered rows, their momentum) are views of persistent scratch: a
         sampled step allocates nothing once warm (the caching allocator otherwise recycles ~0.6 GB per step at 1M classes
         through cudaMalloc / cudaFree stalls of tens of ms), and the step can be captured into a CUDA graph."""
         lib = load()
         n = total_label.numel()
-        check(lib.msml_pfc_remap(_ptr(total_label), n, self.class_start, self.num_local, stream_ptr()))
+        if not remapped:
+            check(lib.msml_pfc_remap(_ptr(total_label), n, self.class_start, self.num_local, stream_ptr()))
         if int(self.sample_rate) != 1:
             index = None
             if n > self.num_sample:
@@ -224,10 +228,52 @@ class PartialFC(Module):
                 total_label.record_stream(torch.cuda.current_stream(self.device))
             return total_label, norm_weight
 
+    def _forward_backward_native(self, label, features, optimizer):
+        """The product path: two C calls, everything on the current stream (a valid subsumption of the reference's side
+        stream, :107 / :97): msml_head_gather [pack -> ncclAllGather -> unpack + remap], sampling, optimizer surgery and
+        msml_wnorm_cast as in prepare(), then msml_head_step [fwd GEMM -> ncclAllGather(row stats) -> merge + loss ->
+        backward GEMMs -> ncclReduceScatter(dX) -> x world_size]."""
+        lib = load()
+        W, B, D = self.world_size, self.batch_size, self.embedding_size
+        B_tot = B * W
+        h = self.comm.handle
+        with torch.no_grad():
+            feat = features.detach().to(torch.float32).contiguous()
+            lab = label.detach().to(torch.int64).contiguous()
+            if feat.shape != (B, D) or lab.shape != (B,):
+                raise ValueError("PartialFC: expected features %s and label %s, got %s and %s" % ((B, D), (B,), tuple(feat.shape), tuple(lab.shape)))
+            x = self._buf("x", (B_tot, D), torch.bfloat16)
+            total_label = self._buf("total_label", (B_tot,), torch.int64)
+            gbytes = lib.msml_head_gather_workspace(B, W, D)
+            gws = self._buf("gather_ws", (gbytes,), torch.uint8)
+            check(lib.msml_head_gather(h, _ptr(feat), _ptr(lab), B, D, self.class_start, self.num_local, _ptr(x), _ptr(total_label),
+                                       _ptr(gws), gbytes, stream_ptr()))
+            self.sample(total_label, remapped=True)
+            if optimizer is not None:
+                # optimizer surgery, ref :112-114
+                optimizer.state.pop(optimizer.param_groups[-1]['params'][0], None)
+                optimizer.param_groups[-1]['params'][0] = self.sub_weight
+                optimizer.state[self.sub_weight]['momentum_buffer'] = self.sub_weight_mom
+            wn, inv_norm = self._normalize_weight()
+            n_s = wn.shape[0]
+            sbytes = lib.msml_head_step_workspace(B, W, n_s, D)
+            sws = self._buf("head_ws", (sbytes,), torch.uint8)
+            x_grad = torch.empty((B, D), dtype=torch.float32, device=self.device)
+            loss_v = torch.empty((), dtype=torch.float32, device=self.device)
+            dw = (torch.empty((n_s, D), dtype=torch.float32, device=self.device) if int(self.sample_rate) == 1
+                  else self._buf("dw", (n_s, D), torch.float32))
+            check(lib.msml_head_step(h, _ptr(x), _ptr(wn), _ptr(inv_norm), _ptr(total_label), B, n_s, D, ctypes.byref(self._margin),
+                                     _ptr(x_grad), _ptr(dw), _ptr(loss_v), _ptr(sws), sbytes, stream_ptr()))
+            self.sub_weight.grad = dw
+        self.last_loss = loss_v
+        return x_grad, loss_v
+
     def forward_backward(self, label, features, optimizer):
         """features (B, D) are assumed L2-normalised by the caller (ref :119)."""
         lib = load()
         _lib.require_cuda(label, features)
+        if getattr(self.comm, "native", False):
+            return self._forward_backward_native(label, features, optimizer)
         W, B, D = self.world_size, self.batch_size, self.embedding_size
         B_tot = B * W
         main = torch.cuda.current_stream(self.device)
