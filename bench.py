@@ -435,7 +435,7 @@ def run_train(args, rank, local_rank, world):
     from msml_b200 import _lib, ops
     from msml_b200.backbones import MSML
     from msml_b200.engine import TrainStep, broadcast_parameters
-    from msml_b200.headers import ArcFace, PartialFC
+    from msml_b200.headers import ArcFace, PartialFC, PartialFCSGD
 
     lib = _lib.load()
     dev = torch.device("cuda", local_rank)
@@ -449,7 +449,10 @@ def run_train(args, rank, local_rank, world):
     pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), NUM_CLASSES, sample_rate=1.0, embedding_size=512)
     lr = 0.1 * BATCH * world / 512
     opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
-    opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
+    # the head's optimizer (ref train.py:188-191: SGD over module_partial_fc.parameters(), momentum 0.9, wd 5e-4) as ONE
+    # kernel on the shard rows that also emits the next step's normalised bf16 centres
+    opt_pfc = (torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True) if args.stock_head_sgd
+               else PartialFCSGD(pfc, lr=lr, momentum=0.9, weight_decay=5e-4, emit_normalized=True))
     step = TrainStep(net, pfc, opt, opt_pfc, (BATCH, 3, 112, 112), world_size=world, max_norm=5.0, use_graph=not args.eager)
     head_check = head_parity_check(pfc, rank, world, dev, BATCH, NUM_CLASSES)     # before anything trains the class centres
 
@@ -708,6 +711,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="head workload only: per-rank batch (1024 on one GPU reproduces the "
                     "per-rank GEMM shapes of the 8-GPU config-4 run: B_tot=1024 rows against a 125,000-class shard)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per step of the CPU arm (a bounded sample of the 128/GPU workload)")
+    ap.add_argument("--stock-head-sgd", action="store_true", help="train workload: torch.optim.SGD(fused=True) + update() for the class centres "
+                    "instead of headers.PartialFCSGD")
     ap.add_argument("--fused-sgd", action="store_true", help="head workload: headers.PartialFCSGD instead of torch.optim.SGD + update()")
     ap.add_argument("--no-head-check", action="store_true", help="skip the fp64-oracle loss check before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")

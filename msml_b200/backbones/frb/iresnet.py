@@ -2,9 +2,13 @@
 iresnet18/34/50 :444-481): iResNet trunk with one Feature-Masking operator after each of the
 four stages (ref :213-223).  The FM operators carry the fused CUDA tail (see fm/fmoperator.py).
 
-The frozen peer (teacher) network and the image decoder of the reference need pretrained files
-that are not shipped (ref backbones/pretrained/README.md) and are out of scope:
-``use_ori`` / ``use_decoder`` are accepted, and a peer can be injected with ``set_peer``.
+Peer-guided training (ref :131-146,203-206): ``peer_params['use_ori']`` builds the frozen teacher of
+backbones/peer/arcface.py exactly as the reference does (arcface18/34/50 for an Arc head, cosface50_casia for a Cos head
+on iresnet50) and feeds its four detached stage outputs to the FM operators when ``ori`` is given.  The reference loads the
+teacher from ``./backbones/pretrained/*.pth``, which it does not ship (FileNotFoundError, as there);
+``peer_params['peer_pretrained'] = False`` (an addition) builds the same teacher with random weights, and ``set_peer``
+injects any module with the ``(feature, [ft0..ft3])`` contract.  The image decoder (``use_decoder``) stays out of scope:
+its loss is dropped by the reference itself (tuple bug, ref :228).
 """
 import torch
 from torch import nn
@@ -41,11 +45,26 @@ class IResNet(nn.Module):
         self.fm_ops = nn.ModuleList(fm_ops)
 
         peer_params = peer_params or {}
-        self.peer = None
+        self.peer = None      # peer type is consistent with msml.header_type (ref :131-146)
         self.header_type = str(peer_params.get('header_type', '')).lower()
-        if peer_params.get('use_ori') and not ('arc' in self.header_type or 'cos' in self.header_type):
-            raise ValueError('Error type of iresnet, cannot decide peer network.')
+        if peer_params.get('use_ori'):
+            from ..peer import arcface18, arcface34, arcface50, cosface50_casia
+            pre = bool(peer_params.get('peer_pretrained', True))
+            layers = list(layers)
+            if 'arc' in self.header_type:
+                ctor = {(2, 2, 2, 2): arcface18, (3, 4, 6, 3): arcface34, (3, 4, 14, 3): arcface50}.get(tuple(layers))
+                if ctor is not None:
+                    self.peer = ctor(pretrained=pre).requires_grad_(False)
+            elif 'cos' in self.header_type:
+                if layers == [3, 4, 14, 3]:
+                    self.peer = cosface50_casia(pretrained=pre).requires_grad_(False)
+            else:
+                raise ValueError('Error type of iresnet, cannot decide peer network.')
         self.use_decoder = bool(peer_params.get('use_decoder'))
+        # NOTE (parity with the code as written): like the reference, the teacher is registered BEFORE the initialisation
+        # loop below, so its convolutions are re-drawn from N(0, 0.1) and its BatchNorm affine parameters reset to (1, 0)
+        # even when pretrained weights were just loaded (ref :131-146 then :152-157) — only PReLU slopes, fc and the BN
+        # running statistics of the checkpoint survive.  Load the teacher's state_dict after construction to avoid that.
 
         for m in self.modules():     # ref :157-162
             if isinstance(m, nn.Conv2d):
@@ -66,8 +85,8 @@ class IResNet(nn.Module):
         ft = (None, None, None, None)
         if ori is not None:
             if self.peer is None:
-                raise NotImplementedError("peer-guided training needs a pretrained peer network (not shipped with "
-                                          "the reference); inject one with IResNet.set_peer()")
+                raise RuntimeError("`ori` given but this FRB has no peer network: build MSML with peer_params['use_ori'] = True "
+                                   "(and an Arc / Cos head), or inject one with IResNet.set_peer()")
             _, ft = self.peer(ori)
         x = ops.bn_act(ops.conv2d_padded_in(x, self.conv1, x.shape[1] - self.conv1.in_channels), self.bn1, self.prelu)
         kd_terms = []

@@ -258,6 +258,11 @@ class TrainStep:
         self.graph = g
         if preserve_state:
             self._restore(snap, had_momentum)
+            if getattr(self.opt_pfc, "emit_normalized", False):
+                # the captured step expects the previous step's normalised centres (headers.PartialFCSGD emits them):
+                # the restore just rewrote the centres, so produce them once, eagerly, for the first replay
+                self.pfc._normalize_weight(force=True)
+                self.pfc._wn_fresh = False
             if mom_snap is not None:
                 with torch.no_grad():
                     bufs = [st["momentum_buffer"] for st in self.opt_backbone.state.values() if st.get("momentum_buffer") is not None]

@@ -200,12 +200,20 @@ class PartialFC(Module):
         check(lib.msml_scatter_rows_f32(_ptr(self.weight), _ptr(self.index), _ptr(self.sub_weight.data), rows,
                                         self.embedding_size, stream_ptr()))
 
-    def _normalize_weight(self):
+    def invalidate_normalized(self):
+        """The class centres were changed from outside (checkpoint load, manual edit): recompute the normalised bf16 copy
+        at the next step even if a PartialFCSGD(emit_normalized=True) had already produced it."""
+        self._wn_fresh = False
+
+    def _normalize_weight(self, force=False):
         """ref :115 -> (wn bf16 (n_s, D), inv_norm fp32 (n_s))."""
         lib = load()
         n_s, D = self.sub_weight.shape
         wn = self._buf("wn", (n_s, D), torch.bfloat16)
         inv = self._buf("inv_norm", (n_s,), torch.float32)
+        if getattr(self, "_wn_fresh", False) and not force and int(self.sample_rate) == 1:
+            self._wn_fresh = False      # produced by the previous step's PartialFCSGD update (one-shot: see emit_normalized)
+            return wn, inv
         check(lib.msml_wnorm_cast(_ptr(self.sub_weight.data), _ptr(wn), None, 0, _ptr(inv), n_s, D, stream_ptr()))
         return wn, inv
 

@@ -31,7 +31,7 @@ def _ptr(t):
 
 
 class PartialFCSGD(torch.optim.Optimizer):
-    def __init__(self, module, lr, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=False):
+    def __init__(self, module, lr, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=False, emit_normalized=False):
         if not isinstance(lr, torch.Tensor) and lr < 0.0:
             raise ValueError("Invalid learning rate: {}".format(lr))
         if momentum < 0.0:
@@ -48,6 +48,11 @@ class PartialFCSGD(torch.optim.Optimizer):
                         capturable_lr=True)
         super().__init__([{"params": list(module.parameters())}], defaults)
         self.module = module
+        # emit_normalized (sample_rate 1 only): the update kernel also writes the NEXT step's unit-norm bf16 centres and
+        # 1/||w|| (it holds the updated row in registers anyway), so PartialFC skips its msml_wnorm_cast pass (ref
+        # partial_fc.py:115).  Opt-in because it assumes nobody else writes module.weight between two steps; call
+        # module.invalidate_normalized() after loading / editing the class centres by hand.
+        self.emit_normalized = bool(emit_normalized) and int(module.sample_rate) == 1
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -70,9 +75,14 @@ class PartialFCSGD(torch.optim.Optimizer):
         lr_dev = lr if isinstance(lr, torch.Tensor) and lr.is_cuda else None        # captured steps read it from memory
         if lr_dev is not None and lr_dev.dtype != torch.float32:
             raise RuntimeError("PartialFCSGD: a tensor lr must be float32")
+        wn = inv = None
+        if self.emit_normalized:
+            wn = m._buf("wn", (n_s, D), torch.bfloat16)
+            inv = m._buf("inv_norm", (n_s,), torch.float32)
         check(load().msml_pfc_sgd_update(_ptr(m.weight), _ptr(m.weight_mom), _ptr(dw), _ptr(index), n_s, m.num_local, D,
                                          _ptr(lr_dev), 0.0 if lr_dev is not None else float(lr), float(g["momentum"]),
-                                         float(g["weight_decay"]), float(g["dampening"]), int(bool(g["nesterov"])), None, None,
+                                         float(g["weight_decay"]), float(g["dampening"]), int(bool(g["nesterov"])), _ptr(wn), _ptr(inv),
                                          stream_ptr()))
+        m._wn_fresh = self.emit_normalized
         m._fused_step_done = True           # this step's rows are already in the shard: the next update() has nothing to scatter
         return loss

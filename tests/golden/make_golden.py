@@ -421,8 +421,44 @@ def gen_model():
              **gn)
 
 
+def gen_model_peer():
+    """MSML with the peer-guided branch on (ref config.yaml:22-26 default: use_ori / use_conv / mask_trans conv): the frozen
+    teacher of ref backbones/peer/arcface.py with RANDOM deterministic weights (the reference ships none: its
+    arcface18() would raise FileNotFoundError, so the constructor is called with pretrained=False — harness-only)."""
+    import backbones
+    import backbones.peer as peer_mod
+    real = peer_mod.arcface18
+    peer_mod.arcface18 = lambda *a, **k: real(pretrained=False)
+    try:
+        net = backbones.MSML("iresnet18", "unet", (1, 1, 1, 1), 97, fp16=False, header_type="AMArcFace",
+                             header_params=(64.0, 0.5, 0.0, 0.0), fm_params=(3, 2, "sigmoid", "mul"),
+                             peer_params={"use_ori": True, "use_conv": True, "mask_trans": "conv", "use_decoder": False})
+    finally:
+        peer_mod.arcface18 = real
+    fill_state_dict_(net)
+    assert not any(p.requires_grad for p in net.frb.peer.parameters())
+    x = det_tensor("model.x", (2, 3, 112, 112))
+    ori = det_tensor("model.ori", (2, 3, 112, 112))
+    label = det_labels("model.l", 2, 97)
+    net.eval()
+    with torch.no_grad():
+        feat, seg = net(x)                                  # eval: no ori, the distillation branch is inactive
+        pf, inter = net.frb.peer(ori)
+    net.train()
+    final_cls, final_seg, kd = net(x, label, ori)
+    loss = torch.nn.functional.cross_entropy(final_cls, label) + final_seg.mean()
+    loss.backward()
+    named = dict(net.named_parameters())
+    keys = ["frb.conv1.weight", "frb.fm_ops.0.same_conv.weight", "frb.fm_ops.0.conv_m.0.weight", "frb.fm_ops.1.conv1.0.weight",
+            "frb.fm_ops.3.conv2.3.weight", "frb.layer4.1.bn3.weight", "classification.weight"]
+    gn = {"gradnorm." + k: named[k].grad.norm() for k in named if named[k].grad is not None}
+    save("model_iresnet18_peer", eval_feature=feat, eval_seg=seg, peer_feature=pf, peer_ft3=inter[3], peer_ft0_norm=inter[0].norm(),
+         train_cls=final_cls, train_seg=final_seg, kd=np.float32(kd.item()), loss=loss,
+         **{"grad." + k: named[k].grad for k in keys if named[k].numel() < 200000}, **gn)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fm", "fm_peer", "dap", "margins", "pfc", "model", "consensus"]
+    which = sys.argv[1:] or ["fm", "fm_peer", "dap", "margins", "pfc", "model", "model_peer", "consensus"]
     seeds()
     for w in which:
         globals()["gen_" + w]()

@@ -160,3 +160,42 @@ def test_fused_pfc_sgd_tensor_lr_emit_momentum_zero_and_errors():
         PartialFCSGD(PartialFC(0, 0, 1, 4, False, ArcFace(), 64), lr=0.1, momentum=0.0, nesterov=True)
     with pytest.raises(TypeError):
         PartialFCSGD(torch.nn.Linear(4, 4), lr=0.1)
+
+
+def test_emitted_normalised_centres_replace_the_wnorm_pass():
+    """PartialFCSGD(emit_normalized=True): the update kernel writes the next step's unit-norm bf16 centres, PartialFC skips
+    msml_wnorm_cast (ref partial_fc.py:115) — same trajectory, one kernel fewer; invalidate_normalized() brings the pass back."""
+    need_gpu()
+    from msml_b200 import ops
+    from msml_b200.headers import PartialFCSGD
+    B, C, D = 16, 1000, 512
+    out = {}
+    for emit in (False, True):
+        pfc = _pfc(1.0, B, C, D)
+        opt = PartialFCSGD(pfc, emit_normalized=emit, **HP)
+        losses, launches = [], []
+        for feat, label in _batches(4, B, C, D):
+            n0 = ops.launch_count()
+            _x, loss = pfc.forward_backward(label, feat, opt)
+            opt.step()
+            pfc.update()
+            launches.append(ops.launch_count() - n0)
+            losses.append(float(loss))
+        out[emit] = (losses, launches, pfc.weight.clone())
+    assert np.allclose(out[True][0], out[False][0], rtol=2e-4), (out[True][0], out[False][0])
+    assert_close(host(out[True][2]), host(out[False][2]), 1e-3, atol_frac=1e-4, what="weight")
+    assert out[True][1][0] == out[False][1][0] and all(a == b - 1 for a, b in zip(out[True][1][1:], out[False][1][1:])), out
+    # a manual edit of the class centres must not be served from the stale copy
+    pfc = _pfc(1.0, B, C, D)
+    opt = PartialFCSGD(pfc, emit_normalized=True, **HP)
+    (f0, l0), (f1, l1) = _batches(2, B, C, D)
+    pfc.forward_backward(l0, f0, opt)
+    opt.step()
+    with torch.no_grad():
+        pfc.weight.mul_(-1.0)
+    pfc.invalidate_normalized()
+    _x, loss = pfc.forward_backward(l1, f1, None)
+    ref = _pfc(1.0, B, C, D)
+    ref.weight.copy_(pfc.weight)
+    _x, want = ref.forward_backward(l1, f1, None)
+    assert abs(float(loss) - float(want)) <= 1e-6 * abs(float(want))
