@@ -155,17 +155,21 @@ struct EpiFwdStats : NoScratch {
             tgt[row] = t * mg.s;
           }
           const int valid = n_s - col0;                      // >= 1
-          float cmax = -INFINITY;
+          if (valid < 32) {                                  // ragged last chunk (warp-uniform, once per row block)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = (j < valid) ? v[j] * s2 : -INFINITY;
-            cmax = fmaxf(cmax, v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = (j < valid) ? v[j] : -INFINITY;
           }
-          const float new_max = fmaxf(run_max, cmax);        // finite: column col0 < n_s exists
-          float acc = 0.f;
+          // max(s2 * v) = s2 * max(v) (s > 0): FMNMX on the raw cosines, four independent chains
+          float mx[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc += fast_exp2(v[j] - new_max);
-          run_sum = run_sum * fast_exp2(run_max - new_max) + acc;
+          for (int j = 4; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], v[j]);
+          const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * s2;
+          const float new_max = fmaxf(run_max, cmax);        // finite: column col0 < n_s exists
+          // exp2(s2 * v - new_max): one FFMA + EX2 + FADD per element, four independent sums (-inf padding gives 0)
+          float a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a4[j & 3] += fast_exp2(fmaf(v[j], s2, -new_max));
+          run_sum = run_sum * fast_exp2(run_max - new_max) + ((a4[0] + a4[1]) + (a4[2] + a4[3]));
           run_max = new_max;
           if (c + h + 1 < n_chunks) tmem_ld_wait(buf[h ^ 1]);
         }
@@ -399,6 +403,7 @@ struct EpiDwNormBwd {
 static int to_margin(const msml_margin_params* p, Margin* out) {
   MSML_REQUIRE(p != nullptr, MSML_EINVAL, "margin params missing");
   MSML_REQUIRE(p->kind == MSML_MARGIN_ARC || p->kind == MSML_MARGIN_COS, MSML_EINVAL, "margin kind error (%d)", p->kind);
+  MSML_REQUIRE(p->s > 0.f, MSML_EINVAL, "margin scale s must be positive (got %g)", (double)p->s);
   out->kind = p->kind; out->s = p->s; out->m = p->m; out->a = p->a; out->k = p->k;
   return 0;
 }
