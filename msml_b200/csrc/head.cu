@@ -425,11 +425,23 @@ static bool dcos_blocked() {
   if (v < 0) { const char* e = getenv("MSML_HEAD_DCOS_ROWMAJOR"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
 }
-// MSML_HEAD_PAIR=0 selects the single-CTA kernels for the three tensor-bound GEMMs (A/B measurements); default: CTA pairs
-static bool head_pairs() {
+// Which of the tensor-bound GEMMs run on CTA pairs (cta_group::2).  Measured at config-4 per-rank shapes (B_tot = 1024,
+// 125,000 classes; profiles/r02_head_ab.md): dX 104.7 -> 98.4 us (long K loop, light epilogue), but fwd 109 -> 120 us and
+// dcos 140 -> 155 us (8 k-blocks per tile: the pair's cross-SM accumulator hand-off is paid per tile), so the default is
+// pairs for dX only.  MSML_HEAD_PAIR=all | dx | 0 overrides (A/B measurements, tests).
+// MSML_HEAD_ARES=0 switches the resident-A forward / dcos kernels off (A/B measurements); default on when they apply
+static bool head_ares() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MSML_HEAD_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("MSML_HEAD_ARES"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
+}
+static int head_pair_mode() {       // 0 none, 1 dX only, 2 all
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MSML_HEAD_PAIR");
+    v = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == 'a' || e[0] == '1' ? 2 : 1));
+  }
+  return v;
 }
 constexpr int kFwdBlockN = 128;   // smallest class tile; each tile yields two softmax partials (one per epilogue half)
 
@@ -603,7 +615,7 @@ extern "C" int msml_head_fwd(const void* x, const void* wn, const int64_t* tl, i
   if (int e = to_margin(margin, &mg)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   HeadWs h = carve(ws, B_tot, n_s);
-  const bool pair = head_pairs() && B_tot > kBlockM;      // a pair needs two 128-row blocks to be worth it
+  const bool pair = head_pair_mode() == 2 && B_tot > kBlockM;      // a pair needs two 128-row blocks to be worth it
   const int bn = pick_block_n(B_tot, n_s, pair);
   CUtensorMap ma, mb;
   if (int e = encode_tmap_bf16_kmajor(&ma, x, B_tot, D, D, kBlockM)) return e;
@@ -612,7 +624,12 @@ extern "C" int msml_head_fwd(const void* x, const void* wn, const int64_t* tl, i
   epi.tl = tl; epi.mg = mg; epi.B_tot = (int)B_tot; epi.n_s = (int)n_s; epi.block_n = bn;
   epi.part_max = h.part_max; epi.part_sum = h.part_sum; epi.tgt = h.tgt;
   const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D;      // stream Wn + X once (bf16)
-  if (pair) {
+  const int64_t mblocks = (B_tot + kBlockM - 1) / kBlockM;
+  // resident A: K = D <= 512, at least two CTAs per m-block, and enough class tiles that the one-off A load is amortised
+  const bool ares = head_ares() && !pair && bn == 256 && D <= 512 && mblocks * 2 <= num_sms() && (n_s + 255) / 256 >= 4 * (num_sms() / mblocks);
+  if (ares) {
+    if (int e = launch_gemm_ares<256, 2, 3, 8, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
+  } else if (pair) {
     if (bn == 256) {
       if (int e = launch_gemm_pair<256, 2, 6, false, false, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
     } else {
@@ -648,7 +665,8 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
   HeadWs h = carve(ws, B_tot, n_s);
 
   const bool blocked = dcos_blocked();
-  const bool pair = head_pairs() && B_tot > kBlockM;
+  const bool pair = head_pair_mode() == 2 && B_tot > kBlockM;
+  const bool pair_dx = head_pair_mode() >= 1 && B_tot > kBlockM;
   // 1. recompute logits -> dcos (bf16; tile-blocked, see tc_gemm.cuh) + rdot[n] = <Wn[n], dWn[n]>
   {
     MSML_CUDA(cudaMemsetAsync(h.rdot, 0, sizeof(float) * (size_t)n_s, st));
@@ -690,18 +708,18 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
       if (int e = encode_tmap_bf16_kmajor(&ma, h.dcos, B_tot, n_s, h.ld_dc, kBlockM)) return e;
     }
     if (int e = encode_tmap_bf16_mnmajor(&mb, wn, D, n_s, D)) return e;
-    const int m_units = pair ? (int)((B_tot + 2 * kBlockM - 1) / (2 * kBlockM)) : (int)((B_tot + kBlockM - 1) / kBlockM);
+    const int m_units = pair_dx ? (int)((B_tot + 2 * kBlockM - 1) / (2 * kBlockM)) : (int)((B_tot + kBlockM - 1) / kBlockM);
     const int tiles = m_units * (int)((D + 255) / 256);
     // as many split-K units as fit in ONE wave of the persistent grid (rounding up would leave a second, almost
     // empty wave: 16 tiles x 10 splits = 160 units on 148 SMs ran at 54 % occupancy)
-    int splits = (pair ? num_sms() / 2 : num_sms()) / tiles;
+    int splits = (pair_dx ? num_sms() / 2 : num_sms()) / tiles;
     if (splits < 1) splits = 1;
     EpiDxAccum epi;
     epi.dx = dx_full; epi.B_tot = (int)B_tot; epi.D = (int)D; epi.block_n = 256;
     const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 4.0 * (double)B_tot * D;
     GemmShape sh = make_shape(B_tot, D, n_s, 256, splits);
     sh.a_blk_pitch = (int)h.blk_pitch;
-    if (pair) {
+    if (pair_dx) {
       if (blocked) { if (int e = launch_gemm_pair<256, 2, 6, false, true, 8, true>("head_bwd_dx_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
       else { if (int e = launch_gemm_pair<256, 2, 6, false, true, 8, false>("head_bwd_dx_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
     } else {

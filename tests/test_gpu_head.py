@@ -296,10 +296,12 @@ def test_label_smoothing_term_is_visible_in_non_target_rows():
         check_w_grad_rows(got, res0["w_grad"][0], res["total_label"][0], "w_grad without smoothing")
 
 
-@pytest.mark.parametrize("B_tot,n_s", [(1024, 11679), (1024, 11678)])
+@pytest.mark.parametrize("B_tot,n_s", [(1024, 11679), (1024, 11678), (1024, 20011), (300, 40003)])
 def test_head_step_at_config3_w8_rank_shape_vs_oracle(B_tot, n_s):
     """The GEMM shapes one rank of the 8-GPU BASELINE config-3 run sees (B_tot = 8 x 128 gathered rows against an
-    11,679 / 11,678-class shard; 8 M-blocks, ragged last class tile) against the fp64 oracle."""
+    11,679 / 11,678-class shard; 8 M-blocks, ragged last class tile) against the fp64 oracle; the two larger shards are
+    long enough for the resident-A forward kernel (tc_gemm.cuh: gemm_ares_kernel) to be selected, one of them with a ragged
+    last row block and an odd number of row blocks for the CTA-pair dX kernel."""
     need_gpu()
     torch.manual_seed(n_s)
     D = 512
