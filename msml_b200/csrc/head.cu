@@ -429,12 +429,6 @@ static bool dcos_blocked() {
 // 125,000 classes; profiles/r02_head_ab.md): dX 104.7 -> 98.4 us (long K loop, light epilogue), but fwd 109 -> 120 us and
 // dcos 140 -> 155 us (8 k-blocks per tile: the pair's cross-SM accumulator hand-off is paid per tile), so the default is
 // pairs for dX only.  MSML_HEAD_PAIR=all | dx | 0 overrides (A/B measurements, tests).
-// MSML_HEAD_ARES=0 switches the resident-A forward / dcos kernels off (A/B measurements); default on when they apply
-static bool head_ares() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MSML_HEAD_ARES"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
 static int head_pair_mode() {       // 0 none, 1 dX only, 2 all
   static int v = -1;
   if (v < 0) {
@@ -624,12 +618,7 @@ extern "C" int msml_head_fwd(const void* x, const void* wn, const int64_t* tl, i
   epi.tl = tl; epi.mg = mg; epi.B_tot = (int)B_tot; epi.n_s = (int)n_s; epi.block_n = bn;
   epi.part_max = h.part_max; epi.part_sum = h.part_sum; epi.tgt = h.tgt;
   const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D;      // stream Wn + X once (bf16)
-  const int64_t mblocks = (B_tot + kBlockM - 1) / kBlockM;
-  // resident A: K = D <= 512, at least two CTAs per m-block, and enough class tiles that the one-off A load is amortised
-  const bool ares = head_ares() && !pair && bn == 256 && D <= 512 && mblocks * 2 <= num_sms() && (n_s + 255) / 256 >= 4 * (num_sms() / mblocks);
-  if (ares) {
-    if (int e = launch_gemm_ares<256, 2, 3, 8, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
-  } else if (pair) {
+  if (pair) {
     if (bn == 256) {
       if (int e = launch_gemm_pair<256, 2, 6, false, false, 8>("head_fwd_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
     } else {

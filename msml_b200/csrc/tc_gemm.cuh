@@ -105,6 +105,45 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- warp-converged issue: every lane of the issuing warp executes these, ONE elected lane performs the operation.
+// The round-1 kernels branched on `lane == 0` around the whole role; ptxas then wraps every uniform-datapath instruction
+// (UTCHMMA, UTCBAR, UTMALDG and the descriptor arithmetic feeding them) in an ELECT / BRA.U.ANY loop, ~25 SASS instructions
+// per MMA: the issuing thread needed ~750 cycles per k-block for 512 cycles of tensor work and WAS the limiter (ncu: the MMA
+// thread never waits on a barrier, tensor pipe 68 % busy; profiles/r02_ncu_head_summary.md).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_elect(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
@@ -318,41 +357,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc(kBlockM, UMMA_N, A_MN, B_MN);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        const int ks = u / (shape.m_blocks * shape.n_blocks);
-        const int kb0 = ks * shape.k_blocks_per_split;
-        int kb1 = kb0 + shape.k_blocks_per_split;
-        if (kb1 > total_k_blocks) kb1 = total_k_blocks;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer: the whole warp walks the loop converged, one elected lane issues ==============
+    constexpr uint32_t idesc = make_idesc(kBlockM, UMMA_N, A_MN, B_MN);
+    // descriptor templates for stage 0, k-step 0: the start-address field holds (address >> 4) in its low 14 bits, so the
+    // operand of another stage / k-step / N half is the template plus a byte offset >> 4 (shared memory is < 256 KB: no carry)
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t da0 = A_MN ? make_smem_desc_mn(smem_base) : make_smem_desc(smem_base);
+    const uint64_t db0 = B_MN ? make_smem_desc_mn(smem_base + L::kABytes) : make_smem_desc(smem_base + L::kABytes);
+    constexpr uint32_t kAStep = (A_MN ? 2048 : kUmmaK * 2) >> 4;          // K-major: +32 B per K-step; MN-major: +16 k-rows = 2 KB
+    constexpr uint32_t kBStep = (B_MN ? 2048 : kUmmaK * 2) >> 4;
+    constexpr uint32_t kBSub = (B_MN ? (UMMA_N / 64) * 8192 : UMMA_N * kBlockK * 2) >> 4;
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int ks = u / (shape.m_blocks * shape.n_blocks);
+      const int kb0 = ks * shape.k_blocks_per_split;
+      int kb1 = kb0 + shape.k_blocks_per_split;
+      if (kb1 > total_k_blocks) kb1 = total_k_blocks;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
+        const uint64_t so = (uint64_t)((uint32_t)(stage * L::kStageBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // K-major: +32 B per K-step inside the 128-byte row; MN-major: +16 k-rows = 2 KB
-            const uint64_t da = A_MN ? make_smem_desc_mn(sa + k * 2048) : make_smem_desc(sa + k * kUmmaK * 2);
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
 #pragma unroll
-            for (int j = 0; j < N_SUB; ++j) {
-              const uint64_t db = B_MN ? make_smem_desc_mn(sb + j * (UMMA_N / 64) * 8192 + k * 2048)
-                                       : make_smem_desc(sb + j * UMMA_N * kBlockK * 2 + k * kUmmaK * 2);
-              umma_bf16(d_tmem + j * UMMA_N, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
-          }
-          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int j = 0; j < N_SUB; ++j)
+            umma_bf16_elect(d_tmem + j * UMMA_N, da0 + so + k * kAStep, db0 + so + j * kBSub + k * kBStep, idesc,
+                            (kb > kb0 || k > 0) ? 1u : 0u);
         }
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        umma_commit_elect(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+        if (kb == kb1 - 1) umma_commit_elect(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -369,134 +409,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane, smem + L::kEpiOffset, half, EW / 4);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-    }
-    epi.finish(quarter, lane);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
-}
-
-// ------------------------------------------------------------------------------- resident-A variant (short K)
-// The tensor pipe of the kernel above is fed from shared memory, and so is TMA's write port: per k-block a 128 x 256 tile
-// WRITES 48 KB (A 16 + B 32) and the four UMMAs READ the same 48 KB, 96 KB per 512 ideal tensor cycles = 192 B/clk against
-// the 128 B/clk an SM's shared memory moves — the measured 68 % tensor-pipe utilisation of the head's forward GEMM is that
-// ratio (profiles/r02_ncu_head_summary.md).  When K is short (the head: K = D = 512) a CTA can keep its 128 x K slice of A in
-// shared memory for its whole life (128 KB) and stream only B: writes drop to 32 KB per k-block (80 KB total, 160 B/clk),
-// and A is fetched from L2 once per CTA instead of once per tile.  A CTA owns ONE m-block (m = blockIdx.x mod m_blocks) and
-// walks the class tiles n = slot, slot + slots_m, ...; the CTAs of one slot work on the same B tile at the same time (L2).
-// K-major operands only; K <= 512; the epilogue concept is unchanged.
-template <int BLOCK_N, int STAGES, int EPI_BYTES, int K_BLOCKS>
-struct SmemLayoutARes {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;            // one k-block of the resident A slice
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kBOffset = K_BLOCKS * kABytes;
-  static constexpr int kEpiOffset = kBOffset + STAGES * kBBytes;
-  static constexpr int kBarOffset = kEpiOffset + EPI_BYTES;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;
-  static_assert(EPI_BYTES % 1024 == 0, "epilogue scratch must keep 1024-byte alignment");
-  static_assert(kTotal <= 232448, "exceeds 227 KB of shared memory");
-};
-
-template <int BLOCK_N, int ACC_STAGES, int STAGES, int K_BLOCKS, class Epi, int EW = 4>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
-gemm_ares_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmShape shape, const __grid_constant__ Epi epi) {
-  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N in {128,256}");
-  static_assert(BLOCK_N * ACC_STAGES <= kTmemCols, "accumulators exceed TMEM");
-  using L = SmemLayoutARes<BLOCK_N, STAGES, Epi::kSmemBytes, K_BLOCKS>;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
-  uint64_t* a_bar = tmem_empty + ACC_STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_k_blocks = (shape.K + kBlockK - 1) / kBlockK;       // <= K_BLOCKS (checked by the launcher)
-  // this CTA's m-block and its walk over the class tiles
-  const int m_blk = (int)blockIdx.x % shape.m_blocks;
-  const int slot = (int)blockIdx.x / shape.m_blocks;
-  const int slots = ((int)gridDim.x - m_blk + shape.m_blocks - 1) / shape.m_blocks;     // CTAs that share this m-block
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EW); }
-    mbar_init(a_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer: A once, then B tiles =====================
-      mbar_expect_tx(a_bar, (uint32_t)(total_k_blocks * L::kABytes));
-      for (int kb = 0; kb < total_k_blocks; ++kb) tma_load_2d(smem + kb * L::kABytes, &map_a, a_bar, kb * kBlockK, m_blk * kBlockM);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int n_blk = slot; n_blk < shape.n_blocks; n_blk += slots) {
-        for (int kb = 0; kb < total_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sb = smem + L::kBOffset + stage * L::kBBytes;
-          mbar_expect_tx(&full_bar[stage], L::kBBytes);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, false, false);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      mbar_wait(a_bar, 0);
-      tc_fence_after();
-      for (int n_blk = slot; n_blk < shape.n_blocks; n_blk += slots) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < total_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + kb * L::kABytes);
-          const uint32_t sb = smem_u32(smem + L::kBOffset + stage * L::kBBytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16(d_tmem, make_smem_desc(sa + k * kUmmaK * 2), make_smem_desc(sb + k * kUmmaK * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (kb == total_k_blocks - 1) umma_commit(&tmem_full[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    // ===================== epilogue warps =====================
-    const int quarter = warp & 3;
-    const int half = (warp - kEpiWarp0) >> 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int n_blk = slot; n_blk < shape.n_blocks; n_blk += slots) {
-      epi.prefetch(m_blk, n_blk, quarter, lane, smem + L::kEpiOffset);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, 0, quarter, lane, smem + L::kEpiOffset, half, EW / 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -672,9 +584,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      // ===================== MMA issuer (rank 0 only) =====================
+    if (rank == 0) {
+      // ===================== MMA issuer (rank 0 only; whole warp converged, one elected lane issues) =================
       constexpr uint32_t idesc = make_idesc(2 * kBlockM, BLOCK_N, A_MN, B_MN);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t da0 = A_MN ? make_smem_desc_mn(smem_base) : make_smem_desc(smem_base);
+      const uint64_t db0 = B_MN ? make_smem_desc_mn(smem_base + L::kABytes) : make_smem_desc(smem_base + L::kABytes);
+      constexpr uint32_t kAStep = (A_MN ? 2048 : kUmmaK * 2) >> 4;
+      constexpr uint32_t kBStep = (B_MN ? 2048 : kUmmaK * 2) >> 4;
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int u = first_unit; u < num_units; u += unit_step) {
@@ -688,16 +605,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
+          const uint64_t so = (uint64_t)((uint32_t)(stage * L::kStageBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc_mn(sa + k * 2048) : make_smem_desc(sa + k * kUmmaK * 2);
-            const uint64_t db = B_MN ? make_smem_desc_mn(sb + k * 2048) : make_smem_desc(sb + k * kUmmaK * 2);
-            umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit_pair(&empty_bar[stage]);
-          if (kb == kb1 - 1) umma_commit_pair(&tmem_full[acc]);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16_pair_elect(d_tmem, da0 + so + k * kAStep, db0 + so + k * kBStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit_pair_elect(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit_pair_elect(&tmem_full[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -764,30 +677,6 @@ int launch_gemm(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, 
   int grid = num_sms();
   if (units < grid) grid = units;
   if (grid < 1) grid = 1;
-  MSML_PROF2(name, 2.0 * shape.M * shape.N * shape.K, min_bytes, st);
-  kern<<<grid, 64 + 32 * EW, L::kTotal, st>>>(ma, mb, shape, epi);
-  MSML_LAUNCH_CHECK();
-  return 0;
-}
-
-// resident-A launcher: requires K <= 64 * K_BLOCKS, K-major operands, m_blocks <= SM count
-template <int BLOCK_N, int ACC_STAGES, int STAGES, int K_BLOCKS, int EW = 4, class Epi>
-int launch_gemm_ares(const char* name, const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& shape, const Epi& epi,
-                     cudaStream_t st, double min_bytes = 0.0) {
-  using L = SmemLayoutARes<BLOCK_N, STAGES, Epi::kSmemBytes, K_BLOCKS>;
-  auto kern = gemm_ares_kernel<BLOCK_N, ACC_STAGES, STAGES, K_BLOCKS, Epi, EW>;
-  MSML_REQUIRE(shape.K <= K_BLOCKS * kBlockK && shape.k_splits == 1 && shape.m_blocks <= num_sms(), MSML_EUNSUPPORTED,
-               "resident-A GEMM: K=%d m_blocks=%d out of range", shape.K, shape.m_blocks);
-  static thread_local bool configured = false;   // per template instantiation
-  if (!configured) {
-    MSML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
-  // as many CTAs per m-block as fit (every m-block gets the same number, so that the walk lengths differ by at most one tile)
-  int per_m = num_sms() / shape.m_blocks;
-  if (per_m > shape.n_blocks) per_m = shape.n_blocks;
-  if (per_m < 1) per_m = 1;
-  const int grid = per_m * shape.m_blocks;
   MSML_PROF2(name, 2.0 * shape.M * shape.N * shape.K, min_bytes, st);
   kern<<<grid, 64 + 32 * EW, L::kTotal, st>>>(ma, mb, shape, epi);
   MSML_LAUNCH_CHECK();
