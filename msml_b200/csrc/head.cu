@@ -270,18 +270,35 @@ struct EpiBwdDcos {
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v[j] = (col0 + j < n_s) ? v[j] : 0.f; pr[j] = (col0 + j < n_s) ? pr[j] : 0.f; }
           }
-          // column sums over the 32 rows of this warp by recursive halving (31 shuffles), then one red per lane
+          // column sums over the 32 rows of this warp, then one red per lane.  The products are packed to bf16x2 first
+          // (rdot = <Wn, dWn> is the projection term of the normalise backward; bf16 products leave it exact to ~2e-3, a
+          // fifth of the tolerance of the bf16 dcos it corrects), so the recursive halving moves 16 packed values: 16 shuffles
+          // + 16 HADD2.BF16 + 30 selects instead of 31 + 31 + 62 on fp32 — the epilogue, not the MMAs, bounds this kernel.
+          uint32_t q2[16];
 #pragma unroll
-          for (int sft = 16; sft >= 1; sft >>= 1) {
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat162 t = __floats2bfloat162_rn(pr[2 * i], pr[2 * i + 1]);
+            q2[i] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+#pragma unroll
+          for (int n = 8; n >= 1; n >>= 1) {
+            const int sft = 2 * n;
             const bool up = (lane & sft) != 0;
 #pragma unroll
-            for (int i = 0; i < sft; ++i) {
-              const float send = up ? pr[i] : pr[i + sft];
-              const float keep = up ? pr[i + sft] : pr[i];
-              pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+            for (int i = 0; i < n; ++i) {
+              const uint32_t send = up ? q2[i] : q2[i + n];
+              const uint32_t keep = up ? q2[i + n] : q2[i];
+              const uint32_t got = __shfl_xor_sync(0xffffffffu, send, sft);
+              const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&keep), *reinterpret_cast<const __nv_bfloat162*>(&got));
+              q2[i] = *reinterpret_cast<const uint32_t*>(&r);
             }
           }
-          if (col0 + lane < n_s) atomicAdd(rdot + col0 + lane, pr[0]);
+          {   // lanes 2p and 2p+1 hold the same column pair (2p, 2p+1), summed over complementary halves of the warp
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, q2[0], 1);
+            const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&q2[0]), *reinterpret_cast<const __nv_bfloat162*>(&got));
+            const float colsum = (lane & 1) ? __high2float(r) : __low2float(r);
+            if (col0 + lane < n_s) atomicAdd(rdot + col0 + lane, colsum);
+          }
           // bf16 pack: 32 values = 64 bytes = 4 x uint4 -> half `h` of the 128-byte staging row
 #pragma unroll
           for (int q = 0; q < 4; ++q) packed[h * 4 + q] = Vec<__nv_bfloat16>::pack(v + q * 8);
