@@ -659,7 +659,8 @@ def run_infer(args, rank, local_rank, world):
     import numpy as np
     import torch
     from msml_b200.backbones import MSML
-    from msml_b200.eval import extract_embeddings, random_block_occlusion
+    from msml_b200.datasets.augment.rand_occ import random_block_batch
+    from msml_b200.eval import extract_embeddings
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = True
@@ -668,9 +669,11 @@ def run_infer(args, rank, local_rank, world):
     net = net.to(memory_format=torch.channels_last).eval()
     bs = 1024
     n = bs * max(1, min(args.steps, 12))                    # LFW: 12,000 images
-    g = torch.Generator(device=dev).manual_seed(1)
-    imgs = torch.randint(0, 256, (n, 3, 112, 112), dtype=torch.uint8, device=dev, generator=g)
-    imgs = random_block_occlusion(imgs, 40, 41, generator=g).cpu().pin_memory()     # RandomBlock(40, 41, 'black')
+    # LFW-shape synthetic set, occluded on the host exactly as ref eval/qeval_mxnet.py:528-547 does: RandomBlock(40, 41, 'black')
+    # (msml_b200.datasets.augment mirrors ref datasets/augment/rand_occ.py:25-72 pixel for pixel for a given numpy seed)
+    np.random.seed(1)
+    imgs = np.random.randint(0, 256, (n, 3, 112, 112), dtype=np.uint8)
+    imgs = torch.from_numpy(random_block_batch(imgs, 40, 41, 'black')).pin_memory()
     for _ in range(max(args.warmup, 3)):
         extract_embeddings([imgs[:bs]], net, bs)
     torch.cuda.synchronize()
@@ -684,7 +687,7 @@ def run_infer(args, rank, local_rank, world):
     return {"metric": "occluded verification embedding extraction imgs/s (BASELINE config 5)", "value": round(n / (ms * 1e-3), 1),
             "unit": "imgs/s", "n_gpus": 1, "steps": n // bs, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / (n // bs), 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ires50_msml eval, %d uint8 112x112 images with a 40x40 black block, batch 1024, f(x)+f(flip x), "
+            "config": {"workload": "ires50_msml eval, %d uint8 112x112 images, RandomBlock(40, 41, 'black') (40 %% of the area, ref rand_occ.py:25-72), batch 1024, f(x)+f(flip x), "
                                    "host-fed (pinned uint8) and embeddings read back: end to end" % n}}
 
 

@@ -106,14 +106,17 @@ def test(data_set, backbone, batch_size, nfolds=10, is_gray=False):
 
 
 def random_block_occlusion(images, lo, hi, generator=None):
-    """Synthetic stand-in for ref datasets/augment/rand_occ.py:36-72 RandomBlock(lo, hi, 'black') on a uint8 device
-    batch: one black square per image, side uniform in [lo, hi), position uniform inside the frame.  Used by bench.py to
-    shape the config-5 workload; the reference's own augment class (PIL, host) is data preparation, not the hot path."""
+    """Device twin of ref datasets/augment/rand_occ.py:36-72 RandomBlock(lo, hi, 'black') for a uint8 batch that already
+    lives on the GPU: one black square per image whose AREA is ratio % of the frame, ratio uniform in [lo, hi) (integer
+    percent), side = int(sqrt(ratio) * W), position uniform over the placements that keep it inside (ref :45-71).  It draws
+    from a torch generator, so it is statistically, not bitwise, the reference's transform; the bit-exact host version is
+    msml_b200.datasets.augment.random_block_batch (what bench.py's config-5 workload uses)."""
     n, _, h, w = images.shape
     dev = images.device
-    side = torch.randint(lo, max(hi, lo + 1), (n,), device=dev, generator=generator)
-    top = (torch.rand(n, device=dev, generator=generator) * (h - side).clamp(min=1)).long()
-    left = (torch.rand(n, device=dev, generator=generator) * (w - side).clamp(min=1)).long()
+    ratio = torch.randint(lo, max(hi, lo + 1), (n,), device=dev, generator=generator).double() * 0.01
+    side = torch.floor(torch.sqrt(ratio * w * w)).long()
+    left = (torch.rand(n, device=dev, generator=generator) * (w - side + 1)).long().clamp(max=w - 1)
+    top = (torch.rand(n, device=dev, generator=generator) * (w - side + 1)).long().clamp(max=h - 1)
     ys = torch.arange(h, device=dev)[None, :, None]
     xs = torch.arange(w, device=dev)[None, None, :]
     inside = ((ys >= top[:, None, None]) & (ys < (top + side)[:, None, None]) &

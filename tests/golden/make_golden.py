@@ -421,6 +421,31 @@ def gen_model():
              **gn)
 
 
+def gen_rand_occ():
+    """ref datasets/augment/rand_occ.py:25-72 RandomBlock on deterministic RGB images, numpy seeded as ref train.py:36.
+    The module is loaded by path (the venv's HuggingFace `datasets` shadows the reference's namespace package) with a stub
+    for its `eval.preprocess.RealOcc.image_infer` import (unused by RandomBlock) — harness-only, SURVEY 8c."""
+    import importlib.util
+    from PIL import Image
+    stub = types.ModuleType("eval.preprocess.RealOcc.image_infer")
+    stub.RealOcc = object
+    for name in ("eval", "eval.preprocess", "eval.preprocess.RealOcc"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["eval.preprocess.RealOcc.image_infer"] = stub
+    spec = importlib.util.spec_from_file_location("ref_rand_occ", os.path.join(REF, "datasets", "augment", "rand_occ.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.RandomState(7)
+    imgs = rng.randint(0, 256, (6, 112, 112, 3)).astype(np.uint8)
+    out = {"imgs": imgs}
+    for fill, lo, hi in (("black", 40, 41), ("white", 10, 31), ("gauss", 20, 61), ("black", 0, 1), ("black", 90, 91)):
+        np.random.seed(1)
+        t = mod.RandomBlock(lo, hi, fill)
+        res = np.stack([np.asarray(t(Image.fromarray(im))) for im in imgs])
+        out["%s_%d_%d" % (fill, lo, hi)] = res
+    save("rand_occ", **out)
+
+
 def gen_model_peer():
     """MSML with the peer-guided branch on (ref config.yaml:22-26 default: use_ori / use_conv / mask_trans conv): the frozen
     teacher of ref backbones/peer/arcface.py with RANDOM deterministic weights (the reference ships none: its
@@ -458,7 +483,7 @@ def gen_model_peer():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fm", "fm_peer", "dap", "margins", "pfc", "model", "model_peer", "consensus"]
+    which = sys.argv[1:] or ["fm", "fm_peer", "dap", "margins", "pfc", "model", "model_peer", "consensus", "rand_occ"]
     seeds()
     for w in which:
         globals()["gen_" + w]()

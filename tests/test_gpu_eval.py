@@ -61,7 +61,10 @@ def test_extract_embeddings_bf16_and_masks():
     g = torch.Generator(device="cuda").manual_seed(7)
     imgs = torch.randint(0, 256, (8, 3, 112, 112), generator=g, dtype=torch.uint8, device="cuda")
     occ = random_block_occlusion(imgs, 40, 41, generator=g)
-    assert occ.dtype == torch.uint8 and (occ == 0).sum() >= 8 * 3 * 40 * 40       # one 40x40 black block per image
+    side = int((0.40 * 112 * 112) ** 0.5)                                          # 40 % of the AREA (ref rand_occ.py:45-50): 70 x 70
+    assert occ.dtype == torch.uint8 and (occ == 0).sum() >= 8 * 3 * side * side
+    black = (occ == 0).all(dim=1)                                                  # the block is inside the frame and square
+    assert all(int(b.any(1).sum()) >= side and int(b.any(0).sum()) >= side for b in black)
     emb, _lists, masks = extract_embeddings([occ], net, batch_size=8, return_masks=True)
     want, _ = _oracle_embeddings(net, occ.cpu())
     cos = (emb * want).sum(1)

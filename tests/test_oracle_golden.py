@@ -193,3 +193,25 @@ def test_consensus_loss_gradient_is_the_derivative():
             num[i] = (consensus.consensus_loss(zp, blobs_c, target_c, *cfg, want_grad=False)[0]
                       - consensus.consensus_loss(zm, blobs_c, target_c, *cfg, want_grad=False)[0]) / (2 * eps)
         close(dz, num, 1e-5, 1e-8)
+
+
+@pytest.mark.parametrize("fill,lo,hi", [("black", 40, 41), ("white", 10, 31), ("gauss", 20, 61), ("black", 0, 1), ("black", 90, 91)])
+def test_random_block_matches_reference(fill, lo, hi):
+    """msml_b200.datasets.augment.RandomBlock (and its batched twin) against the reference's RandomBlock
+    (ref datasets/augment/rand_occ.py:25-72) run on the same images with the same numpy seed: pixel for pixel."""
+    from PIL import Image
+    from msml_b200.datasets.augment import RandomBlock
+    from msml_b200.datasets.augment.rand_occ import random_block_batch
+    g = load_golden("rand_occ")
+    want = g["%s_%d_%d" % (fill, lo, hi)]
+    np.random.seed(1)
+    t = RandomBlock(lo, hi, fill)
+    got = np.stack([np.asarray(t(Image.fromarray(im))) for im in g["imgs"]])
+    assert np.array_equal(got, want)
+    np.random.seed(1)
+    got_b = random_block_batch(np.ascontiguousarray(g["imgs"].transpose(0, 3, 1, 2)), lo, hi, fill)
+    assert np.array_equal(got_b.transpose(0, 2, 3, 1), want)
+    if lo > 0:
+        assert (got != g["imgs"]).any()
+    else:
+        assert np.array_equal(got, g["imgs"])
