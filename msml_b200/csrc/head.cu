@@ -351,7 +351,7 @@ struct EpiDwNormBwd {
   const __nv_bfloat16* wn;     // (n_s, D)
   const float* inv_norm;       // (n_s)
   const float* rdot;           // (n_s)
-  int n_s, D;
+  int n_s, D, block_n;         // block_n: D columns per tile (128 or 256)
   __device__ void finish(int, int lane) const { StageOut::drain(lane); }
   // warp-cooperative async load of Wn[row0 .. row0+32, col0 .. col0+64) into a swizzled 4 KB box
   __device__ __forceinline__ void load_wn_box(uint8_t* box, int row0, int col0, int lane) const {
@@ -365,14 +365,14 @@ struct EpiDwNormBwd {
   }
   __device__ void prefetch(int m_blk, int n_blk, int quarter, int lane, uint8_t* scratch) const {
     uint8_t* wwn = scratch + 4 * StageOut::kBytesPerWarp + quarter * kWnBytesPerWarp;
-    const int row0 = m_blk * kBlockM + quarter * 32, dcol0 = n_blk * 256;
+    const int row0 = m_blk * kBlockM + quarter * 32, dcol0 = n_blk * block_n;
     load_wn_box(wwn, row0, dcol0, lane);
     if (D - dcol0 > 64) load_wn_box(wwn + 4096, row0, dcol0 + 64, lane);
   }
   __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int, int) const {
     const int row0 = m_blk * kBlockM + quarter * 32;
     const int row = row0 + lane;                     // class index (4 epilogue warps: each owns all 256 columns)
-    const int dcol0 = n_blk * 256;                   // this tile covers D columns [dcol0, dcol0 + 256)
+    const int dcol0 = n_blk * block_n;               // this tile covers D columns [dcol0, dcol0 + block_n)
     const bool ok = row < n_s;
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
     uint8_t* wout = scratch + quarter * StageOut::kBytesPerWarp;
@@ -380,7 +380,7 @@ struct EpiDwNormBwd {
     const float inv = ok ? inv_norm[row] : 0.f;
     const float cdot = ok ? rdot[row] * inv : 0.f;   // (acc - w*rdot)*inv = acc*inv - w*cdot
     int n_boxes = (D - dcol0) / 64;
-    if (n_boxes > 4) n_boxes = 4;
+    if (n_boxes > block_n / 64) n_boxes = block_n / 64;
     float buf[2][32];
     tmem_ld32_issue(taddr, buf[0]);                  // boxes 0 and 1 of Wn are already in flight (prefetch())
     tmem_ld_wait(buf[0]);
@@ -746,6 +746,9 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
     if (int e = encode_tmap_2d(&epi.map_dw, dw, 4, D, n_s, D, 32, 32)) return e;
     epi.wn = static_cast<const __nv_bfloat16*>(wn); epi.inv_norm = inv_norm; epi.rdot = h.rdot; epi.n_s = (int)n_s; epi.D = (int)D;
     const double min_bytes = 4.0 * (double)n_s * D + 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 2.0 * (double)B_tot * D;
+    // (128-column tiles with a 5-deep ring, to keep more dcos loads in flight, measured slower: 161.6 vs 144.7 us at
+    //  config-4 shapes, gpurun_out/r02k_head_125k_dw{128,256}.json)
+    epi.block_n = 256;
     GemmShape sh = make_shape(n_s, D, B_tot, 256, 1, /*n_fastest=*/true);
     sh.a_blk_pitch = (int)h.blk_pitch;
     if (blocked) { if (int e = launch_gemm<256, 2, 3, true, true, 4, true>("head_bwd_dw_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
