@@ -91,7 +91,7 @@ __device__ __forceinline__ void put32(float* v, int idx, float x) {
 
 struct NoScratch {
   static constexpr int kSmemBytes = 0;
-  __device__ void prefetch(int, int, int, int, uint8_t*) const {}
+  __device__ void prefetch(int, int, int, int, uint8_t*, int, int) const {}
   __device__ void finish(int, int) const {}
 };
 
@@ -218,7 +218,7 @@ struct EpiBwdDcos {
   float* rdot;         // [n_s] zero-initialised; <Wn[n], dWn[n]> for the normalise backward
   float smooth_on, smooth_off, inv_btot;
   int blk_pitch;       // > 0: dcos is tile-blocked [n_s/64][blk_pitch rows][64] (tc_gemm.cuh); 0: row-major (B_tot x ld)
-  __device__ void prefetch(int, int, int, int, uint8_t*) const {}
+  __device__ void prefetch(int, int, int, int, uint8_t*, int, int) const {}
   __device__ void finish(int, int lane) const { StageOut::drain(lane); }
   __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int half, int nh) const {
     const int row0 = m_blk * kBlockM + quarter * 32;
@@ -344,14 +344,15 @@ struct EpiDxAccum : NoScratch {
 // backward pass 3: dW = (dWn - Wn * rdot) * inv_norm      (ref :115 normalize backward), one pass.
 // Wn tile rows arrive through cp.async (coalesced 128-byte rows -> swizzled smem, 2 boxes in flight; the first two are
 // requested before the tile's MMAs have finished), dW leaves through TMA stores.  rdot = <Wn, dWn> comes from pass 1.
-struct EpiDwNormBwd {
+template <int NW>               // epilogue warps: 4 (each owns all 256 columns of its rows) or 8 (two per TMEM lane quarter, 128 columns each)
+struct EpiDwNormBwdT {
   static constexpr int kWnBytesPerWarp = 2 * 4096;                  // 2 boxes of 32 rows x 64 bf16
-  static constexpr int kSmemBytes = 4 * (StageOut::kBytesPerWarp + kWnBytesPerWarp);   // 64 KB
+  static constexpr int kSmemBytes = NW * (StageOut::kBytesPerWarp + kWnBytesPerWarp);   // 64 / 128 KB
   CUtensorMap map_dw;          // fp32 (n_s x D), boxes 32 cols x 32 rows
   const __nv_bfloat16* wn;     // (n_s, D)
   const float* inv_norm;       // (n_s)
   const float* rdot;           // (n_s)
-  int n_s, D, block_n;         // block_n: D columns per tile (128 or 256)
+  int n_s, D, block_n;         // block_n: D columns per tile
   __device__ void finish(int, int lane) const { StageOut::drain(lane); }
   // warp-cooperative async load of Wn[row0 .. row0+32, col0 .. col0+64) into a swizzled 4 KB box
   __device__ __forceinline__ void load_wn_box(uint8_t* box, int row0, int col0, int lane) const {
@@ -363,24 +364,26 @@ struct EpiDwNormBwd {
     }
     cp_async_commit();
   }
-  __device__ void prefetch(int m_blk, int n_blk, int quarter, int lane, uint8_t* scratch) const {
-    uint8_t* wwn = scratch + 4 * StageOut::kBytesPerWarp + quarter * kWnBytesPerWarp;
-    const int row0 = m_blk * kBlockM + quarter * 32, dcol0 = n_blk * block_n;
-    load_wn_box(wwn, row0, dcol0, lane);
+  __device__ void prefetch(int m_blk, int n_blk, int quarter, int lane, uint8_t* scratch, int half, int nh) const {
+    uint8_t* wwn = scratch + NW * StageOut::kBytesPerWarp + (half * 4 + quarter) * kWnBytesPerWarp;
+    const int row0 = m_blk * kBlockM + quarter * 32, dcol0 = n_blk * block_n + half * (block_n / nh);
+    if (dcol0 < D) load_wn_box(wwn, row0, dcol0, lane);
     if (D - dcol0 > 64) load_wn_box(wwn + 4096, row0, dcol0 + 64, lane);
   }
-  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int, int) const {
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int half, int nh) const {
     const int row0 = m_blk * kBlockM + quarter * 32;
-    const int row = row0 + lane;                     // class index (4 epilogue warps: each owns all 256 columns)
-    const int dcol0 = n_blk * block_n;               // this tile covers D columns [dcol0, dcol0 + block_n)
+    const int row = row0 + lane;                     // class index
+    const int cols = block_n / nh;                   // columns this warp owns
+    const int dcol0 = n_blk * block_n + half * cols; // ... [dcol0, dcol0 + cols) of D
     const bool ok = row < n_s;
-    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* wout = scratch + quarter * StageOut::kBytesPerWarp;
-    uint8_t* wwn = scratch + 4 * StageOut::kBytesPerWarp + quarter * kWnBytesPerWarp;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + half * cols;
+    uint8_t* wout = scratch + (half * 4 + quarter) * StageOut::kBytesPerWarp;
+    uint8_t* wwn = scratch + NW * StageOut::kBytesPerWarp + (half * 4 + quarter) * kWnBytesPerWarp;
     const float inv = ok ? inv_norm[row] : 0.f;
     const float cdot = ok ? rdot[row] * inv : 0.f;   // (acc - w*rdot)*inv = acc*inv - w*cdot
     int n_boxes = (D - dcol0) / 64;
-    if (n_boxes > block_n / 64) n_boxes = block_n / 64;
+    if (n_boxes > cols / 64) n_boxes = cols / 64;
+    if (n_boxes <= 0) return;
     float buf[2][32];
     tmem_ld32_issue(taddr, buf[0]);                  // boxes 0 and 1 of Wn are already in flight (prefetch())
     tmem_ld_wait(buf[0]);
@@ -742,7 +745,25 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
       if (int e = encode_tmap_bf16_mnmajor(&ma, h.dcos, n_s, B_tot, h.ld_dc)) return e;
     }
     if (int e = encode_tmap_bf16_mnmajor(&mb, x, D, B_tot, D)) return e;
-    EpiDwNormBwd epi;
+    // Two shapes of this kernel.  Short K (B_tot <= 128: the 1-GPU training step, 2 k-blocks per tile): the epilogue is
+    // everything, so eight epilogue warps (two per TMEM lane quarter) and a 2-stage operand ring (93,431 classes: 65.9 ->
+    // 53.9 us).  Long K (B_tot = 1024: 16 k-blocks per tile): four warps and three stages — the 2-stage ring starves the
+    // MMAs there (188.7 vs 145.6 us at config-4 shapes; gpurun_out/r02l_head_*.json).  MSML_HEAD_DW_EW=4|8 forces one.
+    static int dw_ew = -1;
+    if (dw_ew < 0) { const char* e = getenv("MSML_HEAD_DW_EW"); dw_ew = e ? atoi(e) : 0; }
+    const double min_bytes_dw = 4.0 * (double)n_s * D + 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 2.0 * (double)B_tot * D;
+    const bool wide_epilogue = dw_ew == 8 || (dw_ew != 4 && B_tot <= 2 * kBlockK);
+    if (blocked && wide_epilogue) {
+      EpiDwNormBwdT<8> epi8;
+      if (int e = encode_tmap_2d(&epi8.map_dw, dw, 4, D, n_s, D, 32, 32)) return e;
+      epi8.wn = static_cast<const __nv_bfloat16*>(wn); epi8.inv_norm = inv_norm; epi8.rdot = h.rdot; epi8.n_s = (int)n_s; epi8.D = (int)D;
+      epi8.block_n = 256;
+      GemmShape sh8 = make_shape(n_s, D, B_tot, 256, 1, /*n_fastest=*/true);
+      sh8.a_blk_pitch = (int)h.blk_pitch;
+      if (int e = launch_gemm<256, 2, 2, true, true, 8, true>("head_bwd_dw_gemm", ma, mb, sh8, epi8, st, min_bytes_dw)) return e;
+      return 0;
+    }
+    EpiDwNormBwdT<4> epi;
     if (int e = encode_tmap_2d(&epi.map_dw, dw, 4, D, n_s, D, 32, 32)) return e;
     epi.wn = static_cast<const __nv_bfloat16*>(wn); epi.inv_norm = inv_norm; epi.rdot = h.rdot; epi.n_s = (int)n_s; epi.D = (int)D;
     const double min_bytes = 4.0 * (double)n_s * D + 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 2.0 * (double)B_tot * D;

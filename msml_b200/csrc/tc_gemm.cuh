@@ -272,7 +272,7 @@ struct SmemLayout {
 //     static constexpr int kSmemBytes;     // per-CTA scratch (multiple of 1024), split by the callee per warp
 //     __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int k_split,
 //                                int quarter, int lane, uint8_t* scratch, int half, int n_halves) const;
-//     __device__ void prefetch(int m_blk, int n_blk, int quarter, int lane, uint8_t* scratch) const;  // before the tile's
+//     __device__ void prefetch(int m_blk, int n_blk, int quarter, int lane, uint8_t* scratch, int half, int n_halves) const;  // before the tile's
 //                                                             // accumulator is complete (may be a no-op)
 //     __device__ void finish(int quarter, int lane) const;   // once per warp after the last tile
 //   };
@@ -405,7 +405,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int m_blk = shape.n_fastest ? mn / shape.n_blocks : mn % shape.m_blocks;
       const int n_blk = shape.n_fastest ? mn % shape.n_blocks : mn / shape.m_blocks;
       const int ks = u / (shape.m_blocks * shape.n_blocks);
-      epi.prefetch(m_blk, n_blk, quarter, lane, smem + L::kEpiOffset);   // operand fetches that need not wait for the MMAs
+      epi.prefetch(m_blk, n_blk, quarter, lane, smem + L::kEpiOffset, half, EW / 4);   // operand fetches that need not wait for the MMAs
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane, smem + L::kEpiOffset, half, EW / 4);
@@ -629,7 +629,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int m_blk = pair * 2 + (int)rank;
       const int ks = u / (m_pairs * shape.n_blocks);
       const bool live = m_blk < shape.m_blocks;          // odd number of 128-row blocks: the last pair's second half is empty
-      if (live) epi.prefetch(m_blk, n_blk, quarter, lane, smem + L::kEpiOffset);
+      if (live) epi.prefetch(m_blk, n_blk, quarter, lane, smem + L::kEpiOffset, half, EW / 4);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (live) epi(tmem_base + acc * BLOCK_N, m_blk, n_blk, ks, quarter, lane, smem + L::kEpiOffset, half, EW / 4);
