@@ -238,29 +238,37 @@ def fusion_microbench(iters=20, batch=512):
                                 "source": ncu_traffic("fm_gate_fwd", "@config2")[1]} if batch == 512 else None)
 
 
-def head_microbench(iters=5, b_tot=1024, n_s=125000):
+def head_microbench(iters=5, b_tot=1024, n_s=125000, fused_projection=False):
     """BASELINE config 4 per-rank shapes on ONE GPU: the 8-GPU run gathers B_tot = 8 x 128 = 1024 embeddings against a
     125,000-class shard per rank (1M classes / 8); the head kernels see exactly these GEMM shapes, only the collectives
     are absent.  Every launch is bracketed by CUDA events (msml_profile_*); tensor-bound kernels are quoted against the
-    measured cuBLAS bf16 burst peak."""
+    measured cuBLAS bf16 burst peak.  fused_projection=False: forward_backward alone, sub_weight.grad is the exact gradient.
+    fused_projection=True: the step as bench.py trains it — forward_backward + headers.PartialFCSGD(fuse_projection=True),
+    where the backward of normalize(sub_weight) moves from the dcos / dW epilogues into the optimizer kernel (whose time is
+    reported beside the GEMMs, not hidden)."""
     import torch
     from msml_b200 import _lib
-    from msml_b200.headers import ArcFace, PartialFC
+    from msml_b200.headers import ArcFace, PartialFC, PartialFCSGD
     lib = _lib.load()
     pk = peaks()
     torch.manual_seed(1)
     pfc = PartialFC(0, torch.cuda.current_device(), 1, b_tot, False, ArcFace(S, M), n_s, sample_rate=1.0, embedding_size=512)
+    opt = PartialFCSGD(pfc, lr=0.1, momentum=0.9, weight_decay=5e-4, fuse_projection=True) if fused_projection else None
     g = torch.Generator(device="cuda").manual_seed(1)
     feat = torch.nn.functional.normalize(torch.randn(b_tot, 512, device="cuda", generator=g))
     label = torch.randint(0, n_s, (b_tot,), device="cuda", generator=g)
-    for _ in range(3):
-        pfc.forward_backward(label, feat, None)
+
+    def one():
+        pfc.forward_backward(label, feat, opt)
+        if opt is not None:
+            opt.step()
         pfc.sub_weight.grad = None
+    for _ in range(3):
+        one()
     torch.cuda.synchronize()
     lib.msml_profile_enable(1)
     for _ in range(iters):
-        pfc.forward_backward(label, feat, None)
-        pfc.sub_weight.grad = None
+        one()
     torch.cuda.synchronize()
     lib.msml_profile_enable(0)
     prof = collect_profile(lib)
@@ -269,7 +277,8 @@ def head_microbench(iters=5, b_tot=1024, n_s=125000):
     gemm_ms = sum(v["total_ms"] for k, v in prof.items() if k.endswith("_gemm")) / iters
     del pfc
     torch.cuda.empty_cache()
-    return dict(b_tot=b_tot, n_s=n_s, algorithmic_flops=6.0 * b_tot * n_s * 512,
+    return dict(b_tot=b_tot, n_s=n_s, algorithmic_flops=6.0 * b_tot * n_s * 512, fused_projection=fused_projection,
+                gemm_us=round(gemm_ms * 1e3, 2),
                 tflops_over_gemm_time=round(6.0 * b_tot * n_s * 512 / (gemm_ms * 1e-3) / 1e12, 1),
                 frac_of_bf16_burst_peak=round(6.0 * b_tot * n_s * 512 / (gemm_ms * 1e-3) / 1e12 / pk["tf_burst"], 4), rooflines=rl)
 
@@ -452,7 +461,7 @@ def run_train(args, rank, local_rank, world):
     # the head's optimizer (ref train.py:188-191: SGD over module_partial_fc.parameters(), momentum 0.9, wd 5e-4) as ONE
     # kernel on the shard rows that also emits the next step's normalised bf16 centres
     opt_pfc = (torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True) if args.stock_head_sgd
-               else PartialFCSGD(pfc, lr=lr, momentum=0.9, weight_decay=5e-4, emit_normalized=True))
+               else PartialFCSGD(pfc, lr=lr, momentum=0.9, weight_decay=5e-4, emit_normalized=True, fuse_projection=not args.exact_head_grad))
     step = TrainStep(net, pfc, opt, opt_pfc, (BATCH, 3, 112, 112), world_size=world, max_norm=5.0, use_graph=not args.eager)
     head_check = head_parity_check(pfc, rank, world, dev, BATCH, NUM_CLASSES)     # before anything trains the class centres
 
@@ -591,7 +600,8 @@ def run_head(args, rank, local_rank, world):
     sampled = int(args.sample_rate) != 1
     pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), args.classes, sample_rate=args.sample_rate, embedding_size=512)
     hp = dict(lr=0.1, momentum=0.9, weight_decay=5e-4)
-    opt = PartialFCSGD(pfc, **hp) if args.fused_sgd else torch.optim.SGD([{"params": pfc.parameters()}], **hp)
+    opt = (PartialFCSGD(pfc, fuse_projection=not args.exact_head_grad, **hp) if args.fused_sgd
+           else torch.optim.SGD([{"params": pfc.parameters()}], **hp))
     check = None
     if not sampled and not args.no_head_check:
         check = head_parity_check(pfc, rank, world, dev, BATCH, args.classes)
@@ -646,7 +656,7 @@ def run_head(args, rank, local_rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "PartialFC head only (forward_backward + SGD + update), %d classes, sample_rate %g, B=%d/GPU, %d rank(s) (BASELINE config 4)"
                                    % (args.classes, args.sample_rate, BATCH, world),
-                       "n_s_per_rank": n_s, "optimizer": "headers.PartialFCSGD (fused)" if args.fused_sgd else "torch.optim.SGD + update()"},
+                       "n_s_per_rank": n_s, "optimizer": ("headers.PartialFCSGD (fused%s)" % ("" if args.exact_head_grad else ", normalise-backward projection in the optimizer kernel")) if args.fused_sgd else "torch.optim.SGD + update()"},
             "head_algorithmic_tflops_over_gemm_time": round(flops / (gemm_ms * 1e-3) / 1e12, 2),
             "own_kernel_ms_per_step": round(own_ms, 4), "gemm_ms_per_step": round(gemm_ms, 4),
             "gpu_launches": int(ops.launch_count()), "head_check": check,
@@ -716,6 +726,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per step of the CPU arm (a bounded sample of the 128/GPU workload)")
     ap.add_argument("--stock-head-sgd", action="store_true", help="train workload: torch.optim.SGD(fused=True) + update() for the class centres "
                     "instead of headers.PartialFCSGD")
+    ap.add_argument("--exact-head-grad", action="store_true", help="with headers.PartialFCSGD: keep the normalise-backward projection in the "
+                    "GEMM epilogues (sub_weight.grad is the exact gradient) instead of fusing it into the optimizer kernel")
     ap.add_argument("--fused-sgd", action="store_true", help="head workload: headers.PartialFCSGD instead of torch.optim.SGD + update()")
     ap.add_argument("--no-head-check", action="store_true", help="skip the fp64-oracle loss check before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -781,6 +793,7 @@ def main():
     if rank == 0 and args.workload == "train":
         res["fusion_microbench"] = fusion_microbench()
         res["head_microbench"] = head_microbench()
+        res["head_microbench_fused_projection"] = head_microbench(fused_projection=True)
         if world == 1 and not args.no_cpu_baseline:
             cb = run_cpu(args.cpu_batch, 4, 1)
             res["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "head_share", "backbone_share")}

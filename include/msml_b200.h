@@ -123,6 +123,14 @@ int msml_pfc_sgd_update(float* weight, float* weight_mom, const float* dw, const
                         int64_t num_local, int64_t D, const float* lr_dev /*nullable*/, float lr, float momentum,
                         float weight_decay, float dampening, int nesterov, void* wn_bf16 /*nullable*/,
                         float* inv_norm /*nullable*/, void* stream);
+/* Same update from the RAW gradient dwn = dcos^T X of msml_head_bwd_raw / msml_head_step_raw: the backward of
+ * normalize(sub_weight) (ref partial_fc.py:115) is applied to the row in registers first,
+ *   n = max(||w||, 1e-12);  dw = dwn / n - w * <w, dwn> / n^3,
+ * with the fp32 master row (as the reference's autograd), then the update above. */
+int msml_pfc_sgd_update_raw(float* weight, float* weight_mom, const float* dwn, const int64_t* index /*nullable*/, int64_t n_s,
+                            int64_t num_local, int64_t D, const float* lr_dev /*nullable*/, float lr, float momentum,
+                            float weight_decay, float dampening, int nesterov, void* wn_bf16 /*nullable*/,
+                            float* inv_norm /*nullable*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K-N  fused BatchNorm (+ residual add) (+ PReLU) over an NHWC tensor viewed as (P = N*H*W, C):
@@ -240,6 +248,14 @@ int msml_head_bwd(const void* x_bf16, const void* wn_bf16, const float* inv_norm
                   const float* gstats, float* dx_full, float* dw,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Raw mode (pairs with msml_pfc_sgd_update_raw): same as msml_head_bwd but dwn (n_s, D) receives dWn = dcos^T X, the gradient
+ * with respect to the NORMALISED centres; the backward of `normalize(sub_weight)` (ref :115) is left to the fused optimizer,
+ * which applies it to the row it already holds.  Removes the <Wn, dWn> reduction from the dcos epilogue and the Wn stream
+ * from the dW epilogue. */
+int msml_head_bwd_raw(const void* x_bf16, const void* wn_bf16, const int64_t* tl, int64_t B_tot, int64_t n_s, int64_t D,
+                      const msml_margin_params* margin_host, const float* gstats, float* dx_full, float* dwn,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * The class-sharded step over NCCL, owned by the library.
  * ref headers/partial_fc.py:110,126,136,141,162,174 issues six collectives per step; here three, enqueued from C on
@@ -267,6 +283,11 @@ size_t msml_head_step_workspace(int64_t B, int64_t W, int64_t n_s, int64_t D);
 int msml_head_step(msml_comm* comm, const void* x_bf16, const void* wn_bf16, const float* inv_norm, const int64_t* tl,
                    int64_t B, int64_t n_s, int64_t D, const msml_margin_params* margin_host, float* x_grad, float* dw,
                    float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* msml_head_step in raw mode: dwn = dcos^T X (see msml_head_bwd_raw). */
+int msml_head_step_raw(msml_comm* comm, const void* x_bf16, const void* wn_bf16, const int64_t* tl, int64_t B, int64_t n_s,
+                       int64_t D, const msml_margin_params* margin_host, float* x_grad, float* dwn, float* loss,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* In-model full-FC margin heads (ref headers/margin_losses.py:275-303, 390-418) on a
  * materialised cosine matrix (B, C) fp32, in place:  fwd applies margin + scale, bwd multiplies

@@ -51,6 +51,8 @@ SIGNATURES = {
     "msml_bn_bwd": (c_int, [c_p] * 14 + [c_i64, c_i64, c_int, c_int, c_int, c_p, c_size, c_p]),
     "msml_pfc_sgd_update": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_float, c_int, c_p, c_p, c_p]),
+    "msml_pfc_sgd_update_raw": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                        ctypes.c_float, c_int, c_p, c_p, c_p]),
     "msml_accum_bf16_multi": (c_int, [c_int, c_p, c_p, c_p, c_p]),
     "msml_dap_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_p]),
     "msml_dap_bwd": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_p]),
@@ -78,6 +80,8 @@ SIGNATURES = {
     "msml_head_gather": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_size, c_p]),
     "msml_head_step_workspace": (c_size, [c_i64, c_i64, c_i64, c_i64]),
     "msml_head_step": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p, c_p, c_p, c_p, c_size, c_p]),
+    "msml_head_bwd_raw": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p, c_p, c_p, c_p, c_size, c_p]),
+    "msml_head_step_raw": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p, c_p, c_p, c_p, c_size, c_p]),
     "msml_margin_fwd": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p]),
     "msml_margin_bwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, ctypes.POINTER(MarginParams), c_p]),
     "msml_gemm_bf16": (c_int, [c_p, c_i64, c_int, c_p, c_i64, c_int, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),

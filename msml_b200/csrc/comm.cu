@@ -194,11 +194,11 @@ extern "C" size_t msml_head_step_workspace(int64_t B, int64_t W, int64_t n_s, in
   return off;
 }
 
-extern "C" int msml_head_step(msml_comm* comm, const void* x, const void* wn, const float* inv_norm, const int64_t* tl, int64_t B,
-                              int64_t n_s, int64_t D, const msml_margin_params* margin, float* x_grad, float* dw, float* loss,
-                              void* ws, size_t ws_bytes, void* stream) {
+static int head_step_impl(msml_comm* comm, const void* x, const void* wn, const float* inv_norm, const int64_t* tl, int64_t B,
+                          int64_t n_s, int64_t D, const msml_margin_params* margin, float* x_grad, float* dw, float* loss,
+                          void* ws, size_t ws_bytes, void* stream, bool raw) {
   const int64_t W = comm ? comm->world : 1, B_tot = B * W;
-  MSML_REQUIRE(x && wn && inv_norm && tl && x_grad && dw && loss && B > 0, MSML_EINVAL, "null pointer");
+  MSML_REQUIRE(x && wn && (raw || inv_norm) && tl && x_grad && dw && loss && B > 0, MSML_EINVAL, "null pointer");
   MSML_REQUIRE(ws && aligned16(ws) && ws_bytes >= msml_head_step_workspace(B, W, n_s, D), MSML_EWORKSPACE,
                "head step workspace missing, misaligned or too small (%zu < %zu)", ws_bytes, msml_head_step_workspace(B, W, n_s, D));
   cudaStream_t st = (cudaStream_t)stream;
@@ -216,11 +216,27 @@ extern "C" int msml_head_step(msml_comm* comm, const void* x, const void* wn, co
   // ONE all-gather of (max, sum-exp, target logit) per row replaces all_reduce(MAX), all_reduce(SUM) and the loss all_reduce
   if (W > 1) MSML_NCCL(nccl_api()->AllGather(stats, gathered, (size_t)3 * B_tot, kNcclFloat32, comm->nccl, st));
   if (int e = msml_head_merge_stats(W > 1 ? gathered : stats, W, B_tot, gstats, loss, stream)) return e;
-  if (int e = msml_head_bwd(x, wn, inv_norm, tl, B_tot, n_s, D, margin, gstats, W > 1 ? dx_full : x_grad, dw, head_ws, hw, stream)) return e;
+  if (raw) {
+    if (int e = msml_head_bwd_raw(x, wn, tl, B_tot, n_s, D, margin, gstats, W > 1 ? dx_full : x_grad, dw, head_ws, hw, stream)) return e;
+  } else {
+    if (int e = msml_head_bwd(x, wn, inv_norm, tl, B_tot, n_s, D, margin, gstats, W > 1 ? dx_full : x_grad, dw, head_ws, hw, stream)) return e;
+  }
   if (W > 1) {
     MSML_NCCL(nccl_api()->ReduceScatter(dx_full, x_grad, (size_t)B * D, kNcclFloat32, kNcclSum, comm->nccl, st));
     scale_kernel<<<(unsigned)((B * D + 255) / 256), 256, 0, st>>>(x_grad, B * D, (float)W);      // ref :175
     MSML_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int msml_head_step(msml_comm* comm, const void* x, const void* wn, const float* inv_norm, const int64_t* tl, int64_t B,
+                              int64_t n_s, int64_t D, const msml_margin_params* margin, float* x_grad, float* dw, float* loss,
+                              void* ws, size_t ws_bytes, void* stream) {
+  return head_step_impl(comm, x, wn, inv_norm, tl, B, n_s, D, margin, x_grad, dw, loss, ws, ws_bytes, stream, false);
+}
+
+extern "C" int msml_head_step_raw(msml_comm* comm, const void* x, const void* wn, const int64_t* tl, int64_t B, int64_t n_s,
+                                  int64_t D, const msml_margin_params* margin, float* x_grad, float* dwn, float* loss, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  return head_step_impl(comm, x, wn, nullptr, tl, B, n_s, D, margin, x_grad, dwn, loss, ws, ws_bytes, stream, true);
 }

@@ -207,7 +207,10 @@ struct StageOut {
 // for the normalise backward).  The inner loop is the bare softmax gradient (FFMA, EX2, FFMA, FMUL per element): the target
 // column is patched afterwards (rare, one element per row) and ragged tiles take a separate path, so that the epilogue of
 // a tile issues fewer instructions than its MMAs take cycles.
-struct EpiBwdDcos {
+// WITH_RDOT = false: the normalise-backward projection is applied by the fused optimizer (msml_pfc_sgd_update_raw), so the
+// <Wn, dWn> column reduction — a third of this epilogue's instructions — is not needed
+template <bool WITH_RDOT>
+struct EpiBwdDcosT {
   static constexpr int kSmemBytes = 8 * StageOut::kBytesPerWarp;   // 64 KB (up to 8 epilogue warps)
   CUtensorMap map_dcos;        // bf16 (B_tot x n_s), boxes 64 cols x 32 rows
   const int64_t* tl;
@@ -253,23 +256,27 @@ struct EpiBwdDcos {
           const bool has_t = rel >= 0 && rel < 32;
           float cos_t = 0.f;
           if (has_t) cos_t = pick32(v, (int)rel);
-          float pr[32];                                      // dcos * raw cosine
+          float pr[WITH_RDOT ? 32 : 1];                      // dcos * raw cosine
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float g = fmaf(fast_exp2(fmaf(v[j], s2, neg_off)), gs, -tg);
-            pr[j] = g * v[j];
+            if constexpr (WITH_RDOT) pr[j] = g * v[j];
             v[j] = g;
           }
           if (has_t) {                                       // the one target element of this row (warp-divergent, rare)
             const float p = fast_exp2(fmaf(margin_target(mg, cos_t), s2, neg_off));
             const float g = (p - smooth_on) * gs * margin_target_grad(mg, cos_t);
             put32(v, (int)rel, g);
-            put32(pr, (int)rel, g * cos_t);
+            if constexpr (WITH_RDOT) put32(pr, (int)rel, g * cos_t);
           }
           if (col0 + 32 > n_s) {                             // ragged last tile (warp-uniform)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = (col0 + j < n_s) ? v[j] : 0.f; pr[j] = (col0 + j < n_s) ? pr[j] : 0.f; }
+            for (int j = 0; j < 32; ++j) {
+              v[j] = (col0 + j < n_s) ? v[j] : 0.f;
+              if constexpr (WITH_RDOT) pr[j] = (col0 + j < n_s) ? pr[j] : 0.f;
+            }
           }
+          if constexpr (WITH_RDOT) {
           // column sums over the 32 rows of this warp, then one red per lane.  The products are packed to bf16x2 first
           // (rdot = <Wn, dWn> is the projection term of the normalise backward; bf16 products leave it exact to ~2e-3, a
           // fifth of the tolerance of the bf16 dcos it corrects), so the recursive halving moves 16 packed values: 16 shuffles
@@ -299,6 +306,7 @@ struct EpiBwdDcos {
             const float colsum = (lane & 1) ? __high2float(r) : __low2float(r);
             if (col0 + lane < n_s) atomicAdd(rdot + col0 + lane, colsum);
           }
+          }   // WITH_RDOT
           // bf16 pack: 32 values = 64 bytes = 4 x uint4 -> half `h` of the 128-byte staging row
 #pragma unroll
           for (int q = 0; q < 4; ++q) packed[h * 4 + q] = Vec<__nv_bfloat16>::pack(v + q * 8);
@@ -416,6 +424,43 @@ struct EpiDwNormBwdT {
       }
       __syncwarp();   // every lane is done with this Wn box before it is refilled
       if (bx + 2 < n_boxes) load_wn_box(wwn + (bx & 1) * 4096, row0, dcol0 + (bx + 2) * 64, lane);
+    }
+  }
+};
+
+// dW in raw mode: dWn = dcos^T X as it leaves the tensor core (fp32), no projection, no 1/||w||: a plain TMEM -> TMA-store copy
+struct EpiDwRaw {
+  static constexpr int kSmemBytes = 8 * StageOut::kBytesPerWarp;    // 64 KB (8 epilogue warps)
+  CUtensorMap map_dw;          // fp32 (n_s x D), boxes 32 cols x 32 rows
+  int n_s, D, block_n;
+  __device__ void prefetch(int, int, int, int, uint8_t*, int, int) const {}
+  __device__ void finish(int, int lane) const { StageOut::drain(lane); }
+  __device__ void operator()(uint32_t tmem_acc, int m_blk, int n_blk, int, int quarter, int lane, uint8_t* scratch, int half, int nh) const {
+    const int row0 = m_blk * kBlockM + quarter * 32;
+    const int cols = block_n / nh;
+    const int dcol0 = n_blk * block_n + half * cols;
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + half * cols;
+    uint8_t* wout = scratch + (half * 4 + quarter) * StageOut::kBytesPerWarp;
+    int n_chunks = (D - dcol0) / 32;
+    if (n_chunks > cols / 32) n_chunks = cols / 32;
+    if (n_chunks <= 0) return;
+    float buf[2][32];
+    tmem_ld32_issue(taddr, buf[0]);
+    tmem_ld_wait(buf[0]);
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; c += 2) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (c + h >= n_chunks) break;
+        const float* v = buf[h];
+        if (c + h + 1 < n_chunks) tmem_ld32_issue(taddr + (c + h + 1) * 32, buf[h ^ 1]);
+        uint4 out[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          out[q] = make_uint4(__float_as_uint(v[q * 4]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+        StageOut::put_and_store(wout, (c + h) & 1, lane, out, &map_dw, dcol0 + (c + h) * 32, row0);
+        if (c + h + 1 < n_chunks) tmem_ld_wait(buf[h ^ 1]);
+      }
     }
   }
 };
@@ -662,11 +707,11 @@ extern "C" int msml_head_merge_stats(const float* gathered, int64_t W, int64_t B
   return 0;
 }
 
-extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_norm, const int64_t* tl, int64_t B_tot,
-                             int64_t n_s, int64_t D, const msml_margin_params* margin, const float* gstats, float* dx_full,
-                             float* dw, void* ws, size_t ws_bytes, void* stream) {
+static int head_bwd_impl(const void* x, const void* wn, const float* inv_norm, const int64_t* tl, int64_t B_tot,
+                         int64_t n_s, int64_t D, const msml_margin_params* margin, const float* gstats, float* dx_full,
+                         float* dw, void* ws, size_t ws_bytes, void* stream, bool raw) {
   if (int e = head_check(B_tot, n_s, D, ws, ws_bytes)) return e;
-  MSML_REQUIRE(x && wn && inv_norm && tl && gstats && dx_full && dw, MSML_EINVAL, "null pointer");
+  MSML_REQUIRE(x && wn && (raw || inv_norm) && tl && gstats && dx_full && dw, MSML_EINVAL, "null pointer");
   MSML_REQUIRE(aligned16(dx_full) && aligned16(dw), MSML_EALIGN, "gradient buffers must be 16-byte aligned");
   Margin mg;
   if (int e = to_margin(margin, &mg)) return e;
@@ -676,36 +721,33 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
   const bool blocked = dcos_blocked();
   const bool pair = head_pair_mode() == 2 && B_tot > kBlockM;
   const bool pair_dx = head_pair_mode() >= 1 && B_tot > kBlockM;
-  // 1. recompute logits -> dcos (bf16; tile-blocked, see tc_gemm.cuh) + rdot[n] = <Wn[n], dWn[n]>
+  // 1. recompute logits -> dcos (bf16; tile-blocked, see tc_gemm.cuh) [+ rdot[n] = <Wn[n], dWn[n]> unless raw]
   {
-    MSML_CUDA(cudaMemsetAsync(h.rdot, 0, sizeof(float) * (size_t)n_s, st));
+    if (!raw) MSML_CUDA(cudaMemsetAsync(h.rdot, 0, sizeof(float) * (size_t)n_s, st));
     const int bn = pick_block_n(B_tot, n_s, pair);
     CUtensorMap ma, mb;
     if (int e = encode_tmap_bf16_kmajor(&ma, x, B_tot, D, D, kBlockM)) return e;
     if (int e = encode_tmap_bf16_kmajor(&mb, wn, n_s, D, D, pair ? bn / 2 : bn)) return e;   // box rows: the B rows ONE CTA loads
     const float eps = 0.1f;   // ref partial_fc.py:154
-    EpiBwdDcos epi;
-    if (blocked) {
-      if (int e = encode_tmap_2d(&epi.map_dcos, h.dcos, 2, 64, h.n_cb * h.blk_pitch, 64, 64, 32)) return e;
-    } else {
-      if (int e = encode_tmap_2d(&epi.map_dcos, h.dcos, 2, n_s, B_tot, h.ld_dc, 64, 32)) return e;
-    }
-    epi.blk_pitch = blocked ? (int)h.blk_pitch : 0;
-    epi.tl = tl; epi.mg = mg; epi.B_tot = (int)B_tot; epi.n_s = (int)n_s; epi.block_n = bn;
-    epi.gmax = gstats; epi.gsum = gstats + B_tot; epi.rdot = h.rdot;
-    epi.smooth_on = 1.0f - eps; epi.smooth_off = eps / (float)(n_s - 1); epi.inv_btot = 1.0f / (float)B_tot;
     const double min_bytes = 2.0 * (double)n_s * D + 2.0 * (double)B_tot * D + 2.0 * (double)B_tot * n_s;   // + dcos out
-    if (pair) {
-      if (bn == 256) {
-        if (int e = launch_gemm_pair<256, 2, 4, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
+    auto run_dcos = [&](auto epi) -> int {
+      if (blocked) {
+        if (int e = encode_tmap_2d(&epi.map_dcos, h.dcos, 2, 64, h.n_cb * h.blk_pitch, 64, 64, 32)) return e;
       } else {
-        if (int e = launch_gemm_pair<128, 4, 6, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
+        if (int e = encode_tmap_2d(&epi.map_dcos, h.dcos, 2, n_s, B_tot, h.ld_dc, 64, 32)) return e;
       }
-    } else if (bn == 256) {
-      if (int e = launch_gemm<256, 2, 3, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes)) return e;
-    } else {
-      if (int e = launch_gemm<128, 4, 4, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes)) return e;
-    }
+      epi.blk_pitch = blocked ? (int)h.blk_pitch : 0;
+      epi.tl = tl; epi.mg = mg; epi.B_tot = (int)B_tot; epi.n_s = (int)n_s; epi.block_n = bn;
+      epi.gmax = gstats; epi.gsum = gstats + B_tot; epi.rdot = raw ? nullptr : h.rdot;
+      epi.smooth_on = 1.0f - eps; epi.smooth_off = eps / (float)(n_s - 1); epi.inv_btot = 1.0f / (float)B_tot;
+      if (pair) {
+        if (bn == 256) return launch_gemm_pair<256, 2, 4, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes);
+        return launch_gemm_pair<128, 4, 6, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes);
+      }
+      if (bn == 256) return launch_gemm<256, 2, 3, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 256), epi, st, min_bytes);
+      return launch_gemm<128, 4, 4, false, false, 8>("head_bwd_dcos_gemm", ma, mb, make_shape(B_tot, n_s, D, 128), epi, st, min_bytes);
+    };
+    if (int e = raw ? run_dcos(EpiBwdDcosT<false>()) : run_dcos(EpiBwdDcosT<true>())) return e;
   }
   // 2. dX_full = dcos (B_tot x n_s) * Wn (n_s x D): A = dcos (K-major), B = Wn read in place (MN-major), split-K
   {
@@ -753,6 +795,25 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
     if (dw_ew < 0) { const char* e = getenv("MSML_HEAD_DW_EW"); dw_ew = e ? atoi(e) : 0; }
     const double min_bytes_dw = 4.0 * (double)n_s * D + 2.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 2.0 * (double)B_tot * D;
     const bool wide_epilogue = dw_ew == 8 || (dw_ew != 4 && B_tot <= 2 * kBlockK);
+    // CTA pairs for dW (each CTA stages half of the X tile, 256 classes x 256 columns per pair, a 5-deep ring): the X slice
+    // is re-read from L2 for every tile, and halving that stream is worth 144.6 -> 132.0 us (exact) / 142.5 -> 127.5 us (raw)
+    // at config-4 shapes; with few tiles (config-3 W=8 shard: 184) the pair's hand-off costs 2 us instead.
+    // MSML_HEAD_DW_PAIR=0|1 forces it.
+    static int dw_pair_env = -1;
+    if (dw_pair_env < 0) { const char* e = getenv("MSML_HEAD_DW_PAIR"); dw_pair_env = !e ? 2 : (e[0] == '1' ? 1 : 0); }
+    const int64_t dw_tiles = ((n_s + kBlockM - 1) / kBlockM) * ((D + 255) / 256);
+    const bool dw_pair = n_s > kBlockM && !wide_epilogue && (dw_pair_env == 1 || (dw_pair_env == 2 && dw_tiles >= 4 * (int64_t)num_sms()));
+    if (raw) {     // dWn as it leaves the tensor core; the fused optimizer projects and scales (msml_pfc_sgd_update_raw)
+      EpiDwRaw epir;
+      if (int e = encode_tmap_2d(&epir.map_dw, dw, 4, D, n_s, D, 32, 32)) return e;
+      epir.n_s = (int)n_s; epir.D = (int)D; epir.block_n = 256;
+      GemmShape shr = make_shape(n_s, D, B_tot, 256, 1, /*n_fastest=*/true);
+      shr.a_blk_pitch = (int)h.blk_pitch;
+      const double mb_raw = 4.0 * (double)n_s * D + 2.0 * (double)B_tot * n_s + 2.0 * (double)B_tot * D;
+      if (blocked && dw_pair) return launch_gemm_pair<256, 2, 5, true, true, 8, true>("head_bwd_dw_gemm", ma, mb, shr, epir, st, mb_raw);
+      if (blocked) return launch_gemm<256, 2, 3, true, true, 8, true>("head_bwd_dw_gemm", ma, mb, shr, epir, st, mb_raw);
+      return launch_gemm<256, 2, 3, true, true, 8, false>("head_bwd_dw_gemm", ma, mb, shr, epir, st, mb_raw);
+    }
     if (blocked && wide_epilogue) {
       EpiDwNormBwdT<8> epi8;
       if (int e = encode_tmap_2d(&epi8.map_dw, dw, 4, D, n_s, D, 32, 32)) return e;
@@ -772,10 +833,23 @@ extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_nor
     epi.block_n = 256;
     GemmShape sh = make_shape(n_s, D, B_tot, 256, 1, /*n_fastest=*/true);
     sh.a_blk_pitch = (int)h.blk_pitch;
-    if (blocked) { if (int e = launch_gemm<256, 2, 3, true, true, 4, true>("head_bwd_dw_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
+    if (blocked && dw_pair) { if (int e = launch_gemm_pair<256, 2, 5, true, true, 4, true>("head_bwd_dw_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
+    else if (blocked) { if (int e = launch_gemm<256, 2, 3, true, true, 4, true>("head_bwd_dw_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
     else { if (int e = launch_gemm<256, 2, 3, true, true, 4, false>("head_bwd_dw_gemm", ma, mb, sh, epi, st, min_bytes)) return e; }
   }
   return 0;
+}
+
+extern "C" int msml_head_bwd(const void* x, const void* wn, const float* inv_norm, const int64_t* tl, int64_t B_tot,
+                             int64_t n_s, int64_t D, const msml_margin_params* margin, const float* gstats, float* dx_full,
+                             float* dw, void* ws, size_t ws_bytes, void* stream) {
+  return head_bwd_impl(x, wn, inv_norm, tl, B_tot, n_s, D, margin, gstats, dx_full, dw, ws, ws_bytes, stream, false);
+}
+
+extern "C" int msml_head_bwd_raw(const void* x, const void* wn, const int64_t* tl, int64_t B_tot, int64_t n_s, int64_t D,
+                                 const msml_margin_params* margin, const float* gstats, float* dx_full, float* dwn,
+                                 void* ws, size_t ws_bytes, void* stream) {
+  return head_bwd_impl(x, wn, nullptr, tl, B_tot, n_s, D, margin, gstats, dx_full, dwn, ws, ws_bytes, stream, true);
 }
 
 extern "C" int msml_margin_fwd(float* cosm, const int64_t* label, int64_t B, int64_t C, int64_t ld,

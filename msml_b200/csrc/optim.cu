@@ -37,9 +37,9 @@ extern "C" int msml_accum_bf16_multi(int nseg, float* const* dst, const void* co
   return 0;
 }
 
-extern "C" int msml_pfc_sgd_update(float* weight, float* weight_mom, const float* dw, const int64_t* index, int64_t n_s,
-                                   int64_t num_local, int64_t D, const float* lr_dev, float lr, float momentum, float weight_decay,
-                                   float dampening, int nesterov, void* wn_bf16, float* inv_norm, void* stream) {
+static int pfc_sgd_impl(float* weight, float* weight_mom, const float* dw, const int64_t* index, int64_t n_s,
+                        int64_t num_local, int64_t D, const float* lr_dev, float lr, float momentum, float weight_decay,
+                        float dampening, int nesterov, void* wn_bf16, float* inv_norm, void* stream, bool project) {
   if (int e = pfc_sgd_check(n_s, num_local, D)) return e;
   if (n_s == 0) return 0;
   MSML_REQUIRE(weight && weight_mom && dw, MSML_EINVAL, "null pointer");
@@ -52,11 +52,29 @@ extern "C" int msml_pfc_sgd_update(float* weight, float* weight_mom, const float
   __nv_bfloat16* wn = static_cast<__nv_bfloat16*>(wn_bf16);
   MSML_PROF("pfc_sgd_update", (double)n_s * D * (20.0 + (wn ? 2.0 : 0.0)), st);
   switch (D / 128) {
-#define MSML_SGD_CASE(V) case V: pfc_sgd_kernel<V><<<grid, kSgdThreads, 0, st>>>(weight, weight_mom, dw, index, n_s, num_local, lr_dev, p, wn, inv_norm); break;
+#define MSML_SGD_CASE(V) case V: \
+      if (project) pfc_sgd_kernel<V, true><<<grid, kSgdThreads, 0, st>>>(weight, weight_mom, dw, index, n_s, num_local, lr_dev, p, wn, inv_norm); \
+      else pfc_sgd_kernel<V, false><<<grid, kSgdThreads, 0, st>>>(weight, weight_mom, dw, index, n_s, num_local, lr_dev, p, wn, inv_norm); \
+      break;
     MSML_SGD_CASE(1) MSML_SGD_CASE(2) MSML_SGD_CASE(3) MSML_SGD_CASE(4) MSML_SGD_CASE(5) MSML_SGD_CASE(6) MSML_SGD_CASE(7) MSML_SGD_CASE(8)
 #undef MSML_SGD_CASE
     default: return set_error(MSML_EUNSUPPORTED, "D=%lld unsupported", (long long)D);
   }
   MSML_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int msml_pfc_sgd_update(float* weight, float* weight_mom, const float* dw, const int64_t* index, int64_t n_s,
+                                   int64_t num_local, int64_t D, const float* lr_dev, float lr, float momentum, float weight_decay,
+                                   float dampening, int nesterov, void* wn_bf16, float* inv_norm, void* stream) {
+  return pfc_sgd_impl(weight, weight_mom, dw, index, n_s, num_local, D, lr_dev, lr, momentum, weight_decay, dampening, nesterov,
+                      wn_bf16, inv_norm, stream, false);
+}
+
+extern "C" int msml_pfc_sgd_update_raw(float* weight, float* weight_mom, const float* dwn, const int64_t* index, int64_t n_s,
+                                       int64_t num_local, int64_t D, const float* lr_dev, float lr, float momentum,
+                                       float weight_decay, float dampening, int nesterov, void* wn_bf16, float* inv_norm,
+                                       void* stream) {
+  return pfc_sgd_impl(weight, weight_mom, dwn, index, n_s, num_local, D, lr_dev, lr, momentum, weight_decay, dampening, nesterov,
+                      wn_bf16, inv_norm, stream, true);
 }

@@ -29,7 +29,12 @@ struct SgdParams {
   int nesterov;
 };
 
-template <int VPL>                     // float4 vectors per lane: D = 128 * VPL
+// PROJECT: `dw` holds the RAW gradient of the normalised centres, dWn = dcos^T X (msml_head_bwd_raw); the backward of
+// ref partial_fc.py:115 `normalize(sub_weight)` is applied here, on the row the warp already holds in registers:
+//     n = max(||w||, 1e-12);  g = dWn / n - w * <w, dWn> / n^3        (= (dWn - wn <wn, dWn>) / n with wn = w / n)
+// so the two GEMM epilogues that used to do it (a <Wn, dWn> column reduction in dcos, a Wn stream in dW) have nothing to do.
+// It uses the fp32 master row, as the reference's autograd does (the unfused path projects with the bf16-rounded wn).
+template <int VPL, bool PROJECT = false>   // float4 vectors per lane: D = 128 * VPL
 __global__ void __launch_bounds__(kSgdThreads)
 pfc_sgd_kernel(float* __restrict__ weight, float* __restrict__ weight_mom, const float* __restrict__ dw,
                const int64_t* __restrict__ index, int64_t n_s, int64_t num_local, const float* __restrict__ lr_dev, SgdParams p,
@@ -51,6 +56,22 @@ pfc_sgd_kernel(float* __restrict__ weight, float* __restrict__ weight_mom, const
     w[v] = w4[v * 32 + lane];
     m[v] = m4[v * 32 + lane];
   }
+  float ga = 1.f, gb = 0.f;              // g_true = ga * g_raw - gb * w
+  if (PROJECT) {
+    float s2 = 0.f, dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const float* wf = reinterpret_cast<const float*>(&w[v]);
+      const float* gf = reinterpret_cast<const float*>(&g[v]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s2 = fmaf(wf[i], wf[i], s2); dot = fmaf(wf[i], gf[i], dot); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s2 += __shfl_xor_sync(0xffffffffu, s2, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); }
+    const float inv_n = 1.0f / fmaxf(sqrtf(s2), 1e-12f);
+    ga = inv_n;
+    gb = dot * inv_n * inv_n * inv_n;
+  }
   float ss = 0.f;
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
@@ -59,7 +80,8 @@ pfc_sgd_kernel(float* __restrict__ weight, float* __restrict__ weight_mom, const
     const float* gf = reinterpret_cast<const float*>(&g[v]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float d = fmaf(p.weight_decay, wf[i], gf[i]);
+      const float gt = PROJECT ? fmaf(ga, gf[i], -gb * wf[i]) : gf[i];
+      const float d = fmaf(p.weight_decay, wf[i], gt);
       const float mn = fmaf(p.momentum, mf[i], (1.f - p.dampening) * d);
       const float upd = p.momentum == 0.f ? d : (p.nesterov ? fmaf(p.momentum, mn, d) : mn);
       const float wnew = fmaf(-lr, upd, wf[i]);

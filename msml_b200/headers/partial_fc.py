@@ -270,8 +270,16 @@ class PartialFC(Module):
             loss_v = torch.empty((), dtype=torch.float32, device=self.device)
             dw = (torch.empty((n_s, D), dtype=torch.float32, device=self.device) if int(self.sample_rate) == 1
                   else self._buf("dw", (n_s, D), torch.float32))
-            check(lib.msml_head_step(h, _ptr(x), _ptr(wn), _ptr(inv_norm), _ptr(total_label), B, n_s, D, ctypes.byref(self._margin),
-                                     _ptr(x_grad), _ptr(dw), _ptr(loss_v), _ptr(sws), sbytes, stream_ptr()))
+            # raw mode: the optimizer handed in is a PartialFCSGD(fuse_projection=True) driving THIS module — it applies the
+            # normalise backward itself, so the GEMM epilogues skip it and dw is dWn = dcos^T X
+            raw = bool(getattr(optimizer, "fuse_projection", False)) and getattr(optimizer, "module", None) is self
+            if raw:
+                check(lib.msml_head_step_raw(h, _ptr(x), _ptr(wn), _ptr(total_label), B, n_s, D, ctypes.byref(self._margin),
+                                             _ptr(x_grad), _ptr(dw), _ptr(loss_v), _ptr(sws), sbytes, stream_ptr()))
+            else:
+                check(lib.msml_head_step(h, _ptr(x), _ptr(wn), _ptr(inv_norm), _ptr(total_label), B, n_s, D, ctypes.byref(self._margin),
+                                         _ptr(x_grad), _ptr(dw), _ptr(loss_v), _ptr(sws), sbytes, stream_ptr()))
+            self._grad_is_raw = raw
             self.sub_weight.grad = dw
         self.last_loss = loss_v
         return x_grad, loss_v
@@ -322,6 +330,7 @@ class PartialFC(Module):
                   else self._buf("dw", (n_s, D), torch.float32))
             check(lib.msml_head_bwd(_ptr(x), _ptr(wn), _ptr(inv_norm), _ptr(total_label), B_tot, n_s, D, mp,
                                     _ptr(gstats), _ptr(dx_full), _ptr(dw), _ptr(ws), ws_bytes, stream_ptr()))
+            self._grad_is_raw = False
             self.sub_weight.grad = dw
 
             # feature gradient reduce-scatter, then * world_size (ref :172-175)

@@ -31,7 +31,8 @@ def _ptr(t):
 
 
 class PartialFCSGD(torch.optim.Optimizer):
-    def __init__(self, module, lr, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=False, emit_normalized=False):
+    def __init__(self, module, lr, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=False, emit_normalized=False,
+                 fuse_projection=False):
         if not isinstance(lr, torch.Tensor) and lr < 0.0:
             raise ValueError("Invalid learning rate: {}".format(lr))
         if momentum < 0.0:
@@ -53,6 +54,12 @@ class PartialFCSGD(torch.optim.Optimizer):
         # partial_fc.py:115).  Opt-in because it assumes nobody else writes module.weight between two steps; call
         # module.invalidate_normalized() after loading / editing the class centres by hand.
         self.emit_normalized = bool(emit_normalized) and int(module.sample_rate) == 1
+        # fuse_projection: PartialFC.forward_backward(label, features, THIS optimizer) then runs the head in raw mode —
+        # sub_weight.grad holds dWn = dcos^T X, the gradient with respect to the NORMALISED centres — and step() applies the
+        # backward of normalize(sub_weight) (ref partial_fc.py:115) to the row it holds in registers before the update
+        # (msml_pfc_sgd_update_raw).  The dcos GEMM loses its <Wn, dWn> column reduction and the dW GEMM its Wn stream.
+        # Opt-in: the gradient is only final inside this optimizer, so do not read or clip sub_weight.grad yourself.
+        self.fuse_projection = bool(fuse_projection)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -79,10 +86,13 @@ class PartialFCSGD(torch.optim.Optimizer):
         if self.emit_normalized:
             wn = m._buf("wn", (n_s, D), torch.bfloat16)
             inv = m._buf("inv_norm", (n_s,), torch.float32)
-        check(load().msml_pfc_sgd_update(_ptr(m.weight), _ptr(m.weight_mom), _ptr(dw), _ptr(index), n_s, m.num_local, D,
-                                         _ptr(lr_dev), 0.0 if lr_dev is not None else float(lr), float(g["momentum"]),
-                                         float(g["weight_decay"]), float(g["dampening"]), int(bool(g["nesterov"])), _ptr(wn), _ptr(inv),
-                                         stream_ptr()))
+        raw = bool(getattr(m, "_grad_is_raw", False))
+        if raw and not self.fuse_projection:
+            raise RuntimeError("PartialFCSGD: the module produced a raw (unprojected) gradient for another optimizer")
+        fn = load().msml_pfc_sgd_update_raw if raw else load().msml_pfc_sgd_update
+        check(fn(_ptr(m.weight), _ptr(m.weight_mom), _ptr(dw), _ptr(index), n_s, m.num_local, D,
+                 _ptr(lr_dev), 0.0 if lr_dev is not None else float(lr), float(g["momentum"]),
+                 float(g["weight_decay"]), float(g["dampening"]), int(bool(g["nesterov"])), _ptr(wn), _ptr(inv), stream_ptr()))
         m._wn_fresh = self.emit_normalized
         m._fused_step_done = True           # this step's rows are already in the shard: the next update() has nothing to scatter
         return loss

@@ -199,3 +199,127 @@ def test_emitted_normalised_centres_replace_the_wnorm_pass():
     ref.weight.copy_(pfc.weight)
     _x, want = ref.forward_backward(l1, f1, None)
     assert abs(float(loss) - float(want)) <= 1e-6 * abs(float(want))
+
+
+# ------------------------------------------------------------------------------- raw mode: the optimizer applies the normalise backward
+def test_raw_update_kernel_applies_the_normalise_backward():
+    """msml_pfc_sgd_update_raw(dWn) == msml_pfc_sgd_update(normalize_bwd(w, dWn)): the projection of ref partial_fc.py:115's
+    backward, (dWn - wn <wn, dWn>) / ||w||, evaluated in fp64 on the host, then the same SGD arithmetic."""
+    need_gpu()
+    from msml_b200 import _lib
+    from oracle.margins import l2_normalize, normalize_bwd
+    lib = _lib.load()
+    torch.manual_seed(5)
+    n, D = 301, 512
+    w = torch.randn(n, D, device="cuda") * 0.02
+    mom = torch.randn(n, D, device="cuda") * 0.001
+    dwn = torch.randn(n, D, device="cuda") * 0.1
+    idx = torch.randperm(n, device="cuda")[:97].sort().values
+    for index in (None, idx):
+        rows = slice(None) if index is None else index
+        w64 = w.double().cpu().numpy()[rows.cpu().numpy() if index is not None else slice(None)]
+        g64 = dwn.double().cpu().numpy()[: w64.shape[0]]
+        dw_true = torch.from_numpy(normalize_bwd(w64, l2_normalize(w64), g64)).float().cuda()
+        wa, ma = w.clone(), mom.clone()
+        wb, mb = w.clone(), mom.clone()
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        st = _lib.stream_ptr()
+        ns = dw_true.shape[0]
+        _lib.check(lib.msml_pfc_sgd_update_raw(p(wa), p(ma), p(dwn[:ns].contiguous()), p(index), ns, n, D, None, 0.1, 0.9, 5e-4, 0.0, 0, None, None, st))
+        _lib.check(lib.msml_pfc_sgd_update(p(wb), p(mb), p(dw_true), p(index), ns, n, D, None, 0.1, 0.9, 5e-4, 0.0, 0, None, None, st))
+        torch.cuda.synchronize()
+        assert_close(host(ma), host(mb), 1e-4, atol=1e-5 * float(mb.abs().max()), what="momentum")
+        assert_close(host(wa), host(wb), 1e-4, atol=1e-6, what="weight")
+        if index is not None:
+            rest = torch.ones(n, dtype=torch.bool, device="cuda")
+            rest[index] = False
+            assert torch.equal(wa[rest], w[rest]) and torch.equal(ma[rest], mom[rest])
+
+
+@pytest.mark.parametrize("name", ["pfc_w1_d512"])          # the update kernel needs D % 128 == 0; the other goldens have D = 64
+def test_fused_projection_step_matches_reference_weights(name):
+    """The whole raw-mode step — head in raw mode (no <Wn, dWn> reduction in dcos, no Wn stream in dW) + PartialFCSGD
+    (fuse_projection=True) — against the reference's own updated class centres and momentum (tests/golden/pfc_w1_*.npz:
+    ref PartialFC.forward_backward + torch SGD + update()), sampled indices bit-exact."""
+    need_gpu()
+    from conftest import load_golden
+    from msml_b200.headers import MarginSoftmax, PartialFC, PartialFCSGD
+    from msml_b200.headers import partial_fc as mod
+    g = load_golden(name)
+    B, C, D, sr = int(g["B"]), int(g["C"]), int(g["D"]), float(g["sample_rate"])
+    dv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pfc = PartialFC(0, 0, 1, B, False, MarginSoftmax(str(g["kind"]), *(float(v) for v in g["smak"])), C, sample_rate=sr, embedding_size=D)
+    pfc.weight.copy_(dv(g["r0.w0"]))
+    opt = PartialFCSGD(pfc, lr=0.1, momentum=0.9, weight_decay=5e-4, fuse_projection=True)
+    state = {"perm": None}
+    real_rand = torch.rand
+    mod.torch.rand = lambda *a, **k: state["perm"] if state["perm"] is not None else real_rand(*a, **k)
+    try:
+        for step in range(int(g["steps"])):
+            p = f"r0.s{step}."
+            if step > 0:
+                pfc.weight.copy_(dv(g[f"r0.s{step - 1}.weight_after"]))
+                pfc.weight_mom.copy_(dv(g[f"r0.s{step - 1}.mom_after"]))
+            perm = g[p + "perm"]
+            state["perm"] = dv(perm) if perm.size else None
+            x_grad, loss = pfc.forward_backward(dv(g[p + "label"]), dv(g[p + "feat"]), opt)
+            state["perm"] = None
+            assert pfc._grad_is_raw
+            if int(sr) != 1:
+                assert np.array_equal(pfc.index.cpu().numpy(), g[p + "index"])
+            opt.step()
+            pfc.update()
+            want_loss = float(g[p + "loss"])
+            assert abs(float(loss) - want_loss) <= 1e-3 * abs(want_loss)
+            assert_close(host(x_grad), g[p + "x_grad"], 2e-2, atol_frac=1e-2, what="x_grad")
+            assert_close(host(pfc.weight), g[p + "weight_after"], 2e-2, atol_frac=1e-2, what="weight_after")
+            assert_close(host(pfc.weight_mom), g[p + "mom_after"], 2e-2, atol_frac=1e-2, what="mom_after")
+    finally:
+        mod.torch.rand = real_rand
+
+
+@pytest.mark.parametrize("sample_rate", [1.0, 0.3])
+def test_fused_projection_trajectory_matches_stock_optimizer(sample_rate):
+    """Raw mode end to end (full and SAMPLED shard: the projection reads the fp32 master row at index[r]) against the
+    stock optimizer + update(): same sampled indices, same losses, same class centres to bf16 noise."""
+    need_gpu()
+    from msml_b200.headers import PartialFCSGD
+    B, C, D = 16, 1000, 512
+    ref_w, ref_m, ref_l, ref_p = _run(False, sample_rate, False)
+    pfc = _pfc(sample_rate, B, C, D)
+    opt = PartialFCSGD(pfc, fuse_projection=True, emit_normalized=True, **HP)
+    losses = []
+    for feat, label in _batches(3, B, C, D):
+        _x, loss = pfc.forward_backward(label, feat, opt)
+        assert pfc._grad_is_raw
+        opt.step()
+        pfc.update()
+        losses.append(float(loss))
+    assert np.allclose(losses, ref_l, rtol=2e-4), (losses, ref_l)
+    # The two paths differ by design in ONE term: the stock path projects with the bf16-rounded wn (head_bwd's epilogue), raw
+    # mode with the fp32 master row (as the reference's autograd does) — 2^-9 relative on the projection term, which is O(1)
+    # of the gradient for the rows of well-aligned targets.  Hence bf16 tolerance here; the comparison against the
+    # reference's own fp32 result is test_fused_projection_step_matches_reference_weights.
+    assert_close(host(pfc.weight), host(ref_w), 2e-2, atol_frac=2e-3, what="weight")
+    assert_close(host(pfc.weight_mom), host(ref_m), 2e-2, atol_frac=2e-3, what="weight_mom")
+    if int(sample_rate) != 1:
+        assert torch.equal(pfc.index, ref_p.index)
+
+
+def test_fused_projection_guards():
+    need_gpu()
+    from msml_b200.headers import PartialFCSGD
+    B, C, D = 16, 1000, 512
+    pfc = _pfc(1.0, B, C, D)
+    opt = PartialFCSGD(pfc, fuse_projection=True, emit_normalized=True, **HP)
+    # forward_backward with any other optimizer (or none) yields the exact gradient again
+    feat, label = _batches(1, B, C, D)[0]
+    pfc.forward_backward(label, feat, None)
+    assert not pfc._grad_is_raw
+    other = _pfc(1.0, B, C, D)
+    other_opt = PartialFCSGD(other, **HP)                    # no fuse_projection
+    pfc.forward_backward(label, feat, opt)                  # raw gradient for `opt` ...
+    other.forward_backward(label, feat, other_opt)
+    other._grad_is_raw = True                               # ... a raw gradient must never reach an optimizer that would not project it
+    with pytest.raises(RuntimeError):
+        other_opt.step()
