@@ -177,10 +177,11 @@ def ncu_traffic(name, suffix=""):
             path = os.path.join(ROOT, "profiles", f)
             if os.path.exists(path):
                 _TRAFFIC.append((f, json.load(open(path))))
-    for f, table in _TRAFFIC:
-        rec = table.get(name + suffix)
-        if rec:
-            return rec["dram_bytes_per_launch"], "profiles/%s (%s)" % (f, rec.get("captured", table.get("_captured", "ncu --set full, earlier commit")))
+    for sfx in (suffix if isinstance(suffix, (list, tuple)) else (suffix,)):
+        for f, table in _TRAFFIC:
+            rec = table.get(name + sfx)
+            if rec:
+                return rec["dram_bytes_per_launch"], "profiles/%s (%s)" % (f, rec.get("captured", table.get("_captured", "ncu --set full, earlier commit")))
     return None, None
 
 
@@ -272,7 +273,8 @@ def head_microbench(iters=5, b_tot=1024, n_s=125000, fused_projection=False):
     torch.cuda.synchronize()
     lib.msml_profile_enable(0)
     prof = collect_profile(lib)
-    rl = sorted((roofline_entry(k, v, pk, sustained=False, traffic_suffix="@config4") for k, v in prof.items()),
+    sfx = ("@config4raw", "@config4") if fused_projection else "@config4"
+    rl = sorted((roofline_entry(k, v, pk, sustained=False, traffic_suffix=sfx) for k, v in prof.items()),
                 key=lambda r: -r["avg_us"] * r["launches"])
     gemm_ms = sum(v["total_ms"] for k, v in prof.items() if k.endswith("_gemm")) / iters
     del pfc
