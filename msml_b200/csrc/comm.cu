@@ -173,7 +173,10 @@ extern "C" int msml_head_gather(msml_comm* comm, const float* feat, const int64_
     head_pack_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(feat, label, W > 1 ? send : recv, B, (int)D);
     MSML_LAUNCH_CHECK();
   }
-  if (W > 1) MSML_NCCL(nccl_api()->AllGather(send, recv, msg, kNcclInt8, comm->nccl, st));
+  if (W > 1) {
+    MSML_PROF("nccl_allgather_embeddings_labels", (double)W * msg, st);     // per-collective device time (includes waiting for peers)
+    MSML_NCCL(nccl_api()->AllGather(send, recv, msg, kNcclInt8, comm->nccl, st));
+  }
   {
     MSML_PROF("head_unpack", (double)W * B * D * 4, st);
     head_unpack_kernel<<<(unsigned)((W * B + 7) / 8), 256, 0, st>>>(recv, msg, static_cast<__nv_bfloat16*>(x_bf16), total_label, B,
@@ -214,7 +217,10 @@ static int head_step_impl(msml_comm* comm, const void* x, const void* wn, const 
 
   if (int e = msml_head_fwd(x, wn, tl, B_tot, n_s, D, margin, stats, head_ws, hw, stream)) return e;
   // ONE all-gather of (max, sum-exp, target logit) per row replaces all_reduce(MAX), all_reduce(SUM) and the loss all_reduce
-  if (W > 1) MSML_NCCL(nccl_api()->AllGather(stats, gathered, (size_t)3 * B_tot, kNcclFloat32, comm->nccl, st));
+  if (W > 1) {
+    MSML_PROF("nccl_allgather_row_stats", (double)W * 3 * B_tot * 4, st);
+    MSML_NCCL(nccl_api()->AllGather(stats, gathered, (size_t)3 * B_tot, kNcclFloat32, comm->nccl, st));
+  }
   if (int e = msml_head_merge_stats(W > 1 ? gathered : stats, W, B_tot, gstats, loss, stream)) return e;
   if (raw) {
     if (int e = msml_head_bwd_raw(x, wn, tl, B_tot, n_s, D, margin, gstats, W > 1 ? dx_full : x_grad, dw, head_ws, hw, stream)) return e;
@@ -222,7 +228,10 @@ static int head_step_impl(msml_comm* comm, const void* x, const void* wn, const 
     if (int e = msml_head_bwd(x, wn, inv_norm, tl, B_tot, n_s, D, margin, gstats, W > 1 ? dx_full : x_grad, dw, head_ws, hw, stream)) return e;
   }
   if (W > 1) {
-    MSML_NCCL(nccl_api()->ReduceScatter(dx_full, x_grad, (size_t)B * D, kNcclFloat32, kNcclSum, comm->nccl, st));
+    {
+      MSML_PROF("nccl_reduce_scatter_dx", (double)B_tot * D * 4, st);
+      MSML_NCCL(nccl_api()->ReduceScatter(dx_full, x_grad, (size_t)B * D, kNcclFloat32, kNcclSum, comm->nccl, st));
+    }
     scale_kernel<<<(unsigned)((B * D + 255) / 256), 256, 0, st>>>(x_grad, B * D, (float)W);      // ref :175
     MSML_LAUNCH_CHECK();
   }
