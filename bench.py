@@ -602,7 +602,7 @@ def run_head(args, rank, local_rank, world):
     sampled = int(args.sample_rate) != 1
     pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), args.classes, sample_rate=args.sample_rate, embedding_size=512)
     hp = dict(lr=0.1, momentum=0.9, weight_decay=5e-4)
-    opt = (PartialFCSGD(pfc, fuse_projection=not args.exact_head_grad, **hp) if args.fused_sgd
+    opt = (PartialFCSGD(pfc, fuse_projection=not args.exact_head_grad, emit_normalized=True, **hp) if args.fused_sgd
            else torch.optim.SGD([{"params": pfc.parameters()}], **hp))
     check = None
     if not sampled and not args.no_head_check:
