@@ -20,7 +20,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from msml_b200.backbones import MSML  # noqa: E402
 from msml_b200.engine import TrainStep, broadcast_parameters  # noqa: E402
-from msml_b200.headers import ArcFace, PartialFC  # noqa: E402
+from msml_b200.headers import ArcFace, PartialFC, PartialFCSGD  # noqa: E402
 
 
 def batches(batch, num_classes, device_generator, steps):
@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--lr", type=float, default=0.1)
     ap.add_argument("--sample-rate", type=float, default=1.0)
     ap.add_argument("--out", default="./", help="prefix for PartialFC.save_params()")
+    ap.add_argument("--stock-head-sgd", action="store_true", help="torch.optim.SGD + update() for the class centres, exactly as ref "
+                    "train.py:188-191,299-300, instead of the fused headers.PartialFCSGD")
     args = ap.parse_args()
 
     rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -59,7 +61,10 @@ def main():
     lr = args.lr / 512 * args.batch * world                               # ref :176, :190
     opt_backbone = torch.optim.SGD([p for p in backbone.parameters() if p.requires_grad], lr=lr, momentum=0.9,
                                    weight_decay=5e-4, fused=True)
-    opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
+    if args.stock_head_sgd:
+        opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
+    else:   # same hyper-parameters and param_groups (LR schedulers work); one kernel on the shard rows, update() has nothing to scatter
+        opt_pfc = PartialFCSGD(pfc, lr=lr, momentum=0.9, weight_decay=5e-4, emit_normalized=True, fuse_projection=True)
     warmup, total = max(1, args.steps // 20), args.steps
 
     def lr_func(step):                                                     # ref config.py: lr_step_func (warm-up, then decay)
@@ -67,9 +72,9 @@ def main():
     sched_backbone = torch.optim.lr_scheduler.LambdaLR(opt_backbone, lr_func)
     sched_pfc = torch.optim.lr_scheduler.LambdaLR(opt_pfc, lr_func)
 
-    # sampled heads need a data-dependent allocation per step: they run the same step eagerly
+    # sampled heads are captured too (fixed-capacity index / gather buffers) as long as the gathered batch fits in the sample
     step = TrainStep(backbone, pfc, opt_backbone, opt_pfc, (args.batch, 3, 112, 112), world_size=world, max_norm=5.0,
-                     use_graph=args.sample_rate == 1.0)
+                     use_graph=args.sample_rate == 1.0 or args.batch * world <= pfc.num_sample)
     gen = torch.Generator().manual_seed(1 + rank)
     it = batches(args.batch, args.classes, gen, args.steps)
     step.prefetch(*next(it))
@@ -87,6 +92,8 @@ def main():
         torch.save(backbone.state_dict(), os.path.join(args.out, "backbone.pth"))   # same keys as the reference's checkpoints
     if world > 1:
         dist.barrier()
+        del step                                                           # release the captured graph before tearing NCCL down
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
