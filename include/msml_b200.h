@@ -156,6 +156,19 @@ int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, con
                 float* running_mean, float* running_var, int64_t* num_batches_tracked, float* save_mean,
                 float* save_invstd, int64_t P, int64_t C, int dtype, int training, float momentum, float eps,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* msml_bn_fwd with the statistics pass of a FOLLOWING BatchNorm folded in (training mode, split launches only).  In the
+ * residual unit of ref backbones/frb/iresnet.py:56-67 the output of `bn3(out) + identity` is the input of the next unit's
+ * `bn1`; torch reads that tensor once more just for bn1's batch statistics.
+ *   next_ws  (nullable, a msml_bn_workspace(P, C) buffer distinct from `workspace`): the apply pass also leaves the slab
+ *            statistics of the y it writes (rounded to `dtype`, i.e. what the next BN would read) there;
+ *   stats_ready != 0: `workspace` is such a buffer, filled by the call that produced x with next_ws == workspace here; this
+ *            call starts at the per-channel merge and never reads x for statistics.
+ * Everything else as msml_bn_fwd.  Results equal the unchained call up to fp32 summation order of the slab partials. */
+int msml_bn_fwd_ex(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
+                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float* save_mean,
+                   float* save_invstd, int64_t P, int64_t C, int dtype, int training, float momentum, float eps,
+                   void* workspace, size_t workspace_bytes, void* next_ws, size_t next_ws_bytes, int stats_ready,
+                   void* stream);
 int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* beta,
                 const float* prelu, const float* save_mean, const float* save_invstd, void* dx, void* dres,
                 const void* dadd /* nullable: dx = bn_bwd(..) + dadd */, float* dgamma, float* dbeta, float* dprelu,

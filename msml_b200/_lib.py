@@ -48,6 +48,8 @@ SIGNATURES = {
     "msml_consensus_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_p]),
     "msml_bn_workspace": (c_size, [c_i64, c_i64]),
     "msml_bn_fwd": (c_int, [c_p] * 11 + [c_i64, c_i64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_p, c_size, c_p]),
+    "msml_bn_fwd_ex": (c_int, [c_p] * 11 + [c_i64, c_i64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_p, c_size, c_p, c_size,
+                                c_int, c_p]),
     "msml_bn_bwd": (c_int, [c_p] * 14 + [c_i64, c_i64, c_int, c_int, c_int, c_p, c_size, c_p]),
     "msml_pfc_sgd_update": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_float, c_int, c_p, c_p, c_p]),

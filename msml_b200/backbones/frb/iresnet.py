@@ -88,7 +88,8 @@ class IResNet(nn.Module):
                 raise RuntimeError("`ori` given but this FRB has no peer network: build MSML with peer_params['use_ori'] = True "
                                    "(and an Arc / Cos head), or inject one with IResNet.set_peer()")
             _, ft = self.peer(ori)
-        x = ops.bn_act(ops.conv2d_padded_in(x, self.conv1, x.shape[1] - self.conv1.in_channels), self.bn1, self.prelu)
+        x = ops.bn_act(ops.conv2d_padded_in(x, self.conv1, x.shape[1] - self.conv1.in_channels), self.bn1, self.prelu,
+                       emit_next_stats=True)      # layer1's first bn1 reads this tensor next
         kd_terms = []
         for i, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
             x = ops.grad_marker(x, i)       # backward: everything from stage i on has its parameter gradients complete

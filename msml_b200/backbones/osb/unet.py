@@ -60,10 +60,10 @@ class Unet(nn.Module):
         self.conv1 = nn.Conv2d(1 if gray else 3, 64, kernel_size=3, stride=2, padding=1, bias=False)
         self.bn1 = nn.BatchNorm2d(64, eps=1e-05)
         self.prelu = nn.PReLU(64)
-        self.layer1 = make_stage(64, 64, layers[0], 2)
-        self.layer2 = make_stage(64, 128, layers[1], 2)
-        self.layer3 = make_stage(128, 256, layers[2], 2)
-        self.layer4 = make_stage(256, 512, layers[3], 2)
+        self.layer1 = make_stage(64, 64, layers[0], 2, feeds_bn=True)
+        self.layer2 = make_stage(64, 128, layers[1], 2, feeds_bn=True)
+        self.layer3 = make_stage(128, 256, layers[2], 2, feeds_bn=True)
+        self.layer4 = make_stage(256, 512, layers[3], 2, feeds_bn=True)
         self.bn2 = nn.BatchNorm2d(512, eps=1e-05)
 
         seg = num_classes * dap_k ** 2
@@ -107,7 +107,8 @@ class Unet(nn.Module):
         return [o[:, :seg] for o in outs]
 
     def _decode(self, x):
-        x0 = ops.bn_act(ops.conv2d_padded_in(x, self.conv1, x.shape[1] - self.conv1.in_channels), self.bn1, self.prelu)
+        x0 = ops.bn_act(ops.conv2d_padded_in(x, self.conv1, x.shape[1] - self.conv1.in_channels), self.bn1, self.prelu,
+                       emit_next_stats=True)      # layer1's first bn1 reads this tensor next
         x1 = self.layer1(x0)
         x2 = self.layer2(x1)
         x3 = self.layer3(x2)

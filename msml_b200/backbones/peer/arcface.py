@@ -43,10 +43,10 @@ class IResNet(nn.Module):
         self.conv1 = nn.Conv2d(3, 64, kernel_size=3, stride=1, padding=1, bias=False)
         self.bn1 = nn.BatchNorm2d(64, eps=1e-05)
         self.prelu = nn.PReLU(64)
-        self.layer1 = make_stage(64, 64, layers[0], 2)
-        self.layer2 = make_stage(64, 128, layers[1], 2)
-        self.layer3 = make_stage(128, 256, layers[2], 2)
-        self.layer4 = make_stage(256, 512, layers[3], 2)
+        self.layer1 = make_stage(64, 64, layers[0], 2, feeds_bn=True)
+        self.layer2 = make_stage(64, 128, layers[1], 2, feeds_bn=True)
+        self.layer3 = make_stage(128, 256, layers[2], 2, feeds_bn=True)
+        self.layer4 = make_stage(256, 512, layers[3], 2, feeds_bn=True)
         self.bn2 = nn.BatchNorm2d(512, eps=1e-05)
         self.dropout = nn.Dropout(p=dropout, inplace=True)
         self.fc = nn.Linear(512 * self.fc_scale, dim_feature)
@@ -70,7 +70,7 @@ class IResNet(nn.Module):
         if x.is_cuda:
             x = x.contiguous(memory_format=torch.channels_last)
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=bool(self.fp16) and x.is_cuda):
-            x = ops.bn_act(ops.conv2d(x, self.conv1), self.bn1, self.prelu)
+            x = ops.bn_act(ops.conv2d(x, self.conv1), self.bn1, self.prelu, emit_next_stats=True)
             for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
                 x = layer(x)
                 inter.append(x.detach())

@@ -110,14 +110,16 @@ static int launch_plain(const void* kern, int blocks, void** args, cudaStream_t 
 template <typename T, bool RES, bool PRELU>
 static int launch_bn_fwd_fused(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
                                float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps, float* save_mean,
-                               float* save_invstd, float* part, float* part_n, float* coef, BnGeom g, cudaStream_t st) {
+                               float* save_invstd, float* part, float* part_n, float* coef, BnGeom g, cudaStream_t st,
+                               float* next_part, float* next_part_n, bool stats_ready) {
   const T* xp = static_cast<const T*>(x);
   const T* rp = static_cast<const T*>(res);
   T* yp = static_cast<T*>(y);
   long long* nb = reinterpret_cast<long long*>(nbt);
   void* args[] = {&xp, &rp, &yp, &gamma, &beta, &prelu, &running_mean, &running_var, &nb, &momentum, &eps,
-                  &save_mean, &save_invstd, &part, &part_n, &coef, &g};
+                  &save_mean, &save_invstd, &part, &part_n, &coef, &g, &next_part, &next_part_n};
   if (bn_fused_mode()) {
+    MSML_REQUIRE(!next_part && !stats_ready, MSML_EUNSUPPORTED, "chained BN statistics need the split launches (MSML_BN_FUSED=0)");
     auto kern = bn_fwd_fused_kernel<T, RES, PRELU, 0>;
     int grid = 0;
     if (int e = coop_grid(kern, g, &grid)) return e;
@@ -127,13 +129,22 @@ static int launch_bn_fwd_fused(const void* x, const void* res, void* y, const fl
   // each streaming phase gets a grid of at most ONE resident wave of its own kernel (a second, partly filled wave of the
   // statically partitioned slabs would only add a tail); phase 3 may partition the rows differently from phase 1
   int g1 = 0, g3 = 0;
+  const void* k3 = next_part ? reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 3, true>)
+                             : reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 3>);
   if (int e = coop_grid(bn_fwd_fused_kernel<T, RES, PRELU, 1>, g, &g1)) return e;
-  if (int e = coop_grid(bn_fwd_fused_kernel<T, RES, PRELU, 3>, g, &g3)) return e;
-  g.G = g1;
-  if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st)) return e;
-  if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st, true)) return e;
+  if (next_part) { if (int e = coop_grid(bn_fwd_fused_kernel<T, RES, PRELU, 3, true>, g, &g3)) return e; }
+  else if (int e = coop_grid(bn_fwd_fused_kernel<T, RES, PRELU, 3>, g, &g3)) return e;
+  if (stats_ready) {
+    // the producer's phase 3 left the slab statistics in this workspace: partial stride kBnMaxCtas, zero counts behind its grid
+    g.G = kBnMaxCtas;
+    if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st)) return e;
+  } else {
+    g.G = g1;
+    if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st)) return e;
+    if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st, true)) return e;
+  }
   g.G = g3;
-  return launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st, true);
+  return launch_plain(k3, g3, args, st, true);
 }
 
 template <typename T, bool RES, bool PRELU>
@@ -166,11 +177,15 @@ static int launch_bn_bwd_fused(const void* dy, const void* x, const void* res, c
   return launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st, true);
 }
 
-extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
-                           float* running_mean, float* running_var, int64_t* num_batches_tracked, float* save_mean,
-                           float* save_invstd, int64_t P, int64_t C, int dtype, int training, float momentum, float eps,
-                           void* ws, size_t ws_bytes, void* stream) {
+static int bn_fwd_impl(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
+                       float* running_mean, float* running_var, int64_t* num_batches_tracked, float* save_mean,
+                       float* save_invstd, int64_t P, int64_t C, int dtype, int training, float momentum, float eps,
+                       void* ws, size_t ws_bytes, void* next_ws, size_t next_ws_bytes, int stats_ready, void* stream) {
   BnGeom g;
+  MSML_REQUIRE(training || (!next_ws && !stats_ready), MSML_EINVAL, "chained BN statistics exist in training mode only");
+  MSML_REQUIRE(!next_ws || (aligned16(next_ws) && next_ws_bytes >= msml_bn_workspace(P, C)), MSML_EWORKSPACE,
+               "next-op BN workspace too small or misaligned");
+  MSML_REQUIRE(next_ws != ws || !next_ws, MSML_EINVAL, "next_ws must not alias ws");
   if (int e = bn_geom(P, C, dtype, &g)) return e;
   MSML_REQUIRE(x && y && save_mean && save_invstd, MSML_EINVAL, "null pointer");
   MSML_REQUIRE(training || (running_mean && running_var), MSML_EINVAL, "eval mode needs running statistics");
@@ -182,6 +197,8 @@ extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float*
   float* part = static_cast<float*>(ws);
   float* part_n = part + (size_t)kBnMaxCtas * 3 * C;
   float* coef = part_n + kBnMaxCtas;
+  float* next_part = static_cast<float*>(next_ws);
+  float* next_part_n = next_part ? next_part + (size_t)kBnMaxCtas * 3 * C : nullptr;
   const double elem = dtype == MSML_F32 ? 4.0 : 2.0;
   if (training) {
     MSML_PROF("bn_fwd", (double)P * C * elem * (res ? 3 : 2), st);
@@ -189,7 +206,8 @@ extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float*
     MSML_BN_DISPATCH(dtype, res != nullptr, prelu != nullptr,
                      (rc = launch_bn_fwd_fused<T, RES, PRELU>(x, res, y, gamma, beta, prelu, running_mean, running_var,
                                                               num_batches_tracked, momentum, eps, save_mean, save_invstd,
-                                                              part, part_n, coef, g, st)));
+                                                              part, part_n, coef, g, st, next_part, next_part_n,
+                                                              stats_ready != 0)));
     return rc;
   }
   bn_eval_coef_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>((int)C, gamma, beta, running_mean, running_var, eps, save_mean,
@@ -207,6 +225,22 @@ extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float*
     MSML_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int msml_bn_fwd(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
+                           float* running_mean, float* running_var, int64_t* num_batches_tracked, float* save_mean,
+                           float* save_invstd, int64_t P, int64_t C, int dtype, int training, float momentum, float eps,
+                           void* ws, size_t ws_bytes, void* stream) {
+  return bn_fwd_impl(x, res, y, gamma, beta, prelu, running_mean, running_var, num_batches_tracked, save_mean, save_invstd, P, C,
+                     dtype, training, momentum, eps, ws, ws_bytes, nullptr, 0, 0, stream);
+}
+
+extern "C" int msml_bn_fwd_ex(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu,
+                              float* running_mean, float* running_var, int64_t* num_batches_tracked, float* save_mean,
+                              float* save_invstd, int64_t P, int64_t C, int dtype, int training, float momentum, float eps,
+                              void* ws, size_t ws_bytes, void* next_ws, size_t next_ws_bytes, int stats_ready, void* stream) {
+  return bn_fwd_impl(x, res, y, gamma, beta, prelu, running_mean, running_var, num_batches_tracked, save_mean, save_invstd, P, C,
+                     dtype, training, momentum, eps, ws, ws_bytes, next_ws, next_ws_bytes, stats_ready, stream);
 }
 
 extern "C" int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gamma, const float* beta,

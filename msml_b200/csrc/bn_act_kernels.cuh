@@ -147,16 +147,48 @@ __device__ __forceinline__ Slab slab_of(const BnGeom& g, int rl) {
   return s;
 }
 
+// Tail of a statistics pass: fold a thread's (sum, sum of squares) over its rows into the CTA's slab (mean, M2) and store
+// them as partial `blockIdx.x` of the [k][C][stride] layout that phase 2 merges.
+template <int VN>
+__device__ __forceinline__ void slab_stats_store(float* s, float* q, float (*red)[kBnThreads * 8], const BnGeom& g, const Slab& sl,
+                                                 int cv, int rl, float* part, float* part_n, int stride) {
+  fold_lanes<VN>(s, g.vpr);
+  fold_lanes<VN>(q, g.vpr);
+  const FoldSlots fs = fold_slots(g.vpr, rl);
+  if (fs.writer) {
+#pragma unroll
+    for (int i = 0; i < VN; ++i) {
+      red[0][fs.slot * g.C + cv * VN + i] = s[i];
+      red[1][fs.slot * g.C + cv * VN + i] = q[i];
+    }
+  }
+  __syncthreads();
+  const float n = (float)(sl.r1 > sl.r0 ? sl.r1 - sl.r0 : 0);
+  for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
+    float ss = 0.f, qq = 0.f;
+    for (int r = 0; r < fs.nslots; ++r) { ss += red[0][r * g.C + c]; qq += red[1][r * g.C + c]; }
+    const float mean = n > 0.f ? ss / n : 0.f;
+    part[(size_t)c * stride + blockIdx.x] = mean;
+    part[(size_t)(g.C + c) * stride + blockIdx.x] = fmaxf(qq - ss * mean, 0.f);   // M2 of this slab
+  }
+  if (threadIdx.x == 0) part_n[blockIdx.x] = n;
+}
+
 // ------------------------------------------------------------------------------------------- forward (training)
 // part layout: [k][C][grid] (channel-major so that phase 2 reads the slabs of a channel coalesced)
-template <typename T, bool RES, bool PRELU, int PHASE>     // PHASE 0: all three phases with grid barriers (cooperative launch);
+// NEXT (phase 3 of the split launches only): y feeds another BatchNorm next (bn3 + skip of one residual unit -> bn1 of the
+// following one, ref iresnet.py:56-67), so the apply pass also leaves the slab statistics of the y it writes (as rounded to T,
+// i.e. exactly what that BN would read) in the NEXT op's workspace, with partial stride kBnMaxCtas and zero counts behind
+// its own grid; that op then starts at phase 2 (msml_bn_fwd_ex stats_ready) and never reads y for statistics.
+template <typename T, bool RES, bool PRELU, int PHASE, bool NEXT = false>   // PHASE 0: all three phases with grid barriers (cooperative launch);
 __global__ void __launch_bounds__(kBnThreads, 4)            // 1 / 2 / 3: that phase only (plain launch, compiled on its own);
                                                             // 4 CTAs / SM: the 592-CTA grid is exactly one wave
 bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ prelu, float* __restrict__ running_mean,
                     float* __restrict__ running_var, long long* __restrict__ nbt, float momentum, float eps,
                     float* __restrict__ save_mean, float* __restrict__ save_invstd, float* part, float* part_n, float* coef,
-                    BnGeom g) {
+                    BnGeom g, float* next_part, float* next_part_n) {
+  static_assert(!NEXT || PHASE == 3, "next-op statistics are emitted by the split phase-3 kernel only");
   constexpr int VN = Vec<T>::N;
   __shared__ float red[2][kBnThreads * 8];   // [2][nslots * C] <= [2][256*8]
   cg::grid_group grid = cg::this_grid();
@@ -194,26 +226,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
 #pragma unroll
       for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
-    fold_lanes<VN>(s, g.vpr);
-    fold_lanes<VN>(q, g.vpr);
-    const FoldSlots fs = fold_slots(g.vpr, rl);
-    if (fs.writer) {
-#pragma unroll
-      for (int i = 0; i < VN; ++i) {
-        red[0][fs.slot * g.C + cv * VN + i] = s[i];
-        red[1][fs.slot * g.C + cv * VN + i] = q[i];
-      }
-    }
-    __syncthreads();
-    const float n = (float)(sl.r1 > sl.r0 ? sl.r1 - sl.r0 : 0);
-    for (int c = threadIdx.x; c < g.C; c += kBnThreads) {
-      float ss = 0.f, qq = 0.f;
-      for (int r = 0; r < fs.nslots; ++r) { ss += red[0][r * g.C + c]; qq += red[1][r * g.C + c]; }
-      const float mean = n > 0.f ? ss / n : 0.f;
-      part[(size_t)c * G + blockIdx.x] = mean;
-      part[(size_t)(g.C + c) * G + blockIdx.x] = fmaxf(qq - ss * mean, 0.f);   // M2 of this slab
-    }
-    if (threadIdx.x == 0) part_n[blockIdx.x] = n;
+    slab_stats_store<VN>(s, q, red, g, sl, cv, rl, part, part_n, G);
   }
   dbg_stamp(g.skip, coef, g.C, 1);
   if (PHASE == 0) grid.sync();
@@ -286,6 +299,9 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     constexpr int U = RES ? 2 : 4;
     const uint4* rv = reinterpret_cast<const uint4*>(res) + cv;
     uint4* yv = reinterpret_cast<uint4*>(y) + cv;
+    float ns[VN], nq[VN];                    // NEXT: sum / sum of squares of the y this thread writes
+#pragma unroll
+    for (int i = 0; i < VN; ++i) { ns[i] = 0.f; nq[i] = 0.f; }
     for (int k = sl.n_it - 1; k >= 0; k -= U) {
       uint4 a[U], b[U];
 #pragma unroll
@@ -308,8 +324,19 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
           if (RES) t += r[i];
           o[i] = PRELU ? (t > 0.f ? t : t * pa[i]) : t;
         }
-        yv[(row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr] = Vec<T>::pack(o);   // re-read by the next conv: default policy
+        const uint4 packed = Vec<T>::pack(o);
+        yv[(row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr] = packed;   // re-read by the next conv: default policy
+        if (NEXT) {
+          Vec<T>::unpack(packed, o);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) { ns[i] += o[i]; nq[i] = fmaf(o[i], o[i], nq[i]); }
+        }
       }
+    }
+    if (NEXT) {
+      slab_stats_store<VN>(ns, nq, red, g, sl, cv, rl, next_part, next_part_n, kBnMaxCtas);
+      if (blockIdx.x == 0)
+        for (int b = (int)gridDim.x + (int)threadIdx.x; b < kBnMaxCtas; b += kBnThreads) next_part_n[b] = 0.f;
     }
   }
   dbg_stamp(g.skip, coef, g.C, 5);

@@ -3,6 +3,7 @@ owns device memory and streams and supplies the autograd graph; every op below i
 hand-written sm_100a kernels from libmsml_b200.so.  No op has a PyTorch/CPU fallback.
 """
 import ctypes
+import os
 
 import torch
 
@@ -212,7 +213,8 @@ def fm_mask(yf, m, act="sigmoid", arith="mul"):
 # --------------------------------------------------------------------------------------------
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, prelu, res, running_mean, running_var, nbt, training, momentum, eps, fork=False):
+    def forward(ctx, x, gamma, beta, prelu, res, running_mean, running_var, nbt, training, momentum, eps, fork=False,
+                emit_next=False, pre_ws=None):
         require_cuda(x, gamma, beta, prelu, res)
         lib = load()
         B, C, H, W = x.shape
@@ -222,10 +224,19 @@ class _BNAct(torch.autograd.Function):
         y = torch.empty_like(x_d)
         stats = torch.empty((2, C), dtype=torch.float32, device=x.device)
         ws_bytes = lib.msml_bn_workspace(P, C)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        check(lib.msml_bn_fwd(_ptr(x_d), _ptr(res_d), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(prelu), _ptr(running_mean),
-                              _ptr(running_var), _ptr(nbt) if training else None, _ptr(stats[0]), _ptr(stats[1]), P, C,
-                              dtype_code(x_d.dtype), int(training), float(momentum), float(eps), _ptr(ws), ws_bytes, stream_ptr()))
+        # chained statistics (msml_bn_fwd_ex): pre_ws is this op's workspace, already holding the slab statistics of x
+        # (left there by the op that wrote x); next_ws receives those of y for the BatchNorm that consumes it
+        ws = pre_ws if pre_ws is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        next_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if emit_next else None
+        if emit_next or pre_ws is not None:
+            check(lib.msml_bn_fwd_ex(_ptr(x_d), _ptr(res_d), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(prelu), _ptr(running_mean),
+                                     _ptr(running_var), _ptr(nbt) if training else None, _ptr(stats[0]), _ptr(stats[1]), P, C,
+                                     dtype_code(x_d.dtype), int(training), float(momentum), float(eps), _ptr(ws), ws_bytes,
+                                     _ptr(next_ws), ws_bytes if emit_next else 0, int(pre_ws is not None), stream_ptr()))
+        else:
+            check(lib.msml_bn_fwd(_ptr(x_d), _ptr(res_d), _ptr(y), _ptr(gamma), _ptr(beta), _ptr(prelu), _ptr(running_mean),
+                                  _ptr(running_var), _ptr(nbt) if training else None, _ptr(stats[0]), _ptr(stats[1]), P, C,
+                                  dtype_code(x_d.dtype), int(training), float(momentum), float(eps), _ptr(ws), ws_bytes, stream_ptr()))
         ctx.save_for_backward(x_d, res_d if prelu is not None else None, gamma, beta, prelu, stats)
         ctx.cfg = (training, res is not None)
         ctx.params = (gamma, beta, prelu)          # the Parameter objects themselves (for the direct-gradient path)
@@ -233,17 +244,22 @@ class _BNAct(torch.autograd.Function):
         ctx.set_materialize_grads(False)           # an unused output arrives as None in backward, not as a zero tensor
         if fork:                                   # second output: x itself, for the skip branch (see bn_act_fork)
             return y, x_d.view_as(x_d)
+        if emit_next:                              # second output: the next BatchNorm's workspace (no gradient)
+            ctx.mark_non_differentiable(next_ws)
+            return y, next_ws
         return y
 
     @staticmethod
     def backward(ctx, dy, dskip=None):
         x, res, gamma, beta, prelu, stats = ctx.saved_tensors
         training, has_res = ctx.cfg
+        if not ctx.fork:                           # a second output that is not the skip branch (next_ws) has no gradient
+            dskip = None
         lib = load()
         B, C, H, W = x.shape
         P = B * H * W
         if dy is None:                             # only the skip branch carried a gradient (or nothing did)
-            return (dskip,) + (None,) * 11
+            return (dskip,) + (None,) * 13
         dy_d = _dense_like(x, dy)
         dadd = _dense_like(x, dskip) if dskip is not None else None
         dx = torch.empty_like(x)
@@ -267,15 +283,35 @@ class _BNAct(torch.autograd.Function):
                               g_ptrs[2], P, C, dtype_code(x.dtype), int(training), int(direct), _ptr(ws), ws_bytes, stream_ptr()))
         d_res = dres if both else (dy_d if has_res else None)
         if direct:
-            return dx, None, None, None, d_res, None, None, None, None, None, None, None
+            return (dx, None, None, None, d_res) + (None,) * 9
         dprelu = grads[2] if prelu is not None else None
-        return dx, grads[0], grads[1], dprelu, d_res, None, None, None, None, None, None, None
+        return (dx, grads[0], grads[1], dprelu, d_res) + (None,) * 9
 
 
 def _direct_grad(p):
     """True when the engine has marked ``p`` as living in its flat gradient buffer (see engine.TrainStep)."""
     return (getattr(p, "_msml_direct_grad", False) and p.grad is not None and p.grad.dtype == torch.float32
             and _is_dense(p.grad) and p.grad.data_ptr() % 16 == 0)
+
+
+_CHAIN_ATTR = "_msml_bn_next_ws"
+
+
+def _chain_enabled():
+    """Chained BN statistics (msml_bn_fwd_ex) need the split launches; MSML_BN_CHAIN=0 turns them off (A/B)."""
+    return os.environ.get("MSML_BN_CHAIN", "1") != "0" and os.environ.get("MSML_BN_FUSED", "0") in ("", "0")
+
+
+def _take_chained_ws(x, bn):
+    """The workspace a producer (bn_act(..., emit_next_stats=True)) attached to ``x``: the slab statistics of exactly this
+    tensor, valid for one training-mode BatchNorm over it.  Consumed (detached from ``x``) here."""
+    ws = getattr(x, _CHAIN_ATTR, None)
+    if ws is None:
+        return None
+    delattr(x, _CHAIN_ATTR)
+    if not bn.training or x._version != ws[1]:
+        return None                                # eval mode, or x was written to since: fall back to reading x
+    return ws[0]
 
 
 def bn_act_fork(x, bn, prelu=None):
@@ -287,7 +323,7 @@ def bn_act_fork(x, bn, prelu=None):
     _check_bn_args(x, bn, prelu)
     a = prelu.weight if prelu is not None else None
     return _BNAct.apply(x, bn.weight, bn.bias, a, None, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                        bn.training, bn.momentum, bn.eps, True)
+                        bn.training, bn.momentum, bn.eps, True, False, _take_chained_ws(x, bn))
 
 
 def _check_bn_args(x, bn, prelu):
@@ -299,20 +335,25 @@ def _check_bn_args(x, bn, prelu):
         raise ValueError("bn_act: PReLU must have one slope per channel")
 
 
-def bn_act(x, bn, prelu=None, res=None):
+def bn_act(x, bn, prelu=None, res=None, emit_next_stats=False):
     """y = prelu(bn(x) [+ res]) with ``bn`` an nn.BatchNorm2d and ``prelu`` an nn.PReLU (or None): statistics,
-    normalisation, residual add and activation in two fused passes (forward) / two (backward)."""
-    if x.dim() != 4:
-        raise ValueError("bn_act expects a 4-D (B, C, H, W) tensor")
-    if bn.momentum is None or not bn.track_running_stats or not bn.affine:
-        raise RuntimeError("bn_act supports affine BatchNorm2d with running statistics and a fixed momentum")
+    normalisation, residual add and activation in two fused passes (forward) / two (backward).
+
+    emit_next_stats: y is the input of ANOTHER training-mode BatchNorm next (the end of one residual unit feeding the next
+    unit's bn1, ref iresnet.py:56-67): the apply pass also leaves the batch statistics of y in that op's workspace, which
+    travels with y; the next bn_act / bn_act_fork over y picks it up and skips its own statistics pass."""
+    _check_bn_args(x, bn, prelu)
     a = prelu.weight if prelu is not None else None
-    if a is not None and a.numel() != x.shape[1]:
-        raise ValueError("bn_act: PReLU must have one slope per channel")
     if res is not None and res.dtype != x.dtype:
         res = res.to(x.dtype)
-    return _BNAct.apply(x, bn.weight, bn.bias, a, res, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                        bn.training, bn.momentum, bn.eps)
+    emit = bool(emit_next_stats) and bn.training and _chain_enabled()
+    out = _BNAct.apply(x, bn.weight, bn.bias, a, res, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                       bn.training, bn.momentum, bn.eps, False, emit, _take_chained_ws(x, bn))
+    if emit:
+        y, next_ws = out
+        setattr(y, _CHAIN_ATTR, (next_ws, y._version))
+        return y
+    return out
 
 
 # --------------------------------------------------------------------------------------------
@@ -776,7 +817,12 @@ class _GradMarker(torch.autograd.Function):
 def grad_marker(x, tag):
     if _MARKER_CALLBACK is None or not x.requires_grad or not torch.is_grad_enabled():
         return x
-    return _GradMarker.apply(x, tag)
+    y = _GradMarker.apply(x, tag)
+    ws = getattr(x, _CHAIN_ATTR, None)          # same values, same version counter: chained BN statistics stay valid
+    if ws is not None:
+        delattr(x, _CHAIN_ATTR)
+        setattr(y, _CHAIN_ATTR, (ws[0], y._version))
+    return y
 
 
 def launch_count():

@@ -38,18 +38,28 @@ static size_t emu_bn_ws_floats(int C) { return (size_t)kBnMaxCtas * 3 * C + kBnM
 
 template <typename T, bool RES, bool PRELU>
 static void fwd3(const void* x, const void* res, void* y, const float* gamma, const float* beta, const float* prelu, float* rm, float* rv,
-                 long long* nbt, float momentum, float eps, float* mean, float* invstd, float* ws, BnGeom g, int G1, int G3) {
+                 long long* nbt, float momentum, float eps, float* mean, float* invstd, float* ws, BnGeom g, int G1, int G3,
+                 float* next_ws = nullptr, bool stats_ready = false) {
   float* part = ws;
   float* part_n = part + (size_t)kBnMaxCtas * 3 * g.C;
   float* coef = part_n + kBnMaxCtas;
+  float* npart = next_ws;                                        // msml_bn_fwd_ex: statistics of y for the BN that follows
+  float* npart_n = next_ws ? next_ws + (size_t)kBnMaxCtas * 3 * g.C : nullptr;
   const T* xp = static_cast<const T*>(x);
   const T* rp = static_cast<const T*>(res);
   T* yp = static_cast<T*>(y);
-  g.G = G1;
-  emu_launch(dim3(G1), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 1>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g); });
-  emu_launch(dim3(g.C), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 2>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g); });
+  if (stats_ready) {                                             // the producer's apply pass left the slab statistics in ws
+    g.G = kBnMaxCtas;
+  } else {
+    g.G = G1;
+    emu_launch(dim3(G1), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 1>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g, npart, npart_n); });
+  }
+  emu_launch(dim3(g.C), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 2>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g, npart, npart_n); });
   g.G = G3;
-  emu_launch(dim3(G3), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 3>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g); });
+  if (next_ws)
+    emu_launch(dim3(G3), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 3, true>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g, npart, npart_n); });
+  else
+    emu_launch(dim3(G3), kBnThreads, [&] { bn_fwd_fused_kernel<T, RES, PRELU, 3>(xp, rp, yp, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, part, part_n, coef, g, npart, npart_n); });
 }
 
 template <typename T, bool RES, bool PRELU>
@@ -87,6 +97,31 @@ extern "C" int emu_bn_fwd(const void* x, const void* res, void* y, const float* 
   std::vector<float> ws(emu_bn_ws_floats((int)C));
   BN_DISPATCH(dtype, res != nullptr, prelu != nullptr,
               (fwd3<T, RES, PRELU>(x, res, y, gamma, beta, prelu, rm, rv, nbt, momentum, eps, mean, invstd, ws.data(), g, G1, G3)));
+  return 0;
+}
+
+// Two chained ops as the residual trunk runs them: y1 = bn_a(x) + res (its apply pass emits the statistics of y1), then
+// y2 = prelu(bn_b(y1)) starting at the merge.  G3a is the producer's apply grid, G3b the consumer's.
+extern "C" int emu_bn_fwd_chain(const void* x, const void* res, void* y1, void* y2, const float* gamma_a, const float* beta_a,
+                                const float* gamma_b, const float* beta_b, const float* prelu_b, float* rm_b, float* rv_b,
+                                long long* nbt_b, float* mean_b, float* invstd_b, int64_t P, int64_t C, int dtype, float momentum,
+                                float eps, int G1, int G3a, int G3b) {
+  BnGeom g;
+  if (!emu_bn_geom(P, C, dtype, &g) || G1 < 1 || G3a < 1 || G3b < 1 || G1 > kBnMaxCtas || G3a > kBnMaxCtas || G3b > kBnMaxCtas) return 1;
+  std::vector<float> ws_a(emu_bn_ws_floats((int)C)), ws_b(emu_bn_ws_floats((int)C), std::nanf(""));   // stale slots must not matter
+  std::vector<float> mean_a(C), invstd_a(C);
+  if (dtype == MSML_F32) {
+    fwd3<float, true, false>(x, res, y1, gamma_a, beta_a, nullptr, nullptr, nullptr, nullptr, momentum, eps, mean_a.data(), invstd_a.data(),
+                             ws_a.data(), g, G1, G3a, ws_b.data());
+    if (prelu_b) fwd3<float, false, true>(y1, nullptr, y2, gamma_b, beta_b, prelu_b, rm_b, rv_b, nbt_b, momentum, eps, mean_b, invstd_b, ws_b.data(), g, G1, G3b, nullptr, true);
+    else fwd3<float, false, false>(y1, nullptr, y2, gamma_b, beta_b, nullptr, rm_b, rv_b, nbt_b, momentum, eps, mean_b, invstd_b, ws_b.data(), g, G1, G3b, nullptr, true);
+  } else {
+    using T = __nv_bfloat16;
+    fwd3<T, true, false>(x, res, y1, gamma_a, beta_a, nullptr, nullptr, nullptr, nullptr, momentum, eps, mean_a.data(), invstd_a.data(),
+                         ws_a.data(), g, G1, G3a, ws_b.data());
+    if (prelu_b) fwd3<T, false, true>(y1, nullptr, y2, gamma_b, beta_b, prelu_b, rm_b, rv_b, nbt_b, momentum, eps, mean_b, invstd_b, ws_b.data(), g, G1, G3b, nullptr, true);
+    else fwd3<T, false, false>(y1, nullptr, y2, gamma_b, beta_b, nullptr, rm_b, rv_b, nbt_b, momentum, eps, mean_b, invstd_b, ws_b.data(), g, G1, G3b, nullptr, true);
+  }
   return 0;
 }
 

@@ -287,12 +287,55 @@ def test_emulated_kernels_are_clean_under_sanitizers(sanitizer_builds, tag):
 
 
 # ------------------------------------------------------------------------------------------------ fused BN (+res) (+PReLU) (GPU-verified)
+kBN_MAX_CTAS = 148 * 4          # csrc/bn_act_kernels.cuh kBnMaxCtas
 @pytest.fixture(scope="module")
 def emu_bn(tmp_path_factory):
     lib = build_emu(tmp_path_factory, "emu_bn.cpp")
     lib.emu_bn_fwd.argtypes = [c_p] * 11 + [c_i64, c_i64, c_int, c_f, c_f, c_int, c_int]
     lib.emu_bn_bwd.argtypes = [c_p] * 14 + [c_i64, c_i64, c_int, c_int, c_int, c_int, c_int]
+    lib.emu_bn_fwd_chain.argtypes = [c_p] * 14 + [c_i64, c_i64, c_int, c_f, c_f, c_int, c_int, c_int]
     return lib
+
+
+@pytest.mark.parametrize("P,C,G1,G3a,G3b,prelu,dtype", [
+    (162, 32, 3, 5, 4, False, BF16), (401, 64, 7, 4, 9, True, BF16), (98, 256, 2, 2, 3, False, BF16),
+    (5, 16, 9, 7, 2, True, BF16),                # empty producer slabs: zero-weight partials
+    (2, 8, 1, 1, 1, False, BF16), (37, 4, 2, 3, 2, True, F32),
+    (1500, 64, 40, kBN_MAX_CTAS, 17, False, BF16),   # producer grid = the whole partial stride
+])
+def test_bn_chained_statistics(emu_bn, P, C, G1, G3a, G3b, prelu, dtype):
+    """msml_bn_fwd_ex: the apply pass of `bn_a(x) + res` (ref iresnet.py:66-67, the end of one residual unit) also emits the
+    slab statistics of its output, and the next unit's `bn1` (iresnet.py:57) starts at the merge.  The second op must agree
+    with the oracle run on the first op's ROUNDED output, statistics included, although it never read that tensor for them;
+    the consumer workspace starts out as NaN, so slots behind the producer's grid must carry zero weight."""
+    rng = np.random.default_rng(7 * P + C)
+    q = (lambda a: from_bf16_bits(to_bf16_bits(a)).reshape(a.shape)) if dtype == BF16 else (lambda a: a.astype(np.float32))
+    enc = (lambda t: to_bf16_bits(t).reshape(t.shape)) if dtype == BF16 else (lambda t: np.ascontiguousarray(t, np.float32))
+    dec = (lambda b: from_bf16_bits(b).reshape(b.shape)) if dtype == BF16 else (lambda b: b)
+    ptr = lambda t: t.ctypes.data if t is not None else None
+    x = q(rng.normal(-0.5, 1.5, size=(P, C)).astype(np.float32))
+    r = q(rng.normal(0.7, 1.0, size=(P, C)).astype(np.float32))
+    ga, ba = rng.uniform(0.5, 1.5, C).astype(np.float32), rng.uniform(-0.5, 0.5, C).astype(np.float32)
+    gb, bb = rng.uniform(0.5, 1.5, C).astype(np.float32), rng.uniform(-0.5, 0.5, C).astype(np.float32)
+    a = rng.uniform(0.1, 0.4, C).astype(np.float32) if prelu else None
+    rm0, rv0 = rng.normal(size=C).astype(np.float32), rng.uniform(0.5, 2.0, C).astype(np.float32)
+    xb, rb = enc(x), enc(r)
+    y1b, y2b = np.zeros_like(xb), np.zeros_like(xb)
+    rm, rv, nbt = rm0.copy(), rv0.copy(), np.array([2], np.int64)
+    mean, invstd = np.zeros(C, np.float32), np.zeros(C, np.float32)
+    assert emu_bn.emu_bn_fwd_chain(ptr(xb), ptr(rb), ptr(y1b), ptr(y2b), ptr(ga), ptr(ba), ptr(gb), ptr(bb), ptr(a), ptr(rm), ptr(rv),
+                                   ptr(nbt), ptr(mean), ptr(invstd), P, C, dtype, 0.1, 1e-5, G1, G3a, G3b) == 0
+    y1_want, _ = obn.bn_act_fwd(x, ga, ba, None, r, True, np.zeros(C, np.float32), np.ones(C, np.float32))
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == BF16 else dict(rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(dec(y1b), y1_want, **tol)
+    y1 = dec(y1b).astype(np.float32)                                    # what the unchained second op would have read
+    y2_want, st = obn.bn_act_fwd(y1, gb, bb, a, None, True, rm0, rv0)
+    np.testing.assert_allclose(mean, st["mean"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(invstd, st["invstd"], rtol=2e-5)
+    np.testing.assert_allclose(rm, st["running_mean"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(rv, st["running_var"], rtol=2e-5)
+    np.testing.assert_allclose(dec(y2b), y2_want, **tol)
+    assert nbt[0] == 3
 
 
 @pytest.mark.parametrize("P,C,G1,G3,prelu,res,dtype", [

@@ -379,6 +379,79 @@ def test_bn_act_fork_fuses_the_skip_gradient(dtype):
     assert_close(host(x.grad), host(d2), 0.0, atol=0.0, what="skip only")
 
 
+@pytest.mark.parametrize("C,H,B", [(64, 14, 5), (128, 7, 6), (512, 7, 4), (64, 56, 32)])
+@pytest.mark.parametrize("consumer", ["fork", "plain_prelu"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bn_chained_statistics_match_unchained(C, H, B, consumer, dtype):
+    """msml_bn_fwd_ex: `bn3(out) + identity` of one residual unit hands the batch statistics of its output to the next
+    unit's bn1 (ref iresnet.py:56-67).  Outputs, saved / running statistics and every gradient must equal the unchained
+    sequence (same kernels, statistics pass included) up to the fp32 summation order of the slab partials."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(C + H)
+    mk = lambda: torch.randn(B, C, H, H, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    out0, skip0, d1, d2 = mk() * 1.7 + 0.3, mk(), mk(), mk()
+    res = {}
+    for chained in (False, True):
+        torch.manual_seed(1)
+        bn_a = torch.nn.BatchNorm2d(C, eps=1e-5).cuda().train()
+        bn_b = torch.nn.BatchNorm2d(C, eps=1e-5).cuda().train()
+        pr = torch.nn.PReLU(C).cuda()
+        with torch.no_grad():
+            for bn in (bn_a, bn_b):
+                bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+            pr.weight.uniform_(0.1, 0.4)
+        out, skip = out0.clone().requires_grad_(True), skip0.clone().requires_grad_(True)
+        y1 = ops.bn_act(out, bn_a, None, skip, emit_next_stats=chained)
+        assert hasattr(y1, ops._CHAIN_ATTR) == chained
+        if consumer == "fork":
+            y2, xs = ops.bn_act_fork(y1, bn_b)
+            loss = (y2.float() * d1.float()).sum() + (xs.float() * d2.float()).sum()
+        else:
+            y2 = ops.bn_act(y1, bn_b, pr)
+            loss = (y2.float() * d1.float()).sum()
+        assert not hasattr(y1, ops._CHAIN_ATTR)                 # consumed exactly once
+        loss.backward()
+        res[chained] = dict(y1=host(y1), y2=host(y2), dout=host(out.grad), dskip=host(skip.grad), rm=host(bn_b.running_mean),
+                            rv=host(bn_b.running_var), dg_a=host(bn_a.weight.grad), dg_b=host(bn_b.weight.grad),
+                            db_b=host(bn_b.bias.grad), nbt=int(bn_b.num_batches_tracked))
+    assert np.array_equal(res[True]["y1"], res[False]["y1"])    # the producer's own output does not change at all
+    assert res[True]["nbt"] == res[False]["nbt"] == 1
+    lo = dtype == torch.bfloat16
+    assert_close(res[True]["rm"], res[False]["rm"], 1e-5, atol=1e-6, what="running_mean")
+    assert_close(res[True]["rv"], res[False]["rv"], 1e-5, atol=1e-6, what="running_var")
+    for k in ("y2", "dout", "dskip", "dg_a", "dg_b", "db_b"):
+        assert_close(res[True][k], res[False][k], 1e-2 if lo else 2e-5, atol_frac=4e-3 if lo else 1e-5, what=k)
+
+
+def test_bn_chained_statistics_are_dropped_when_stale():
+    """The attached statistics describe one tensor at one version: an in-place write, eval mode or MSML_BN_CHAIN=0
+    must fall back to reading the tensor."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(2)
+    bn_a = torch.nn.BatchNorm2d(64).cuda().train()
+    bn_b = torch.nn.BatchNorm2d(64).cuda().train()
+    x = torch.randn(4, 64, 9, 9, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y1 = ops.bn_act(x, bn_a, emit_next_stats=True)
+        assert hasattr(y1, ops._CHAIN_ATTR)
+        y1.mul_(3.0).add_(1.0)                                   # the statistics on y1 are now wrong
+        y2 = ops.bn_act(y1, bn_b).float()
+    assert y2.mean((0, 2, 3)).abs().max().item() < 2e-2
+    assert (y2.var((0, 2, 3), unbiased=False) - 1).abs().max().item() < 3e-2
+    with torch.no_grad():
+        y1 = ops.bn_act(x, bn_a, emit_next_stats=True)
+        bn_b.eval()
+        want = torch.nn.functional.batch_norm(y1.float(), bn_b.running_mean, bn_b.running_var, bn_b.weight, bn_b.bias, False, 0.0, bn_b.eps)
+        got = ops.bn_act(y1, bn_b).float()
+    assert not hasattr(y1, ops._CHAIN_ATTR)
+    assert_close(host(got), host(want), 2e-2, atol=2e-2, what="eval consumer ignores batch statistics")
+    bn_a.eval()
+    with torch.no_grad():
+        assert not hasattr(ops.bn_act(x, bn_a, emit_next_stats=True), ops._CHAIN_ATTR)     # eval producer emits nothing
+
+
 def test_bn_cooperative_single_launch_matches_default(tmp_path):
     """MSML_BN_FUSED=1 (one cooperative launch with two grid barriers, kept for the measured comparison) must compute the
     same BN forward / backward as the default three-launch path.  The mode is read once per process, so the
