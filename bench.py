@@ -445,7 +445,7 @@ def run_train(args, rank, local_rank, world):
     import torch.distributed as dist
     from msml_b200 import _lib, ops
     from msml_b200.backbones import MSML
-    from msml_b200.engine import TrainStep, broadcast_parameters
+    from msml_b200.engine import FlatSGD, TrainStep, broadcast_parameters
     from msml_b200.headers import ArcFace, PartialFC, PartialFCSGD
 
     lib = _lib.load()
@@ -459,7 +459,11 @@ def run_train(args, rank, local_rank, world):
     broadcast_parameters(net)
     pfc = PartialFC(rank, local_rank, world, BATCH, False, ArcFace(S, M), NUM_CLASSES, sample_rate=1.0, embedding_size=512)
     lr = 0.1 * BATCH * world / 512
-    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
+    # the backbone optimizer (ref train.py:186-191: SGD over backbone.parameters(), momentum 0.9, wd 5e-4) as ONE kernel over
+    # flat parameter / momentum / gradient buffers that also writes next step's bf16 shadow weights (engine.FlatSGD)
+    bb_params = [p for p in net.parameters() if p.requires_grad]
+    opt = (torch.optim.SGD(bb_params, lr=lr, momentum=0.9, weight_decay=5e-4, fused=True) if args.stock_backbone_sgd
+           else FlatSGD(bb_params, lr=lr, momentum=0.9, weight_decay=5e-4))
     # the head's optimizer (ref train.py:188-191: SGD over module_partial_fc.parameters(), momentum 0.9, wd 5e-4) as ONE
     # kernel on the shard rows that also emits the next step's normalised bf16 centres
     opt_pfc = (torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True) if args.stock_head_sgd
@@ -552,6 +556,8 @@ def run_train(args, rank, local_rank, world):
                    "global_batch": BATCH * world,
                    "parallelism": "dp%d backbone (flat-gradient NCCL all-reduce) + class-sharded head" % world,
                    "execution": "eager" if args.eager else "whole step captured in one CUDA graph, two streams (wgrad + OSB on a side stream) (msml_b200.engine.TrainStep)",
+                   "optimizers": {"backbone": "torch.optim.SGD(fused=True)" if args.stock_backbone_sgd else "engine.FlatSGD (one kernel, emits bf16 shadow weights)",
+                                  "head": "torch.optim.SGD(fused=True) + update()" if args.stock_head_sgd else "headers.PartialFCSGD"},
                    "l2": "per-step working set (activations, GBs) >> 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(args.steps * BATCH * world / (ms_e2e * 1e-3), 1), "unit": "imgs/s",
                 "h2d_bytes_per_step": imgs_h[0].numel() * 4 + labels_h[0].numel() * 8, "d2h_bytes_per_step": 4,
@@ -726,6 +732,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="head workload only: per-rank batch (1024 on one GPU reproduces the "
                     "per-rank GEMM shapes of the 8-GPU config-4 run: B_tot=1024 rows against a 125,000-class shard)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per step of the CPU arm (a bounded sample of the 128/GPU workload)")
+    ap.add_argument("--stock-backbone-sgd", action="store_true", help="train workload: torch.optim.SGD(fused=True) for the backbone instead "
+                    "of engine.FlatSGD (one flat kernel + emitted bf16 shadow weights)")
     ap.add_argument("--stock-head-sgd", action="store_true", help="train workload: torch.optim.SGD(fused=True) + update() for the class centres "
                     "instead of headers.PartialFCSGD")
     ap.add_argument("--exact-head-grad", action="store_true", help="with headers.PartialFCSGD: keep the normalise-backward projection in the "

@@ -185,6 +185,21 @@ int msml_bn_bwd(const void* dy, const void* x, const void* res, const float* gam
 int msml_accum_bf16_multi(int nseg, float* const* dst, const void* const* src, const int64_t* n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Backbone optimizer of the training step: ref train.py:186-191 (torch.optim.SGD over backbone.parameters(), momentum 0.9,
+ * weight decay 5e-4), stepped at train.py:299 after clip_grad_norm_(…, 5).  All parameters, momentum buffers and
+ * gradients are views of three flat fp32 buffers with identical offsets (engine.FlatSGD lays them out), n elements each,
+ * n a multiple of 4, padding lanes zero:
+ *     g = grad / *grad_scale_dev (skipped when null) + weight_decay * w;   m = momentum * m + g;
+ *     w -= *lr_dev * (nesterov ? g + momentum * m : m);                    shadow_bf16 (nullable) = bf16(w)
+ * i.e. torch.optim.SGD with dampening 0 (a zero momentum buffer makes the first step m = g, as torch's does), with the
+ * GradScaler-style division torch's fused SGD applies (the engine passes clip coefficient x world size there), plus the
+ * bf16 copy of the new weights that the next step's autocast convolutions read.  One launch, HBM-bound
+ * (20 B read/written per element + 2 B shadow).  lr and grad_scale are DEVICE scalars: capturable in a CUDA graph.
+ * ------------------------------------------------------------------------------------------ */
+int msml_sgd_flat(float* weight, float* momentum_buf, const float* grad, void* shadow_bf16, int64_t n, const float* lr_dev,
+                  const float* grad_scale_dev, float momentum, float weight_decay, int nesterov, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K-B  DAP head of the segmentation branch + argmax mask.
  *   ref backbones/osb/unet.py:158-161,223 (PixelShuffle(k)+AvgPool2d(k) == mean over k*k channel
  *   groups), train.py:357 / eval/qeval_mxnet.py:347 (final_seg[b].max(0)[1]).

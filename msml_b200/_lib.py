@@ -55,6 +55,7 @@ SIGNATURES = {
                                     ctypes.c_float, c_int, c_p, c_p, c_p]),
     "msml_pfc_sgd_update_raw": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                         ctypes.c_float, c_int, c_p, c_p, c_p]),
+    "msml_sgd_flat": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_p, c_p, ctypes.c_float, ctypes.c_float, c_int, c_p]),
     "msml_accum_bf16_multi": (c_int, [c_int, c_p, c_p, c_p, c_p]),
     "msml_dap_fwd": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_p]),
     "msml_dap_bwd": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_p]),

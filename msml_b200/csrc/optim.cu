@@ -1,12 +1,15 @@
 // Gradient plumbing kernels of the training step (SURVEY.md 8f-2 neighbourhood).
 //   msml_pfc_sgd_update   : fused momentum SGD + weight decay + in-place write-back (+ next normalised bf16 centres) on the sampled
 //     rows of the PartialFC shard; kernel and algorithm in pfc_sgd_kernels.cuh.
+//   msml_sgd_flat         : momentum SGD + weight decay + gradient scale over one flat fp32 buffer, emitting the bf16 shadow weights of
+//     the next step; kernel and algorithm in sgd_flat_kernels.cuh.
 //   msml_accum_bf16_multi : dst_f32[i] += float(src_bf16[i]) for up to MSML_ACCUM_MAX_SEGMENTS tensors in ONE launch.
 //     The bf16 weight gradients cuDNN returns are added into the fp32 flat-gradient views of engine.TrainStep after
 //     the backward pass: one launch instead of one mixed-dtype ATen add (a non-vectorised kernel) per weight.
 #include "common.cuh"
 #include "accum_kernels.cuh"
 #include "pfc_sgd_kernels.cuh"
+#include "sgd_flat_kernels.cuh"
 
 using namespace msml;
 
@@ -77,4 +80,26 @@ extern "C" int msml_pfc_sgd_update_raw(float* weight, float* weight_mom, const f
                                        void* stream) {
   return pfc_sgd_impl(weight, weight_mom, dwn, index, n_s, num_local, D, lr_dev, lr, momentum, weight_decay, dampening, nesterov,
                       wn_bf16, inv_norm, stream, true);
+}
+
+extern "C" int msml_sgd_flat(float* weight, float* momentum_buf, const float* grad, void* shadow_bf16, int64_t n, const float* lr_dev,
+                             const float* grad_scale_dev, float momentum, float weight_decay, int nesterov, void* stream) {
+  MSML_REQUIRE(n >= 0 && n % 4 == 0, MSML_EINVAL, "flat SGD: n=%lld must be a non-negative multiple of 4", (long long)n);
+  if (n == 0) return 0;
+  MSML_REQUIRE(weight && grad && lr_dev && (momentum == 0.f || momentum_buf), MSML_EINVAL, "null pointer");
+  MSML_REQUIRE(!nesterov || momentum > 0.f, MSML_EINVAL, "nesterov needs momentum > 0");
+  MSML_REQUIRE(aligned16(weight) && aligned16(momentum_buf) && aligned16(grad) && aligned16(shadow_bf16), MSML_EALIGN,
+               "weight, momentum, grad and shadow must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n4 = n / 4;
+  const int64_t per_cta = (int64_t)kFlatSgdThreads * kFlatSgdUnroll;
+  int64_t blocks = (n4 + per_cta - 1) / per_cta;
+  const int64_t cap = (int64_t)num_sms() * 8;                 // one resident wave of 8 CTAs per SM, grid-stride beyond
+  if (blocks > cap) blocks = cap;
+  FlatSgdParams p{momentum, weight_decay, nesterov};
+  MSML_PROF("sgd_flat", (double)n * ((momentum != 0.f ? 20.0 : 12.0) + (shadow_bf16 ? 2.0 : 0.0)), st);
+  sgd_flat_kernel<<<(unsigned)blocks, kFlatSgdThreads, 0, st>>>(weight, momentum_buf, grad, static_cast<__nv_bfloat16*>(shadow_bf16), n4,
+                                                             lr_dev, grad_scale_dev, p);
+  MSML_LAUNCH_CHECK();
+  return 0;
 }

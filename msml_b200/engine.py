@@ -13,6 +13,8 @@ and runs it the B200 way:
     mean ride in the fused SGD's grad_scale;
   * conv / linear weights have bf16 shadows refreshed by one multi-tensor copy; their bf16 gradients are added into the
     flat buffer by one launch; BN / PReLU gradients are added by the BN backward kernels themselves;
+  * with ``FlatSGD`` (flat_sgd.py) as the backbone optimizer the parameters and momentum buffers are flat too and the
+    whole backbone update, clip scale included, is ONE kernel that also writes next step's bf16 shadow weights;
   * two streams: convolution weight gradients (off the critical path) and the occlusion-segmentation branch (not needed
     before the first FM operator) run on a side stream and fill the SMs that the latency-bound BN kernels leave idle;
   * after three eager warm-up steps the whole step — cuDNN convolutions, this library's kernels, NCCL collectives, the
@@ -30,6 +32,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import ops
+from .flat_sgd import FlatSGD  # noqa: F401  (re-exported: the engine's backbone optimizer)
 
 
 class TrainStep:
@@ -48,6 +51,7 @@ class TrainStep:
         self.graph = None
         self._used = None
         self._shadow_src, self._shadow_dst = [], []
+        self._emitted, self._emitted_versions = [], None      # weights whose bf16 shadows the optimizer kernel writes (FlatSGD)
         self._copy_stream, self._has_staged = None, False
         # convolution weight gradients run on a second stream and fill the idle SMs under the latency-bound BN kernels
         self.wgrad_side_stream = wgrad_side_stream
@@ -75,6 +79,10 @@ class TrainStep:
             p._msml_direct_grad = True          # fused kernels may add their parameter gradients into p.grad themselves
             off += pad4(p.numel())
         self._used = used
+        if hasattr(self.opt_backbone, "bind_flat"):
+            # FlatSGD: parameters and momentum buffers move into flat buffers with the gradients' offsets, and the whole
+            # optimizer step (+ next step's bf16 shadow weights) becomes one kernel
+            self.opt_backbone.bind_flat(used, self.flat)
         # element ranges of the flat buffer per bucket (bucket i is complete when the backward pass crosses marker i)
         self._bucket_ranges, lo = {}, 0
         for tag, cnt in self._buckets:
@@ -121,21 +129,42 @@ class TrainStep:
     def share_state_from(self, other):
         """Make this TrainStep operate on `other`'s flat gradient buffer, buckets and shadow weights (bench.py runs an
         eager twin of the captured step to time individual launches)."""
-        for k in ("flat", "_used", "_buckets", "_bucket_ranges", "_bucket_start", "_shadow_src", "_shadow_dst"):
+        for k in ("flat", "_used", "_buckets", "_bucket_ranges", "_bucket_start", "_shadow_src", "_shadow_dst", "_emitted",
+                  "_emitted_versions"):
             setattr(self, k, getattr(other, k))
 
     def _install_shadows(self):
         """bf16 shadow of every conv / linear weight that runs under autocast (ops._ShadowWeight): refreshed by ONE
         multi-tensor copy per step instead of one cast kernel per layer, and gradients flow into the flat buffer."""
         self._shadow_src, self._shadow_dst = [], []
+        self._emitted, self._emitted_versions = [], None
         if not getattr(self.backbone, "fp16", False):
             return
+        flat_opt = self.opt_backbone if hasattr(self.opt_backbone, "shadow_view") else None
         for m in self.backbone.modules():
             if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d, torch.nn.Linear)):
                 w = m.weight
+                emitted = flat_opt.shadow_view(w) if flat_opt is not None else None
+                if emitted is not None:                 # rewritten by every FlatSGD.step(): no per-step copy
+                    w._msml_shadow = emitted
+                    self._emitted.append(w)
+                    continue
                 w._msml_shadow = torch.empty_like(w, dtype=torch.bfloat16)      # preserves strides (channels-last weights)
                 self._shadow_src.append(w.detach())
                 self._shadow_dst.append(w._msml_shadow)
+        self.refresh_shadows()
+
+    def refresh_shadows(self):
+        """Recompute the optimizer-emitted bf16 shadow weights from the fp32 weights.  Done automatically when a weight
+        was written in place through the Parameter (``load_state_dict``, ``p.copy_``: its version counter moves); call it
+        yourself after writes that bypass the counter (``p.data`` / ``p.detach()`` aliases, ``dist.broadcast(p.data)``)."""
+        if self._emitted:
+            self.opt_backbone.refresh_shadows()
+            self._emitted_versions = [w._version for w in self._emitted]
+
+    def _sync_shadows(self):
+        if self._emitted and self._emitted_versions != [w._version for w in self._emitted]:
+            self.refresh_shadows()
 
     def _step(self, img, label):
         ops.discard_pending_weight_grads()          # nothing may survive from an aborted earlier step
@@ -194,6 +223,8 @@ class TrainStep:
 
     def _fused_sgd_takes_scale(self):
         opt = self.opt_backbone
+        if hasattr(opt, "bind_flat"):               # FlatSGD divides by grad_scale inside its kernel, like torch's fused SGD
+            return True
         return (isinstance(opt, torch.optim.SGD) and all(g.get("fused") for g in opt.param_groups)
                 and all(not g.get("maximize") for g in opt.param_groups))
 
@@ -237,6 +268,7 @@ class TrainStep:
         capture.  The warm-up and the capture pass train on noise, so model / optimizer state is snapshotted before
         and restored afterwards unless preserve_state is False."""
         self._prepare()
+        self._sync_shadows()
         self.graph = None
         self._make_lr_capturable()
         had_momentum = any(st.get("momentum_buffer") is not None for st in self.opt_backbone.state.values())
@@ -258,6 +290,7 @@ class TrainStep:
         self.graph = g
         if preserve_state:
             self._restore(snap, had_momentum)
+            self.refresh_shadows()                  # the restore rewrote the weights behind the optimizer-emitted shadows
             if getattr(self.opt_pfc, "emit_normalized", False):
                 # the captured step expects the previous step's normalised centres (headers.PartialFCSGD emits them):
                 # the restore just rewrote the centres, so produce them once, eagerly, for the first replay
@@ -292,6 +325,7 @@ class TrainStep:
         """img (B,3,H,W) and label (B,) may live on the host (pinned) or the device; with no arguments the batch staged by
         ``prefetch`` is used."""
         self._prepare()
+        self._sync_shadows()
         if img is None:
             if not self._has_staged:
                 raise RuntimeError("TrainStep(): no inputs given and nothing staged by prefetch()")

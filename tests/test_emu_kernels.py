@@ -681,6 +681,39 @@ def test_fm_mask_kernels_match_oracle(emu_mask, Cm, Hm, Wm, dtype, sigmoid_mul):
     np.testing.assert_allclose(dm, wdm, rtol=1e-4, atol=1e-4 * np.abs(wdm).max())
 
 
+# ------------------------------------------------------------------------------------------------ flat momentum SGD (+ bf16 shadow)
+@pytest.mark.parametrize("n,blocks,momentum,wd,nesterov,scale", [
+    (4096, 3, 0.9, 5e-4, 0, 1.7), (4 * 1031, 2, 0.9, 5e-4, 1, None), (8, 5, 0.0, 0.0, 0, 0.5), (4 * 5000, 1, 0.5, 1e-2, 0, 3.0),
+])
+def test_sgd_flat_kernel(tmp_path_factory, n, blocks, momentum, wd, nesterov, scale):
+    """msml_sgd_flat == torch.optim.SGD's update rule (ref train.py:186-191, 299; dampening 0) written out in fp64, over
+    three steps (the momentum buffer starts at zero: the first step is m = g), with the GradScaler-style division and the
+    bf16 shadow of the new weights."""
+    lib = build_emu(tmp_path_factory, "emu_sgd_flat.cpp")
+    lib.emu_sgd_flat.argtypes = [c_p, c_p, c_p, c_p, c_i64, c_f, c_p, c_f, c_f, c_int, c_int]
+    rng = np.random.default_rng(n + blocks)
+    w = rng.normal(size=n).astype(np.float32)
+    m = np.zeros(n, np.float32)
+    shadow = np.zeros(n, np.uint16)
+    w64, m64 = w.astype(np.float64), np.zeros(n)
+    sc = np.array([scale], np.float32) if scale is not None else None
+    lr = 0.05
+    for step in range(3):
+        g = rng.normal(size=n).astype(np.float32)
+        assert lib.emu_sgd_flat(w.ctypes.data, m.ctypes.data, g.ctypes.data, shadow.ctypes.data, n, lr, sc.ctypes.data if sc is not None else None,
+                                momentum, wd, nesterov, blocks) == 0
+        g64 = g.astype(np.float64) / (float(sc[0]) if sc is not None else 1.0) + wd * w64
+        if momentum != 0.0:
+            m64 = momentum * m64 + g64
+            g64 = g64 + momentum * m64 if nesterov else m64
+        w64 = w64 - lr * g64
+        np.testing.assert_allclose(w, w64, rtol=2e-6, atol=2e-6)
+        if momentum != 0.0:
+            np.testing.assert_allclose(m, m64, rtol=2e-6, atol=2e-6)
+        assert np.array_equal(shadow, to_bf16_bits(w).reshape(-1))          # bit-exact round-to-nearest-even of the new weights
+        w64, m64 = w.astype(np.float64), m.astype(np.float64)                # follow the fp32 trajectory
+
+
 # ------------------------------------------------------------------------------------------------ multi-tensor gradient accumulate
 def test_accum_bf16_multi_kernel(tmp_path_factory):
     """dst_f32 += float(src_bf16) over many tensors in one launch: sizes around the 8192-element block, ragged tails, a tensor whose

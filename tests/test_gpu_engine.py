@@ -290,3 +290,114 @@ def test_captured_step_with_a_sampled_head(fused_head):
     assert bool(moved[touched].all()) and not bool(moved[~touched].any())
     with pytest.raises(ValueError):                                                    # gathered batch > num_sample: refused up front
         TrainStep(net, PartialFC(0, 0, 1, B, False, ArcFace(64.0, 0.5), 70, sample_rate=0.1), opt, opt_pfc, (B, 3, 112, 112), use_graph=True)
+
+
+# ------------------------------------------------------------------------------------------------ engine.FlatSGD
+def _toy(seed):
+    torch.manual_seed(seed)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1, bias=False), torch.nn.BatchNorm2d(8), torch.nn.PReLU(8),
+                              torch.nn.Conv2d(8, 5, 3, padding=1, bias=True), torch.nn.Flatten(), torch.nn.Linear(5 * 6 * 6, 7))
+    return net.cuda().to(memory_format=torch.channels_last)
+
+
+def _bind(net, opt):
+    """What engine.TrainStep does: one flat fp32 gradient buffer, every p.grad a view padded to 4 elements."""
+    params = list(net.parameters())
+    pad4 = lambda k: (k + 3) // 4 * 4
+    flat = torch.zeros(sum(pad4(p.numel()) for p in params), device="cuda")
+    off = 0
+    for p in params:
+        p.grad = torch.as_strided(flat, p.size(), p.stride(), off)
+        off += pad4(p.numel())
+    opt.bind_flat(params, flat)
+    return flat
+
+
+@pytest.mark.parametrize("nesterov,scale", [(False, None), (True, 2.5), (False, 0.5)])
+def test_flat_sgd_matches_torch_sgd(nesterov, scale):
+    """engine.FlatSGD (one msml_sgd_flat launch over flat parameter / momentum / gradient buffers) against
+    torch.optim.SGD (ref train.py:186-191, 299) on the same gradients for four steps: parameters, momentum buffers and the
+    emitted bf16 shadow weights; grad_scale as torch's fused optimizers take it."""
+    need_gpu()
+    from msml_b200.engine import FlatSGD
+    ref_net, net = _toy(5), _toy(5)
+    hp = dict(lr=0.05, momentum=0.9, weight_decay=5e-4, nesterov=nesterov)
+    ref_opt = torch.optim.SGD(ref_net.parameters(), **hp)
+    opt = FlatSGD(net.parameters(), **hp)
+    with pytest.raises(RuntimeError, match="not bound"):
+        opt.step()
+    flat = _bind(net, opt)
+    shadows = [opt.shadow_view(p) for p in net.parameters()]
+    opt.refresh_shadows()
+    for p, sh, q in zip(net.parameters(), shadows, ref_net.parameters()):
+        assert torch.equal(p, q) and p.stride() == q.stride()                       # the move into the flat buffer kept values and layout
+        assert torch.equal(sh, p.to(torch.bfloat16)) and sh.stride() == p.stride()
+    if scale is not None:
+        opt.grad_scale = torch.tensor(scale, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for it in range(4):
+        x = torch.randn(4, 3, 6, 6, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+        ref_opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
+        assert float(flat.abs().sum()) == 0.0 and all(p.grad is not None for p in net.parameters())
+        ref_net(x).square().mean().backward()
+        if it == 0:
+            net(x).square().mean().backward()                                     # autograd accumulates into the flat views
+            for q, p in zip(ref_net.parameters(), net.parameters()):
+                assert_close(host(p.grad), host(q.grad), 1e-4, atol_frac=1e-5, what="gradient through the flat view")
+        for q, p in zip(ref_net.parameters(), net.parameters()):                  # both optimizers see the SAME gradients, so the
+            p.grad.copy_(q.grad)                                                  # comparison is of the update rule alone
+        if scale is not None:
+            for q in ref_net.parameters():
+                q.grad.div_(scale)
+        ref_opt.step()
+        opt.step()
+        for (name, q), p, sh in zip(ref_net.named_parameters(), net.parameters(), shadows):
+            assert_close(host(p), host(q), 2e-5, atol=2e-6, what="%s step %d" % (name, it))
+            assert_close(host(opt.state[p]["momentum_buffer"]), host(ref_opt.state[q]["momentum_buffer"]), 2e-5, atol=2e-6, what="momentum " + name)
+            assert torch.equal(sh, p.to(torch.bfloat16)), name
+    # state_dict round trip keeps the momentum inside the flat buffer
+    sd = copy.deepcopy(opt.state_dict())
+    for p in net.parameters():
+        opt.state[p]["momentum_buffer"].zero_()
+    opt.load_state_dict(sd)
+    for q, p in zip(ref_net.parameters(), net.parameters()):
+        mb = opt.state[p]["momentum_buffer"]
+        assert opt._m.data_ptr() <= mb.data_ptr() < opt._m.data_ptr() + 4 * opt._m.numel()
+        assert_close(host(mb), host(ref_opt.state[q]["momentum_buffer"]), 2e-5, atol=2e-6, what="reloaded momentum")
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_step_with_flat_sgd_matches_torch_fused_sgd(use_graph):
+    """The whole bf16 step with engine.FlatSGD as the backbone optimizer == the same step with torch.optim.SGD(fused=True):
+    losses of four steps and the weights afterwards (the clip coefficient rides in grad_scale for both), and a checkpoint
+    loaded between steps reaches the optimizer-emitted bf16 shadow weights."""
+    need_gpu()
+    from msml_b200.engine import FlatSGD, TrainStep
+    B = 8
+    g = torch.Generator(device="cuda").manual_seed(5)
+    imgs = [torch.randn(B, 3, 112, 112, device="cuda", generator=g) for _ in range(4)]
+    labels = [torch.randint(0, 1000, (B,), device="cuda", generator=g) for _ in range(4)]
+    out = {}
+    for kind in ("torch", "flat"):
+        net, pfc, opt, opt_pfc = _build(fp16=True, fused=True)
+        if kind == "flat":
+            opt = FlatSGD([p for p in net.parameters() if p.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4)
+        step = TrainStep(net, pfc, opt, opt_pfc, (B, 3, 112, 112), use_graph=use_graph)
+        losses = [float(step(i, l)) for i, l in zip(imgs, labels)]
+        out[kind] = (losses, host(net.frb.conv1.weight), host(net.frb.layer3[0].conv1.weight), host(net.frb.fc.weight), host(net.frb.bn2.weight))
+        if kind == "flat":
+            assert opt.is_bound() and step._emitted and not any(w is s for w in step._emitted for s in step._shadow_src)
+            w = net.frb.conv1.weight
+            assert torch.equal(w._msml_shadow, w.detach().to(torch.bfloat16))     # written by the optimizer kernel
+            sd = {k: v.clone() for k, v in net.state_dict().items()}
+            sd["frb.conv1.weight"] = sd["frb.conv1.weight"] * 0.5
+            net.load_state_dict(sd)                                                 # in place through the Parameter: version moves
+            assert not torch.equal(w._msml_shadow, w.detach().to(torch.bfloat16))   # stale until the next call notices
+            step._sync_shadows()                                                    # what TrainStep.__call__ does first
+            assert torch.equal(w._msml_shadow, w.detach().to(torch.bfloat16))
+            assert np.isfinite(float(step(imgs[0], labels[0])))
+    for a, b in zip(out["torch"][0], out["flat"][0]):
+        assert abs(a - b) <= 3e-3 * abs(a), (out["torch"][0], out["flat"][0])
+    for a, b in zip(out["torch"][1:], out["flat"][1:]):
+        assert np.linalg.norm(a - b) <= 3e-3 * np.linalg.norm(a), np.linalg.norm(a - b) / np.linalg.norm(a)
