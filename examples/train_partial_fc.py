@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from msml_b200.backbones import MSML  # noqa: E402
-from msml_b200.engine import TrainStep, broadcast_parameters  # noqa: E402
+from msml_b200.engine import FlatSGD, TrainStep, broadcast_parameters  # noqa: E402
 from msml_b200.headers import ArcFace, PartialFC, PartialFCSGD  # noqa: E402
 
 
@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--lr", type=float, default=0.1)
     ap.add_argument("--sample-rate", type=float, default=1.0)
     ap.add_argument("--out", default="./", help="prefix for PartialFC.save_params()")
+    ap.add_argument("--stock-backbone-sgd", action="store_true", help="torch.optim.SGD(fused=True) for the backbone, as ref train.py:186-187, "
+                    "instead of engine.FlatSGD")
     ap.add_argument("--stock-head-sgd", action="store_true", help="torch.optim.SGD + update() for the class centres, exactly as ref "
                     "train.py:188-191,299-300, instead of the fused headers.PartialFCSGD")
     args = ap.parse_args()
@@ -59,8 +61,11 @@ def main():
     pfc = PartialFC(rank, local_rank, world, args.batch, False, ArcFace(64.0, 0.5), args.classes,
                     sample_rate=args.sample_rate, embedding_size=512, prefix=args.out)
     lr = args.lr / 512 * args.batch * world                               # ref :176, :190
-    opt_backbone = torch.optim.SGD([p for p in backbone.parameters() if p.requires_grad], lr=lr, momentum=0.9,
-                                   weight_decay=5e-4, fused=True)
+    bb_params = [p for p in backbone.parameters() if p.requires_grad]
+    if args.stock_backbone_sgd:
+        opt_backbone = torch.optim.SGD(bb_params, lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
+    else:   # the same optimizer (a torch.optim.SGD subclass) as one kernel over flat parameter / momentum / gradient buffers
+        opt_backbone = FlatSGD(bb_params, lr=lr, momentum=0.9, weight_decay=5e-4)
     if args.stock_head_sgd:
         opt_pfc = torch.optim.SGD([{"params": pfc.parameters()}], lr=lr, momentum=0.9, weight_decay=5e-4, fused=True)
     else:   # same hyper-parameters and param_groups (LR schedulers work); one kernel on the shard rows, update() has nothing to scatter

@@ -133,6 +133,30 @@ int msml_pfc_sgd_update_raw(float* weight, float* weight_mom, const float* dwn, 
                             float* inv_norm /*nullable*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K-P  Peer-guided branch of the Feature-Masking operator, elementwise ends.
+ * Replaces ref backbones/fm/fmoperator.py:293-302
+ *     m_bar = conv_m(gate);  f_out = conv1(m_bar * yf);  f_occ = conv2(m_bar * yt);  l2 = MSELoss()(f_occ, f_out)
+ * where the reference runs one ATen multiply per product (plus activation and `1 - x` for mask_trans 'invert',
+ * ref :160-166) and sub / pow / mean for the loss.
+ * msml_fm_peer_mul_fwd: pf = m_bar * yf and (yt non-null) pt = m_bar * yt in one pass over n elements of `dtype`, all
+ *   operands in one shared physical layout.  mode 0: src IS m_bar.  mode 1: src is the PRE-activation z and
+ *   m_bar = 1 - act(z) (act: MSML_ACT_*), so neither the gate nor its inverse is materialised.
+ * msml_fm_peer_mul_bwd: dsrc = d m_bar (mode 0) or -d m_bar * act'(z) (mode 1) with d m_bar = dpf*yf + dpt*yt, and
+ *   dyf = dpf * m_bar.  yt (the frozen teacher's feature map, ref peer/arcface.py:176-190) receives no gradient.
+ * msml_mse_fwd: *out (fp32, device) = mean((a - b)^2) accumulated in fp32 from `dtype` storage (autocast runs mse_loss in
+ *   fp32); per-CTA partials in `workspace` (msml_mse_workspace() bytes) summed in a fixed order: deterministic.
+ * msml_mse_bwd: da = 2 (a - b) / n * *gout (gout: fp32 device scalar), db = -da (db nullable).
+ * ------------------------------------------------------------------------------------------ */
+int msml_fm_peer_mul_fwd(const void* src, const void* yf, const void* yt, void* pf, void* pt, int64_t n, int dtype, int mode,
+                         int act, void* stream);
+int msml_fm_peer_mul_bwd(const void* dpf, const void* dpt, const void* src, const void* yf, const void* yt, void* dsrc, void* dyf,
+                         int64_t n, int dtype, int mode, int act, void* stream);
+size_t msml_mse_workspace(void);
+int msml_mse_fwd(const void* a, const void* b, int64_t n, int dtype, float* out, void* workspace, size_t workspace_bytes,
+                 void* stream);
+int msml_mse_bwd(const void* a, const void* b, const float* gout, void* da, void* db, int64_t n, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K-N  fused BatchNorm (+ residual add) (+ PReLU) over an NHWC tensor viewed as (P = N*H*W, C):
  *        y = prelu( (x - mean) * invstd * gamma + beta [+ res] )
  *   ref backbones/frb/iresnet.py:56-67, backbones/osb/unet.py:80-91, backbones/fm/fmoperator.py:52-68

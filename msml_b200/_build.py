@@ -16,10 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmsml_b200.so")
-SOURCES = ["capi.cu", "fm_gate.cu", "fm_cat.cu", "fm_mask.cu", "dap.cu", "pfc_sample.cu", "head.cu", "bn_act.cu", "optim.cu", "seg_loss.cu", "comm.cu"]
+SOURCES = ["capi.cu", "fm_gate.cu", "fm_cat.cu", "fm_mask.cu", "dap.cu", "pfc_sample.cu", "head.cu", "bn_act.cu", "optim.cu", "seg_loss.cu", "comm.cu", "fm_peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
-HEADERS = [os.path.join(CSRC, h) for h in ("common.cuh", "tc_gemm.cuh", "seg_loss_kernels.cuh", "pfc_sgd_kernels.cuh", "fm_cat_kernels.cuh", "bn_act_kernels.cuh", "fm_gate_kernels.cuh", "pfc_sample_kernels.cuh", "dap_kernels.cuh", "head_small_kernels.cuh", "fm_mask_kernels.cuh", "accum_kernels.cuh")] + [
+HEADERS = [os.path.join(CSRC, h) for h in ("common.cuh", "tc_gemm.cuh", "seg_loss_kernels.cuh", "pfc_sgd_kernels.cuh", "fm_cat_kernels.cuh", "bn_act_kernels.cuh", "fm_gate_kernels.cuh", "pfc_sample_kernels.cuh", "dap_kernels.cuh", "head_small_kernels.cuh", "fm_mask_kernels.cuh", "accum_kernels.cuh", "sgd_flat_kernels.cuh", "fm_peer_kernels.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "msml_b200.h")]
 
 

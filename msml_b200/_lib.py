@@ -47,6 +47,11 @@ SIGNATURES = {
                                    c_int, c_int, c_p, c_p, c_p, c_size, c_p]),
     "msml_consensus_bwd": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_p]),
     "msml_bn_workspace": (c_size, [c_i64, c_i64]),
+    "msml_fm_peer_mul_fwd": (c_int, [c_p] * 5 + [c_i64, c_int, c_int, c_int, c_p]),
+    "msml_fm_peer_mul_bwd": (c_int, [c_p] * 7 + [c_i64, c_int, c_int, c_int, c_p]),
+    "msml_mse_workspace": (c_size, []),
+    "msml_mse_fwd": (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_size, c_p]),
+    "msml_mse_bwd": (c_int, [c_p] * 5 + [c_i64, c_int, c_p]),
     "msml_bn_fwd": (c_int, [c_p] * 11 + [c_i64, c_i64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_p, c_size, c_p]),
     "msml_bn_fwd_ex": (c_int, [c_p] * 11 + [c_i64, c_i64, c_int, c_int, ctypes.c_float, ctypes.c_float, c_p, c_size, c_p, c_size,
                                 c_int, c_p]),

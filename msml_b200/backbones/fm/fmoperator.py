@@ -47,6 +47,15 @@ def _conv_bn_prelu_x2(c):
                          nn.Conv2d(c, c, 3, 1, 1), nn.BatchNorm2d(c, eps=1e-05), nn.PReLU(c))
 
 
+def _run_conv_bn_prelu(seq, x):
+    """An nn.Sequential of (Conv2d, BatchNorm2d, PReLU) triples (or the empty one of use_conv False, ref :138-158) through the
+    fused BN + PReLU kernels; module and parameter names stay those of the reference's Sequential."""
+    mods = list(seq)
+    for i in range(0, len(mods), 3):
+        x = ops.bn_act(ops.conv2d(x, mods[i]), mods[i + 1], mods[i + 2])
+    return x
+
+
 class _Invert(nn.Module):
     def forward(self, x):
         return 1 - x
@@ -129,15 +138,21 @@ class FMCnn(nn.Module):
         x, pad, yf = ops.fm_cat(yf, yo)        # C+18 channels zero-padded to a multiple of 8 (K-C); yf for the tail
         z = self.res_block(ops.conv2d_padded_in(x, self.same_conv, pad))
         f_out, l2 = None, None
-        if self.use_ori or self.en_save:
-            gate = self.mask_norm(z)
+        if self.en_save:
             self._save_intermediate_features('contaminated', yf)
-            self._save_intermediate_features('mask', gate)
+            self._save_intermediate_features('mask', self.mask_norm(z))
         if self.use_ori:
-            m_bar = self.conv_m(gate)
-            f_out = self.conv1(m_bar * yf)
+            # peer-guided branch (ref :293-302): both masked products in one pass (K-P); with mask_trans 'invert' the kernel
+            # forms 1 - act(z) itself, with 'conv' the gate has to exist for conv_m
+            if isinstance(self.conv_m, _Invert):
+                prod = ops.fm_peer_mul(z, yf, yt, "invert", self.activation)
+            else:
+                m_bar = ops.bn_act(ops.conv2d(self.mask_norm(z), self.conv_m[0]), self.conv_m[1])
+                prod = ops.fm_peer_mul(m_bar, yf, yt)
+            pf, pt = prod if yt is not None else (prod, None)
+            f_out = _run_conv_bn_prelu(self.conv1, pf)
             if yt is not None:
-                l2 = torch.nn.functional.mse_loss(self.conv2(m_bar * yt), f_out)
+                l2 = ops.mse_loss(_run_conv_bn_prelu(self.conv2, pt), f_out)
         if self.en_save:
             self._save_intermediate_features('purified', ops.fm_gate(yf, z, self.activation, self.arith_strategy) - yf)
         out = ops.fm_gate(yf, z, self.activation, self.arith_strategy, f_out)   # fused tail (K-A)

@@ -208,6 +208,100 @@ def fm_mask(yf, m, act="sigmoid", arith="mul"):
 
 
 # --------------------------------------------------------------------------------------------
+# K-P  peer-guided branch of the FM operator: masked products + MSE      ref backbones/fm/fmoperator.py:293-302
+# --------------------------------------------------------------------------------------------
+PEER_MODE = {"given": 0, "invert": 1}
+
+
+class _FMPeerMul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, yf, yt, mode, act):
+        require_cuda(src, yf, yt)
+        lib = load()
+        yf_d = _dense(yf)
+        src_d = _dense_like(yf_d, src)
+        yt_d = _dense_like(yf_d, yt) if yt is not None else None
+        pf = torch.empty_like(yf_d)
+        pt = torch.empty_like(yf_d) if yt is not None else None
+        check(lib.msml_fm_peer_mul_fwd(_ptr(src_d), _ptr(yf_d), _ptr(yt_d), _ptr(pf), _ptr(pt), yf_d.numel(), dtype_code(yf_d.dtype),
+                                       PEER_MODE[mode], ACT[act], stream_ptr()))
+        ctx.save_for_backward(src_d, yf_d, yt_d)
+        ctx.cfg = (mode, act)
+        ctx.set_materialize_grads(False)
+        if yt is None:
+            return pf
+        return pf, pt
+
+    @staticmethod
+    def backward(ctx, dpf, dpt=None):
+        src, yf, yt = ctx.saved_tensors
+        mode, act = ctx.cfg
+        if dpf is None and dpt is None:
+            return None, None, None, None, None
+        lib = load()
+        if dpf is None:                             # only the teacher product was used downstream
+            dpf = torch.zeros_like(yf)
+        if yt is not None and dpt is None:
+            dpt = torch.zeros_like(yf)
+        dpf_d = _dense_like(yf, dpf)
+        dpt_d = _dense_like(yf, dpt) if yt is not None else None
+        dsrc, dyf = torch.empty_like(yf), torch.empty_like(yf)
+        check(lib.msml_fm_peer_mul_bwd(_ptr(dpf_d), _ptr(dpt_d), _ptr(src), _ptr(yf), _ptr(yt), _ptr(dsrc), _ptr(dyf), yf.numel(),
+                                       dtype_code(yf.dtype), PEER_MODE[mode], ACT[act], stream_ptr()))
+        return dsrc, dyf, None, None, None
+
+
+def fm_peer_mul(src, yf, yt=None, mode="given", act="sigmoid"):
+    """(m_bar * yf, m_bar * yt) in one pass (ref fmoperator.py:295-299).  mode "given": ``src`` is m_bar (the output of
+    conv_m); mode "invert": ``src`` is the PRE-activation z and m_bar = 1 - act(z) (ref :160-166 with mask_trans 'invert'),
+    formed in registers.  ``yt`` (the frozen teacher's feature map) gets no gradient; without it only the first product is
+    returned."""
+    if mode not in PEER_MODE:
+        raise ValueError("mask_trans type error")
+    if act not in ACT:
+        raise ValueError("activation type error")
+    if src.shape != yf.shape or (yt is not None and yt.shape != yf.shape):
+        raise ValueError("fm_peer_mul: m_bar, yf and yt must have one shape")
+    return _FMPeerMul.apply(src, yf, yt.detach() if yt is not None else None, mode, act)
+
+
+class _MSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        require_cuda(a, b)
+        lib = load()
+        a_d = _dense(a)
+        b_d = _dense_like(a_d, b)
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        ws_bytes = lib.msml_mse_workspace()
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+        check(lib.msml_mse_fwd(_ptr(a_d), _ptr(b_d), a_d.numel(), dtype_code(a_d.dtype), _ptr(out), _ptr(ws), ws_bytes, stream_ptr()))
+        ctx.save_for_backward(a_d, b_d)
+        ctx.need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        lib = load()
+        g = gout.to(torch.float32).contiguous()
+        da = torch.empty_like(a)
+        db = torch.empty_like(a) if ctx.need[1] else None
+        check(lib.msml_mse_bwd(_ptr(a), _ptr(b), _ptr(g), _ptr(da), _ptr(db), a.numel(), dtype_code(a.dtype), stream_ptr()))
+        return (da if ctx.need[0] else None), db
+
+
+def mse_loss(a, b):
+    """torch.nn.MSELoss()(a, b) (ref fmoperator.py:300, mean reduction) as one reduction pass: fp32 accumulation from the
+    storage dtype, fp32 scalar result, deterministic."""
+    if a.shape != b.shape:
+        raise ValueError("mse_loss: shapes differ")
+    if a.numel() == 0:
+        raise ValueError("mse_loss of an empty tensor")
+    return _MSE.apply(a, b)
+
+
+# --------------------------------------------------------------------------------------------
 # K-N  fused BatchNorm (+ residual) (+ PReLU), NHWC            ref backbones/frb/iresnet.py:56-67,
 #                                                               backbones/fm/fmoperator.py:52-68
 # --------------------------------------------------------------------------------------------

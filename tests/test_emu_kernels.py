@@ -681,6 +681,73 @@ def test_fm_mask_kernels_match_oracle(emu_mask, Cm, Hm, Wm, dtype, sigmoid_mul):
     np.testing.assert_allclose(dm, wdm, rtol=1e-4, atol=1e-4 * np.abs(wdm).max())
 
 
+# ------------------------------------------------------------------------------------------------ K-P peer-branch products + MSE
+@pytest.fixture(scope="module")
+def emu_peer(tmp_path_factory):
+    lib = build_emu(tmp_path_factory, "emu_fm_peer.cpp")
+    lib.emu_fm_peer_mul_fwd.argtypes = [c_p] * 5 + [c_i64, c_int, c_int, c_int, c_int]
+    lib.emu_fm_peer_mul_bwd.argtypes = [c_p] * 7 + [c_i64, c_int, c_int, c_int, c_int]
+    lib.emu_mse.argtypes = [c_p, c_p, c_i64, c_int, c_p, c_f, c_p, c_p, c_int]
+    return lib
+
+
+@pytest.mark.parametrize("n,blocks,dtype,mode,act,has_t", [
+    (4096, 2, BF16, 0, "sigmoid", True), (4099, 3, BF16, 1, "sigmoid", True), (1003, 1, F32, 1, "tanh", True),
+    (8 * 700 + 5, 4, BF16, 1, "tanh", False), (7, 2, F32, 0, "sigmoid", False), (2048, 9, F32, 0, "sigmoid", True),
+])
+def test_fm_peer_mul_kernels(emu_peer, n, blocks, dtype, mode, act, has_t):
+    """pf = m_bar*yf, pt = m_bar*yt (ref fmoperator.py:295-299) with m_bar given or formed as 1 - act(z) (ref :160-166), and the
+    backward dm_bar = dpf*yf + dpt*yt, dyf = dpf*m_bar, against fp64 numpy; ragged tails and more CTAs than work."""
+    rng = np.random.default_rng(n + blocks)
+    q = (lambda a: from_bf16_bits(to_bf16_bits(a)).reshape(a.shape)) if dtype == BF16 else (lambda a: a.astype(np.float32))
+    enc = (lambda t: to_bf16_bits(t).reshape(t.shape)) if dtype == BF16 else (lambda t: np.ascontiguousarray(t, np.float32))
+    dec = (lambda b: from_bf16_bits(b).reshape(b.shape)) if dtype == BF16 else (lambda b: b)
+    ptr = lambda t: t.ctypes.data if t is not None else None
+    src, yf, yt, dpf, dpt = (q(rng.normal(size=n).astype(np.float32)) for _ in range(5))
+    sb, fb, tb, gfb, gtb = enc(src), enc(yf), (enc(yt) if has_t else None), enc(dpf), (enc(dpt) if has_t else None)
+    pfb, ptb = np.zeros_like(fb), (np.zeros_like(fb) if has_t else None)
+    assert emu_peer.emu_fm_peer_mul_fwd(ptr(sb), ptr(fb), ptr(tb), ptr(pfb), ptr(ptb), n, dtype, mode, ACTS[act], blocks) == 0
+    s64 = src.astype(np.float64)
+    if mode == 0:
+        m, dm_dsrc = s64, np.ones(n)
+    else:
+        gate = 1 / (1 + np.exp(-s64)) if act == "sigmoid" else np.tanh(s64)
+        m = 1 - gate
+        dm_dsrc = -(gate * (1 - gate) if act == "sigmoid" else 1 - gate * gate)
+    tol = dict(rtol=1e-2, atol=1e-2) if dtype == BF16 else dict(rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(dec(pfb), m * yf, **tol)
+    if has_t:
+        np.testing.assert_allclose(dec(ptb), m * yt, **tol)
+    dsb, dyb = np.zeros_like(fb), np.zeros_like(fb)
+    assert emu_peer.emu_fm_peer_mul_bwd(ptr(gfb), ptr(gtb), ptr(sb), ptr(fb), ptr(tb), ptr(dsb), ptr(dyb), n, dtype, mode, ACTS[act], blocks) == 0
+    dm = dpf.astype(np.float64) * yf + (dpt.astype(np.float64) * yt if has_t else 0.0)
+    gt = dict(rtol=2e-2, atol=2e-2) if dtype == BF16 else dict(rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(dec(dsb), dm * dm_dsrc, **gt)
+    np.testing.assert_allclose(dec(dyb), dpf * m, **gt)
+
+
+@pytest.mark.parametrize("n,blocks,dtype,both", [(5000, 3, BF16, True), (8 * 256 * 5 + 3, 7, BF16, False), (13, 4, F32, True), (40000, 148 * 8, F32, True)])
+def test_mse_kernels(emu_peer, n, blocks, dtype, both):
+    """mean((a-b)^2) with fp32 accumulation from the storage dtype (ref fmoperator.py:300 under autocast) and its gradient
+    2(a-b)/n * g; unused partial slots start as NaN and must not be read."""
+    rng = np.random.default_rng(n)
+    q = (lambda a: from_bf16_bits(to_bf16_bits(a)).reshape(a.shape)) if dtype == BF16 else (lambda a: a.astype(np.float32))
+    enc = (lambda t: to_bf16_bits(t).reshape(t.shape)) if dtype == BF16 else (lambda t: np.ascontiguousarray(t, np.float32))
+    dec = (lambda b: from_bf16_bits(b).reshape(b.shape)) if dtype == BF16 else (lambda b: b)
+    a, b = q(rng.normal(size=n).astype(np.float32)), q(rng.normal(0.3, 1.0, size=n).astype(np.float32))
+    ab, bb = enc(a), enc(b)
+    out = np.zeros(1, np.float32)
+    da, db = np.zeros_like(ab), (np.zeros_like(ab) if both else None)
+    assert emu_peer.emu_mse(ab.ctypes.data, bb.ctypes.data, n, dtype, out.ctypes.data, 0.7, da.ctypes.data, db.ctypes.data if both else None, blocks) == 0
+    d = a.astype(np.float64) - b
+    assert abs(out[0] - (d * d).mean()) <= 2e-6 * (d * d).mean()
+    want = 2 * d / n * 0.7
+    tol = dict(rtol=1e-2, atol=1e-2 * np.abs(want).max()) if dtype == BF16 else dict(rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(dec(da), want, **tol)
+    if both:
+        np.testing.assert_allclose(dec(db), -want, **tol)
+
+
 # ------------------------------------------------------------------------------------------------ flat momentum SGD (+ bf16 shadow)
 @pytest.mark.parametrize("n,blocks,momentum,wd,nesterov,scale", [
     (4096, 3, 0.9, 5e-4, 0, 1.7), (4 * 1031, 2, 0.9, 5e-4, 1, None), (8, 5, 0.0, 0.0, 0, 0.5), (4 * 5000, 1, 0.5, 1e-2, 0, 3.0),

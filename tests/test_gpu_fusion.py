@@ -486,6 +486,60 @@ torch.save({"y": y.detach().float().cpu(), "dx": x.grad.float().cpu(), "dg": bn.
                      atol_frac=2e-2 if k in ("y", "dx") else 1e-4, what="cooperative vs default: " + k)
 
 
+@pytest.mark.parametrize("mode,act", [("given", "sigmoid"), ("invert", "sigmoid"), ("invert", "tanh")])
+@pytest.mark.parametrize("with_teacher", [True, False])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fm_peer_mul_and_mse_match_autograd(mode, act, with_teacher, dtype):
+    """K-P: ops.fm_peer_mul + ops.mse_loss against the reference's expressions (ref fmoperator.py:293-302: `m_bar * identity`,
+    `m_bar * yt`, `MSELoss()(f_occ, f_out)`; `1 - x` over the activated mask for mask_trans 'invert', ref :160-166) run by
+    torch autograd in fp64 on the same (rounded) inputs: values, the loss, and the gradients of the mask source and yf."""
+    need_gpu()
+    from msml_b200 import ops
+    torch.manual_seed(11)
+    B, C, H = 3, 64, 14
+    mk = lambda: torch.randn(B, C, H, H, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    src, yf, yt, w1, w2 = mk(), mk(), mk(), mk(), mk()
+    src_a, yf_a = src.clone().requires_grad_(True), yf.clone().requires_grad_(True)
+    out = ops.fm_peer_mul(src_a, yf_a, yt if with_teacher else None, mode, act)
+    pf, pt = out if with_teacher else (out, None)
+    l2 = ops.mse_loss(pt * 1.0, pf) if with_teacher else ops.mse_loss(pf, w2)
+    assert l2.dtype == torch.float32 and l2.dim() == 0
+    ((pf.float() * w1.float()).sum() + 3.0 * l2).backward()
+    src_r, yf_r = src.double().requires_grad_(True), yf.double().requires_grad_(True)
+    gate = src_r if mode == "given" else (torch.sigmoid(src_r) if act == "sigmoid" else torch.tanh(src_r))
+    m_bar = gate if mode == "given" else 1 - gate
+    pf_r = m_bar * yf_r
+    rd = lambda t: t.to(dtype).double()                      # the kernels hand the products on in the storage dtype
+    if with_teacher:
+        pt_r = m_bar * yt.double()
+        l2_r = torch.nn.MSELoss()(pt_r, pf_r)
+    else:
+        l2_r = torch.nn.MSELoss()(pf_r, w2.double())
+    ((pf_r * w1.double()).sum() + 3.0 * l2_r).backward()
+    lo = dtype == torch.bfloat16
+    assert_close(host(pf), host(rd(pf_r)), 1e-2 if lo else 2e-5, atol=1e-2 if lo else 2e-6, what="pf")
+    if with_teacher:
+        assert_close(host(pt), host(rd(pt_r)), 1e-2 if lo else 2e-5, atol=1e-2 if lo else 2e-6, what="pt")
+    assert abs(float(l2) - float(l2_r)) <= (1e-2 if lo else 2e-5) * abs(float(l2_r))
+    assert_close(host(yf_a.grad), host(yf_r.grad), 3e-2 if lo else 1e-4, atol_frac=1e-2 if lo else 1e-5, what="dyf")
+    assert_close(host(src_a.grad), host(src_r.grad), 3e-2 if lo else 1e-4, atol_frac=1e-2 if lo else 1e-5, what="dsrc")
+
+
+def test_fm_peer_ops_reject_bad_arguments():
+    need_gpu()
+    from msml_b200 import ops
+    a = torch.randn(2, 8, 4, 4, device="cuda")
+    with pytest.raises(ValueError):
+        ops.fm_peer_mul(a, a, None, "flip")
+    with pytest.raises(ValueError):
+        ops.fm_peer_mul(a, a[:, :4], None)
+    with pytest.raises(ValueError):
+        ops.mse_loss(a, a[:1])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.mse_loss(a.cpu(), a.cpu())
+    assert float(ops.mse_loss(a, a)) == 0.0
+
+
 @pytest.mark.parametrize("name", ["fm_peer_c64_conv", "fm_peer_c128_invert"])
 def test_fmcnn_peer_branch_matches_reference_golden(name):
     """FMCnn with the peer-guided branch on (use_ori=True; ref fmoperator.py:129-166,293-302,307-308), random
