@@ -491,12 +491,22 @@ def run_train(args, rank, local_rank, world):
         if host_fed:
             # every step: H2D of that step's inputs from pinned memory (issued through the engine's prefetcher, so it
             # runs under the previous step, as a data loader's prefetcher would) and a D2H read of that step's loss
+            # (an async copy into pinned memory, read one step later — how a training loop logs its loss without draining the
+            # GPU: step i+1 is already enqueued when the host waits for the loss of step i)
+            loss_h = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+            loss_ev = [torch.cuda.Event() for _ in range(2)]
             step.prefetch(imgs_h[0], labels_h[0])
             for i in range(n):
                 loss_t = step()
+                loss_h[i & 1].copy_(loss_t, non_blocking=True)
+                loss_ev[i & 1].record()
                 if i + 1 < n:
                     step.prefetch(imgs_h[(i + 1) % n_buf], labels_h[(i + 1) % n_buf])
-                last = loss_t.item()
+                if i > 0:
+                    loss_ev[(i - 1) & 1].synchronize()
+                    last = float(loss_h[(i - 1) & 1])
+            loss_ev[(n - 1) & 1].synchronize()
+            last = float(loss_h[(n - 1) & 1])
         else:
             for i in range(n):
                 last = step(imgs[i % n_buf], labels[i % n_buf])
@@ -561,7 +571,9 @@ def run_train(args, rank, local_rank, world):
                    "l2": "per-step working set (activations, GBs) >> 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(args.steps * BATCH * world / (ms_e2e * 1e-3), 1), "unit": "imgs/s",
                 "h2d_bytes_per_step": imgs_h[0].numel() * 4 + labels_h[0].numel() * 8, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / args.steps, 3)},
+                "ms_per_step": round(ms_e2e / args.steps, 3),
+                "how": "TrainStep.prefetch(pinned img, label) under the previous step + TrainStep(); every step's loss copied to pinned "
+                       "memory and read by the host one step later"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
         "own_kernel_ms_per_step": round(mine_ms, 4),

@@ -15,6 +15,8 @@
 #include "../../msml_b200/csrc/fm_cat_kernels.cuh"
 #include "../../msml_b200/csrc/pfc_sgd_kernels.cuh"
 #include "../../msml_b200/csrc/seg_loss_kernels.cuh"
+#include "../../msml_b200/csrc/sgd_flat_kernels.cuh"
+#include "../../msml_b200/csrc/fm_peer_kernels.cuh"
 
 namespace msml {
 static char g_err[512];
@@ -130,6 +132,60 @@ static int run_bn(int64_t P, int64_t C, int G1, int G3) {
                        PRELU ? a.data() : nullptr, dx.data(), both ? dres.data() : nullptr, dadd.data(), dg.data(), db.data(),
                        PRELU ? dp.data() : nullptr, 1, 1, ws.data(), g, G1, G3);
   return nbt != 1;
+}
+
+// msml_bn_fwd_ex: producer (bn + res, emits the statistics of its output) -> consumer (starts at the merge); the consumer's
+// workspace is an exact-size allocation the producer writes with the kBnMaxCtas partial stride.
+template <typename T>
+static int run_bn_chain(int64_t P, int64_t C, int G1, int G3a, int G3b) {
+  const int dtype = sizeof(T) == 4 ? MSML_F32 : MSML_BF16;
+  BnGeom g;
+  if (!emu_bn_geom(P, C, dtype, &g)) return 1;
+  std::vector<T> x(P * C), r(P * C), y1(P * C), y2(P * C);
+  for (auto& v : x) v = conv<T>(1.f + 2.f * frand());
+  for (auto& v : r) v = conv<T>(frand());
+  std::vector<float> gamma(C, 1.1f), beta(C, -0.2f), a(C, 0.25f), rm(C, 0.f), rv(C, 1.f), mean(C), invstd(C);
+  std::vector<float> ws_a(emu_bn_ws_floats((int)C)), ws_b(emu_bn_ws_floats((int)C));
+  long long nbt = 0;
+  fwd3<T, true, false>(x.data(), r.data(), y1.data(), gamma.data(), beta.data(), nullptr, nullptr, nullptr, nullptr, 0.1f, 1e-5f, mean.data(),
+                       invstd.data(), ws_a.data(), g, G1, G3a, ws_b.data());
+  fwd3<T, false, true>(y1.data(), nullptr, y2.data(), gamma.data(), beta.data(), a.data(), rm.data(), rv.data(), &nbt, 0.1f, 1e-5f, mean.data(),
+                       invstd.data(), ws_b.data(), g, G1, G3b, nullptr, true);
+  return nbt != 1;
+}
+
+static int run_sgd_flat(int64_t n, int blocks, bool with_shadow, bool with_scale) {
+  std::vector<float> w(n), m(n, 0.f), gr(n);
+  for (auto& v : w) v = frand();
+  for (auto& v : gr) v = frand();
+  std::vector<__nv_bfloat16> shadow(with_shadow ? n : 0);
+  float lr = 0.05f, scale = 1.5f;
+  FlatSgdParams p{0.9f, 5e-4f, 0};
+  const float* lr_p = &lr;
+  const float* sc_p = with_scale ? &scale : nullptr;
+  emu_launch(dim3(blocks), kFlatSgdThreads,
+             [&] { sgd_flat_kernel(w.data(), m.data(), gr.data(), with_shadow ? shadow.data() : nullptr, n / 4, lr_p, sc_p, p); });
+  return 0;
+}
+
+template <typename T, int MODE>
+static int run_peer(int64_t n, int blocks) {
+  std::vector<T> src(n), yf(n), yt(n), pf(n), pt(n), dpf(n), dpt(n), dsrc(n), dyf(n), da(n), db(n);
+  for (auto* v : {&src, &yf, &yt, &dpf, &dpt})
+    for (auto& e : *v) e = conv<T>(frand());
+  emu_launch(dim3(blocks), kPeerThreads, [&] { fm_peer_mul_fwd_kernel<T, MODE, MSML_ACT_SIGMOID, true>(src.data(), yf.data(), yt.data(), pf.data(), pt.data(), n); });
+  emu_launch(dim3(blocks), kPeerThreads, [&] { fm_peer_mul_fwd_kernel<T, MODE, MSML_ACT_TANH, false>(src.data(), yf.data(), nullptr, pf.data(), nullptr, n); });
+  emu_launch(dim3(blocks), kPeerThreads,
+             [&] { fm_peer_mul_bwd_kernel<T, MODE, MSML_ACT_SIGMOID, true>(dpf.data(), dpt.data(), src.data(), yf.data(), yt.data(), dsrc.data(), dyf.data(), n); });
+  std::vector<float> partial(blocks);
+  float out = 0.f, gout = 0.7f;
+  float* pp = partial.data();
+  float* op = &out;
+  const float* gp = &gout;
+  emu_launch(dim3(blocks), kPeerThreads, [&] { mse_partial_kernel<T>(pf.data(), pt.data(), n, pp); });
+  emu_launch(dim3(1), kPeerThreads, [&] { mse_finish_kernel(pp, blocks, n, op); });
+  emu_launch(dim3(blocks), kPeerThreads, [&] { mse_bwd_kernel<T>(pf.data(), pt.data(), gp, da.data(), db.data(), n); });
+  return !(out >= 0.f);
 }
 
 template <typename T, int ACT, int ARITH>
@@ -268,6 +324,12 @@ int main(int argc, char** argv) {
   rc |= run_bn<__nv_bfloat16, true, true>(162, 32, 3, 5);
   rc |= run_bn<__nv_bfloat16, false, true>(40, 64, 2, 3);
   rc |= run_bn<float, true, false>(53, 64, 4, 2);
+  rc |= run_bn_chain<__nv_bfloat16>(162, 32, 3, 5, 4);
+  rc |= run_bn_chain<float>(53, 64, 2, 7, 3);
+  rc |= run_sgd_flat(4 * 1031, 3, true, true);
+  rc |= run_sgd_flat(8, 2, false, false);
+  rc |= run_peer<__nv_bfloat16, 1>(8 * 300 + 5, 3);
+  rc |= run_peer<float, 0>(4 * 129 + 3, 2);
   rc |= run_gate<float, 1, 3>(false);
   rc |= run_gate<__nv_bfloat16, 0, 0>(false);
   rc |= run_gate<__nv_bfloat16, 1, 2>(true);
