@@ -86,6 +86,13 @@ static int bn_fused_mode() {
   static const int mode = getenv("MSML_BN_FUSED") ? atoi(getenv("MSML_BN_FUSED")) : 0;
   return mode;
 }
+// The FIRST launch of an op as a programmatic dependent of the kernel before it in the stream (a cuDNN convolution, usually):
+// that kernel never triggers early, so the launch is released when its last CTA exits, but without the full kernel-boundary
+// flush + launch latency in between; the BN kernel blocks in griddepcontrol.wait until the predecessor's writes are visible.
+static bool bn_pdl_first() {
+  static const int on = getenv("MSML_BN_PDL_FIRST") ? atoi(getenv("MSML_BN_PDL_FIRST")) : 0;
+  return on != 0;
+}
 static int launch_plain(const void* kern, int blocks, void** args, cudaStream_t st, bool dependent = false) {
   static const int pdl = getenv("MSML_BN_PDL") ? atoi(getenv("MSML_BN_PDL")) : 1;     // 0 disables (comparison)
   if (dependent && pdl) {
@@ -137,10 +144,10 @@ static int launch_bn_fwd_fused(const void* x, const void* res, void* y, const fl
   if (stats_ready) {
     // the producer's phase 3 left the slab statistics in this workspace: partial stride kBnMaxCtas, zero counts behind its grid
     g.G = kBnMaxCtas;
-    if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st)) return e;
+    if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st, bn_pdl_first())) return e;
   } else {
     g.G = g1;
-    if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st)) return e;
+    if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st, bn_pdl_first())) return e;
     if (int e = launch_plain(reinterpret_cast<const void*>(bn_fwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st, true)) return e;
   }
   g.G = g3;
@@ -171,7 +178,7 @@ static int launch_bn_bwd_fused(const void* dy, const void* x, const void* res, c
   if (int e = coop_grid(bn_bwd_fused_kernel<T, RES, PRELU, 1>, g, &g1)) return e;
   if (int e = coop_grid(bn_bwd_fused_kernel<T, RES, PRELU, 3>, g, &g3)) return e;
   g.G = g1;
-  if (int e = launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st)) return e;
+  if (int e = launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 1>), g1, args, st, bn_pdl_first())) return e;
   if (int e = launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 2>), g.C, args, st, true)) return e;
   g.G = g3;
   return launch_plain(reinterpret_cast<const void*>(bn_bwd_fused_kernel<T, RES, PRELU, 3>), g3, args, st, true);

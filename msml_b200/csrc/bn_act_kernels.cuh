@@ -200,7 +200,8 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
   const int64_t row0 = sl.r0 + rl;
   dbg_stamp(g.skip, coef, g.C, 0);
   if (PHASE == 1 || PHASE == 2) pdl_launch_dependents();
-  if (PHASE == 2 || PHASE == 3) pdl_wait();
+  if (PHASE != 0) pdl_wait();      // phase 1 too: it may be launched as a programmatic dependent of whatever kernel precedes it in the
+                                   // stream (a no-op when it was not), so nothing below may be read before this point
 
   // ---- phase 1: slab statistics
   if (PHASE == 0 ? !(g.skip & 1) : PHASE == 1) {
@@ -430,6 +431,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   const uint4* rv = reinterpret_cast<const uint4*>(res) + cv;
 
   float sc[VN], sh[VN], pa[VN];
+  if (PHASE == 1) pdl_wait();        // as a programmatic dependent of an arbitrary predecessor: wait before the first global read.
+                                     // (Phase 3 loads the coefficients below BEFORE its wait: they were written by the forward pass /
+                                     // the optimizer, never by this op's phases 1-2, and the loads hide under phase 2.)
   if (PHASE != 2) {
     float is[VN], mu[VN], ga[VN], be[VN];
     ld_coef<VN>(invstd + cv * VN, is);
@@ -446,7 +450,8 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   }
   dbg_stamp(g.skip, coef, g.C, 0);
   if (PHASE == 1 || PHASE == 2) pdl_launch_dependents();
-  if (PHASE == 2 || PHASE == 3) pdl_wait();
+  if (PHASE != 0) pdl_wait();      // phase 1 too: it may be launched as a programmatic dependent of whatever kernel precedes it in the
+                                   // stream (a no-op when it was not), so nothing below may be read before this point
 
   // ---- phase 1: slab reductions
   if (PHASE == 0 ? !(g.skip & 1) : PHASE == 1) {
