@@ -49,7 +49,8 @@ struct BnGeom {
   int vpr;         // 16-byte vectors per row
   int rows_per_pass;   // kBnThreads / vpr
   int skip;            // bitmask: 1, 2, 4 skip the work of phase 1, 2, 3 (split launches / debug); 8 = timestamps (debug);
-                       // 16 = no grid barriers (the phases run as separate plain launches)
+                       // 16 = no grid barriers (the phases run as separate plain launches);
+                       // 32 = L2 residency hints: the statistics pass tags the slab evict_last, the apply pass evict_first
   int G;               // CTAs of the streaming phases (1 and 3): partial layout and slab geometry
 };
 
@@ -174,6 +175,11 @@ __device__ __forceinline__ void slab_stats_store(float* s, float* q, float (*red
   if (threadIdx.x == 0) part_n[blockIdx.x] = n;
 }
 
+// slab loads of the two streaming passes: with the residency hint (BnGeom.skip & 32) the first pass keeps, the second drops
+__device__ __forceinline__ uint4 ld_slab(const uint4* p, bool hint, uint64_t policy) {
+  return hint ? ld_stream_hint(p, policy) : ld_stream(p);
+}
+
 // ------------------------------------------------------------------------------------------- forward (training)
 // part layout: [k][C][grid] (channel-major so that phase 2 reads the slabs of a channel coalesced)
 // NEXT (phase 3 of the split launches only): y feeds another BatchNorm next (bn3 + skip of one residual unit -> bn1 of the
@@ -198,6 +204,8 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
   const Slab sl = slab_of(g, rl);
   const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
   const int64_t row0 = sl.r0 + rl;
+  const bool hint = (g.skip & 32) != 0;
+  const uint64_t pol = hint ? (PHASE == 1 ? l2_policy_keep() : l2_policy_drop()) : 0;
   dbg_stamp(g.skip, coef, g.C, 0);
   if (PHASE == 1 || PHASE == 2) pdl_launch_dependents();
   if (PHASE != 0) pdl_wait();      // phase 1 too: it may be launched as a programmatic dependent of whatever kernel precedes it in the
@@ -212,7 +220,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     for (; k + 4 <= sl.n_it; k += 4) {
       uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld_stream(xv + (row0 + (int64_t)(k + u) * g.rows_per_pass) * g.vpr);
+      for (int u = 0; u < 4; ++u) v[u] = ld_slab(xv + (row0 + (int64_t)(k + u) * g.rows_per_pass) * g.vpr, hint, pol);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[VN];
@@ -223,7 +231,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     }
     for (; k < sl.n_it; ++k) {
       float f[VN];
-      Vec<T>::unpack(ld_stream(xv + (row0 + (int64_t)k * g.rows_per_pass) * g.vpr), f);
+      Vec<T>::unpack(ld_slab(xv + (row0 + (int64_t)k * g.rows_per_pass) * g.vpr, hint, pol), f);
 #pragma unroll
       for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
@@ -309,7 +317,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
       for (int u = 0; u < U; ++u) {
         if (k - u >= 0) {
           const int64_t v = (row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr;
-          a[u] = ld_stream(xv + v);
+          a[u] = ld_slab(xv + v, hint, pol);
           if (RES) b[u] = ld_stream(rv + v);
         }
       }
@@ -430,6 +438,8 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
   const uint4* rv = reinterpret_cast<const uint4*>(res) + cv;
 
+  const bool hint = (g.skip & 32) != 0;
+  const uint64_t pol = hint ? (PHASE == 1 ? l2_policy_keep() : l2_policy_drop()) : 0;
   float sc[VN], sh[VN], pa[VN];
   if (PHASE == 1) pdl_wait();        // as a programmatic dependent of an arbitrary predecessor: wait before the first global read.
                                      // (Phase 3 loads the coefficients below BEFORE its wait: they were written by the forward pass /
@@ -465,9 +475,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       for (int u = 0; u < U; ++u) {
         if (k + u < sl.n_it) {
           const int64_t v = (row0 + (int64_t)(k + u) * g.rows_per_pass) * g.vpr;
-          a[u] = ld_stream(dyv + v);
-          b[u] = ld_stream(xv + v);
-          if (R3) c4[u] = ld_stream(rv + v);
+          a[u] = ld_slab(dyv + v, hint, pol);
+          b[u] = ld_slab(xv + v, hint, pol);
+          if (R3) c4[u] = ld_slab(rv + v, hint, pol);
         }
       }
 #pragma unroll
@@ -582,9 +592,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       for (int u = 0; u < U; ++u) {
         if (k - u >= 0) {
           const int64_t v = (row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr;
-          a[u] = ld_stream(dyv + v);
-          b[u] = ld_stream(xv + v);
-          if (R3) c4[u] = ld_stream(rv + v);
+          a[u] = ld_slab(dyv + v, hint, pol);
+          b[u] = ld_slab(xv + v, hint, pol);
+          if (R3) c4[u] = ld_slab(rv + v, hint, pol);
           if (has_add) e[u] = ld_stream(dav + v);
         }
       }

@@ -70,9 +70,32 @@ __device__ __forceinline__ void st_stream(void* p, const uint4& v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+// L2 residency hints for a slab that one kernel reads and a LATER kernel of the same op reads again (two-pass BatchNorm):
+// the first read tags its lines evict_last so that unrelated streams (a convolution on the side stream) are evicted before
+// them, the second read tags them evict_first so that they leave the cache once used.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_drop() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld_stream_hint(const void* p, uint64_t policy) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(policy));
+  return r;
+}
 #else   // host build under tests/emu/cuda_emu.h (logic checks without a GPU): cache hints have no meaning there
 inline uint4 ld_stream(const void* p) { return *static_cast<const uint4*>(p); }
 inline void st_stream(void* p, const uint4& v) { *static_cast<uint4*>(p) = v; }
+inline uint64_t l2_policy_keep() { return 0; }
+inline uint64_t l2_policy_drop() { return 0; }
+inline uint4 ld_stream_hint(const void* p, uint64_t) { return *static_cast<const uint4*>(p); }
 #endif
 
 // ---- element packs: one 16-byte vector = VEC<T>::N elements ------------------------------------
