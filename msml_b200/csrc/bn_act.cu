@@ -24,8 +24,10 @@ static int bn_geom(int64_t P, int64_t C, int dtype, BnGeom* g) {
 // L2 residency hints (BnGeom.skip & 32) for ops whose slab (`tensors` streams of P x C elements) can stay in the 126 MB L2
 // between the statistics pass and the apply pass.  ncu (--cache-control none, every launch of one step) showed the backward
 // apply pass re-reading about one tensor per op from HBM even for 13 MB layers: the convolution weight gradients on the side
-// stream push the slab out between the two passes.  Measured on one B200, two alternating repetitions: 15.24 / 15.24 ms per
-// step without, 15.13 / 15.13 with a 64 MB limit, 15.26 / 15.26 with 110 MB (larger slabs do not fit and only pollute).
+// stream push the slab out between the two passes.  Measured on one B200, alternating same-box runs: 15.24 / 15.24 ms per step
+// without, 15.13 / 15.13 with a 64 MB limit, 15.26 / 15.26 with 110 MB (larger slabs do not fit and only pollute); again on the
+// final single-code-path kernels (every slab load carries a block-uniform policy, evict_normal when the hint is off; a
+// separate unhinted path had cost registers and spilled): 14.89 -> 14.79 ms.
 // MSML_BN_L2_KEEP=0 disables, MSML_BN_L2_KEEP_MB sets the limit.
 static void bn_l2_hint(BnGeom* g, int dtype, int tensors) {
   static const int on = getenv("MSML_BN_L2_KEEP") ? atoi(getenv("MSML_BN_L2_KEEP")) : 1;

@@ -24,7 +24,9 @@
 //     its heaviest phase (205 MB layer: 147 vs 116 us forward, 349 vs 197 us backward);
 //   * fp64 atomics into per-channel accumulators with a single barrier: same-address atomics from 300-600
 //     CTAs cost more than the second barrier.
-// Minimum HBM traffic is one read of each input + one write of each output (the re-reads hit L2).
+// Minimum HBM traffic is one read of each input + one write of each output (the re-reads hit L2: for slabs of <= 64 MB the
+// statistics pass loads with an L2 evict_last policy and the apply pass with evict_first (BnGeom.skip & 32), so that other
+// streams' data — the weight-gradient convolutions on the side stream — are evicted before the slab between the two passes).
 // All phases stream a (P = N*H*W) x C matrix with C contiguous: a thread owns one 16-byte channel
 // vector for its whole life, so per-channel coefficients live in registers; loads are 128-bit, several
 // rows in flight per thread; each streaming phase runs exactly one resident wave of its own kernel.
@@ -175,10 +177,15 @@ __device__ __forceinline__ void slab_stats_store(float* s, float* q, float (*red
   if (threadIdx.x == 0) part_n[blockIdx.x] = n;
 }
 
-// slab loads of the two streaming passes: with the residency hint (BnGeom.skip & 32) the first pass keeps, the second drops
-__device__ __forceinline__ uint4 ld_slab(const uint4* p, bool hint, uint64_t policy) {
-  return hint ? ld_stream_hint(p, policy) : ld_stream(p);
+// Slab loads of the two streaming passes always carry an L2 policy (ONE code path: a second, unhinted path cost registers and
+// spilled): evict_normal — the default behaviour — unless the residency hint (BnGeom.skip & 32) is on, in which case the
+// statistics pass keeps (evict_last) and the apply pass drops (evict_first).  The policy is block-uniform.
+template <int PHASE>
+__device__ __forceinline__ uint64_t slab_policy(int skip) {
+  const uint64_t on = PHASE == 1 ? l2_policy_keep() : l2_policy_drop();
+  return (skip & 32) ? on : l2_policy_normal();
 }
+__device__ __forceinline__ uint4 ld_slab(const uint4* p, uint64_t policy) { return ld_stream_hint(p, policy); }
 
 // ------------------------------------------------------------------------------------------- forward (training)
 // part layout: [k][C][grid] (channel-major so that phase 2 reads the slabs of a channel coalesced)
@@ -204,8 +211,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
   const Slab sl = slab_of(g, rl);
   const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
   const int64_t row0 = sl.r0 + rl;
-  const bool hint = (g.skip & 32) != 0;
-  const uint64_t pol = hint ? (PHASE == 1 ? l2_policy_keep() : l2_policy_drop()) : 0;
+  const uint64_t pol = slab_policy<PHASE>(g.skip);
   dbg_stamp(g.skip, coef, g.C, 0);
   if (PHASE == 1 || PHASE == 2) pdl_launch_dependents();
   if (PHASE != 0) pdl_wait();      // phase 1 too: it may be launched as a programmatic dependent of whatever kernel precedes it in the
@@ -220,7 +226,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     for (; k + 4 <= sl.n_it; k += 4) {
       uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld_slab(xv + (row0 + (int64_t)(k + u) * g.rows_per_pass) * g.vpr, hint, pol);
+      for (int u = 0; u < 4; ++u) v[u] = ld_slab(xv + (row0 + (int64_t)(k + u) * g.rows_per_pass) * g.vpr, pol);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[VN];
@@ -231,7 +237,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
     }
     for (; k < sl.n_it; ++k) {
       float f[VN];
-      Vec<T>::unpack(ld_slab(xv + (row0 + (int64_t)k * g.rows_per_pass) * g.vpr, hint, pol), f);
+      Vec<T>::unpack(ld_slab(xv + (row0 + (int64_t)k * g.rows_per_pass) * g.vpr, pol), f);
 #pragma unroll
       for (int i = 0; i < VN; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
@@ -317,7 +323,7 @@ bn_fwd_fused_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __res
       for (int u = 0; u < U; ++u) {
         if (k - u >= 0) {
           const int64_t v = (row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr;
-          a[u] = ld_slab(xv + v, hint, pol);
+          a[u] = ld_slab(xv + v, pol);
           if (RES) b[u] = ld_stream(rv + v);
         }
       }
@@ -438,8 +444,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   const uint4* xv = reinterpret_cast<const uint4*>(x) + cv;
   const uint4* rv = reinterpret_cast<const uint4*>(res) + cv;
 
-  const bool hint = (g.skip & 32) != 0;
-  const uint64_t pol = hint ? (PHASE == 1 ? l2_policy_keep() : l2_policy_drop()) : 0;
+  const uint64_t pol = slab_policy<PHASE>(g.skip);
   float sc[VN], sh[VN], pa[VN];
   if (PHASE == 1) pdl_wait();        // as a programmatic dependent of an arbitrary predecessor: wait before the first global read.
                                      // (Phase 3 loads the coefficients below BEFORE its wait: they were written by the forward pass /
@@ -475,9 +480,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       for (int u = 0; u < U; ++u) {
         if (k + u < sl.n_it) {
           const int64_t v = (row0 + (int64_t)(k + u) * g.rows_per_pass) * g.vpr;
-          a[u] = ld_slab(dyv + v, hint, pol);
-          b[u] = ld_slab(xv + v, hint, pol);
-          if (R3) c4[u] = ld_slab(rv + v, hint, pol);
+          a[u] = ld_slab(dyv + v, pol);
+          b[u] = ld_slab(xv + v, pol);
+          if (R3) c4[u] = ld_slab(rv + v, pol);
         }
       }
 #pragma unroll
@@ -592,9 +597,9 @@ bn_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
       for (int u = 0; u < U; ++u) {
         if (k - u >= 0) {
           const int64_t v = (row0 + (int64_t)(k - u) * g.rows_per_pass) * g.vpr;
-          a[u] = ld_slab(dyv + v, hint, pol);
-          b[u] = ld_slab(xv + v, hint, pol);
-          if (R3) c4[u] = ld_slab(rv + v, hint, pol);
+          a[u] = ld_slab(dyv + v, pol);
+          b[u] = ld_slab(xv + v, pol);
+          if (R3) c4[u] = ld_slab(rv + v, pol);
           if (has_add) e[u] = ld_stream(dav + v);
         }
       }

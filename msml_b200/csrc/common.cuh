@@ -83,6 +83,11 @@ __device__ __forceinline__ uint64_t l2_policy_drop() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ uint64_t l2_policy_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ uint4 ld_stream_hint(const void* p, uint64_t policy) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
@@ -95,6 +100,7 @@ inline uint4 ld_stream(const void* p) { return *static_cast<const uint4*>(p); }
 inline void st_stream(void* p, const uint4& v) { *static_cast<uint4*>(p) = v; }
 inline uint64_t l2_policy_keep() { return 0; }
 inline uint64_t l2_policy_drop() { return 0; }
+inline uint64_t l2_policy_normal() { return 0; }
 inline uint4 ld_stream_hint(const void* p, uint64_t) { return *static_cast<const uint4*>(p); }
 #endif
 
