@@ -53,6 +53,58 @@ def test_ops_refuse_cpu_tensors():
         ops.fm_gate(x, x, arith="pow")
 
 
+def test_new_entry_points_validate_their_arguments_without_a_gpu():
+    """msml_sgd_flat, msml_bn_fwd_ex, the peer-branch kernels and the MSE: argument errors come back as negative status codes
+    with a message before anything touches the device."""
+    from msml_b200 import _lib
+    lib = _lib.load()
+    p16 = ctypes.c_void_p(16)
+    assert lib.msml_sgd_flat(p16, p16, p16, None, 6, p16, None, 0.9, 0.0, 0, None) < 0 and b"multiple of 4" in lib.msml_last_error()
+    assert lib.msml_sgd_flat(p16, None, p16, None, 8, p16, None, 0.9, 0.0, 0, None) < 0 and b"null" in lib.msml_last_error()
+    assert lib.msml_sgd_flat(p16, p16, p16, None, 8, p16, None, 0.0, 0.0, 1, None) < 0 and b"nesterov" in lib.msml_last_error()
+    assert lib.msml_sgd_flat(ctypes.c_void_p(8), p16, p16, None, 8, p16, None, 0.9, 0.0, 0, None) == -2      # MSML_EALIGN
+    assert lib.msml_sgd_flat(p16, p16, p16, None, 0, p16, None, 0.9, 0.0, 0, None) == 0                       # nothing to do
+    assert lib.msml_fm_peer_mul_fwd(p16, p16, p16, p16, None, 16, 1, 0, 1, None) < 0 and b"come together" in lib.msml_last_error()
+    assert lib.msml_fm_peer_mul_fwd(p16, p16, None, p16, None, 16, 1, 2, 1, None) < 0 and b"mode" in lib.msml_last_error()
+    assert lib.msml_fm_peer_mul_bwd(p16, None, p16, p16, p16, p16, p16, 16, 1, 1, 1, None) < 0
+    assert lib.msml_mse_fwd(p16, p16, 0, 1, p16, p16, 1 << 20, None) < 0
+    assert lib.msml_mse_fwd(p16, p16, 16, 1, p16, p16, 4, None) < 0 and b"workspace" in lib.msml_last_error()
+    assert lib.msml_mse_workspace() >= 148 * 4
+    ws = lib.msml_bn_workspace(64, 32)
+    # eval mode has no batch statistics to chain; a next-op workspace must be big enough and distinct from the op's own
+    assert lib.msml_bn_fwd_ex(p16, None, p16, None, None, None, p16, p16, None, p16, p16, 64, 32, 1, 0, 0.1, 1e-5, p16, ws,
+                              ctypes.c_void_p(32), ws, 0, None) < 0 and b"training" in lib.msml_last_error()
+    assert lib.msml_bn_fwd_ex(p16, None, p16, None, None, None, None, None, None, p16, p16, 64, 32, 1, 1, 0.1, 1e-5, p16, ws,
+                              ctypes.c_void_p(32), 8, 0, None) < 0 and b"next-op" in lib.msml_last_error()
+    assert lib.msml_bn_fwd_ex(p16, None, p16, None, None, None, None, None, None, p16, p16, 64, 32, 1, 1, 0.1, 1e-5, p16, ws,
+                              p16, ws, 0, None) < 0 and b"alias" in lib.msml_last_error()
+
+
+def test_flat_sgd_surface_without_a_gpu():
+    """engine.FlatSGD is a torch.optim.SGD (param_groups, state_dict, schedulers) that refuses what its kernel does not
+    implement and has no unbound / CPU fallback."""
+    from msml_b200.engine import FlatSGD
+    net = torch.nn.Linear(4, 4)
+    opt = FlatSGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    assert isinstance(opt, torch.optim.SGD) and not opt.is_bound()
+    assert opt.param_groups[0]["capturable_lr"] is True and opt.param_groups[0]["momentum"] == 0.9
+    with pytest.raises(RuntimeError, match="not bound"):
+        opt.step()
+    with pytest.raises(ValueError, match="dampening"):
+        FlatSGD(net.parameters(), lr=0.1, dampening=0.5)
+    with pytest.raises(ValueError, match="one parameter group"):
+        FlatSGD([{"params": [net.weight]}, {"params": [net.bias], "lr": 0.2}], lr=0.1)
+    with pytest.raises(RuntimeError, match="only a CUDA"):
+        net.weight.grad, net.bias.grad = torch.zeros(4, 4), torch.zeros(4)
+        opt.bind_flat(list(net.parameters()), torch.zeros(20))
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda i: 0.5)
+    assert abs(opt.param_groups[0]["lr"] - 0.05) < 1e-12
+    sd = opt.state_dict()
+    assert sd["param_groups"][0]["lr"] == opt.param_groups[0]["lr"] and sched is not None
+    opt.zero_grad()                                 # unbound: torch's behaviour
+    assert net.weight.grad is None
+
+
 def test_msml_state_dict_matches_reference_layout():
     """Key names and shapes recorded from the reference models (tests/golden/state_keys.json)."""
     from msml_b200.backbones import MSML
