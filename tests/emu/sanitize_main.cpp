@@ -324,12 +324,10 @@ int main(int argc, char** argv) {
   rc |= run_bn<__nv_bfloat16, true, true>(162, 32, 3, 5);
   rc |= run_bn<__nv_bfloat16, false, true>(40, 64, 2, 3);
   rc |= run_bn<float, true, false>(53, 64, 4, 2);
-  rc |= run_bn_chain<__nv_bfloat16>(162, 32, 3, 5, 4);
-  rc |= run_bn_chain<float>(53, 64, 2, 7, 3);
-  rc |= run_sgd_flat(4 * 1031, 3, true, true);
-  rc |= run_sgd_flat(8, 2, false, false);
-  rc |= run_peer<__nv_bfloat16, 1>(8 * 300 + 5, 3);
-  rc |= run_peer<float, 0>(4 * 129 + 3, 2);
+  rc |= run_bn_chain<__nv_bfloat16>(70, 32, 2, 3, 2);
+  rc |= run_sgd_flat(4 * 600, 2, true, true);
+  rc |= run_peer<__nv_bfloat16, 1>(8 * 300 + 5, 2);
+  rc |= run_peer<float, 0>(4 * 129 + 3, 1);
   rc |= run_gate<float, 1, 3>(false);
   rc |= run_gate<__nv_bfloat16, 0, 0>(false);
   rc |= run_gate<__nv_bfloat16, 1, 2>(true);
