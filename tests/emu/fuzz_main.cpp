@@ -27,6 +27,8 @@ int set_error(int code, const char* fmt, ...) {
 #define MSML_EMU_TEMPLATES_ONLY 1
 #include "../../msml_b200/csrc/fm_cat_kernels.cuh"
 #include "../../msml_b200/csrc/seg_loss_kernels.cuh"
+#include "../../msml_b200/csrc/sgd_flat_kernels.cuh"
+#include "../../msml_b200/csrc/fm_peer_kernels.cuh"
 #include "emu_bn.cpp"
 #include "emu_fm_gate.cpp"
 #include "emu_pfc_sample.cpp"
@@ -62,6 +64,75 @@ static void fuzz_bn() {
   bwd3<T, both, PRELU>(dy.data(), x.data(), both ? r.data() : nullptr, mean.data(), invstd.data(), gamma.data(), beta.data(),
                        PRELU ? a.data() : nullptr, dx.data(), both ? dres.data() : nullptr, ri(0, 1) ? dadd.data() : nullptr, dg.data(), db.data(),
                        PRELU ? dp.data() : nullptr, 1, ri(0, 1), ws.data(), g, G1, G3);
+}
+
+// msml_bn_fwd_ex: a producer whose apply pass emits the statistics of its output into the consumer's exact-size workspace
+// (partial stride kBnMaxCtas), then the consumer started at the merge.
+template <typename T, bool PRELU_B>
+static void fuzz_bn_chain() {
+  const int vn = sizeof(T) == 4 ? 4 : 8;
+  static const int vprs[] = {1, 2, 4, 8, 16, 32, 64};
+  const int64_t C = (int64_t)vprs[ri(0, 6)] * vn, P = ri(1, 300);
+  const int G1 = ri(1, 9), G3a = ri(1, 12), G3b = ri(1, 9);
+  BnGeom g;
+  if (!emu_bn_geom(P, C, sizeof(T) == 4 ? MSML_F32 : MSML_BF16, &g)) return;
+  std::vector<T> x(P * C), r(P * C), y1(P * C), y2(P * C);
+  for (auto& v : x) v = conv<T>(frand());
+  for (auto& v : r) v = conv<T>(frand());
+  std::vector<float> gamma(C, 1.f), beta(C, 0.f), a(C, 0.25f), rm(C, 0.f), rv(C, 1.f), mean(C), invstd(C);
+  std::vector<float> ws_a(emu_bn_ws_floats((int)C)), ws_b(emu_bn_ws_floats((int)C));
+  long long nbt = 0;
+  fwd3<T, true, false>(x.data(), r.data(), y1.data(), gamma.data(), beta.data(), nullptr, nullptr, nullptr, nullptr, 0.1f, 1e-5f, mean.data(),
+                       invstd.data(), ws_a.data(), g, G1, G3a, ws_b.data());
+  fwd3<T, false, PRELU_B>(y1.data(), nullptr, y2.data(), gamma.data(), beta.data(), PRELU_B ? a.data() : nullptr, rm.data(), rv.data(), &nbt, 0.1f,
+                          1e-5f, mean.data(), invstd.data(), ws_b.data(), g, G1, G3b, nullptr, true);
+  for (float v : invstd)
+    if (!(v > 0.f)) { printf("fuzz_bn_chain: bad invstd\n"); exit(3); }
+}
+
+static void fuzz_sgd_flat() {
+  const int64_t n = 4 * (int64_t)ri(1, 3000);
+  const int blocks = ri(1, 7);
+  std::vector<float> w(n), m(n, 0.f), gr(n);
+  for (auto& v : w) v = frand();
+  for (auto& v : gr) v = frand();
+  const bool with_shadow = ri(0, 1), with_scale = ri(0, 1);
+  std::vector<__nv_bfloat16> shadow(with_shadow ? n : 0);
+  float lr = 0.05f, scale = 1.5f;
+  FlatSgdParams p{ri(0, 1) ? 0.9f : 0.f, 5e-4f, 0};
+  p.nesterov = p.momentum != 0.f && ri(0, 1);
+  const float* lr_p = &lr;
+  const float* sc_p = with_scale ? &scale : nullptr;
+  float* mp = p.momentum != 0.f ? m.data() : nullptr;
+  emu_launch(dim3(blocks), kFlatSgdThreads, [&] { sgd_flat_kernel(w.data(), mp, gr.data(), with_shadow ? shadow.data() : nullptr, n / 4, lr_p, sc_p, p); });
+}
+
+template <typename T, int MODE, int ACT>
+static void fuzz_peer() {
+  const int64_t n = ri(1, 5000);
+  const int blocks = ri(1, 6);
+  std::vector<T> src(n), yf(n), yt(n), pf(n), pt(n), dpf(n), dpt(n), dsrc(n), dyf(n), da(n), db(n);
+  for (auto* v : {&src, &yf, &yt, &dpf, &dpt})
+    for (auto& e : *v) e = conv<T>(frand());
+  if (ri(0, 1)) {
+    emu_launch(dim3(blocks), kPeerThreads, [&] { fm_peer_mul_fwd_kernel<T, MODE, ACT, true>(src.data(), yf.data(), yt.data(), pf.data(), pt.data(), n); });
+    emu_launch(dim3(blocks), kPeerThreads,
+               [&] { fm_peer_mul_bwd_kernel<T, MODE, ACT, true>(dpf.data(), dpt.data(), src.data(), yf.data(), yt.data(), dsrc.data(), dyf.data(), n); });
+  } else {
+    emu_launch(dim3(blocks), kPeerThreads, [&] { fm_peer_mul_fwd_kernel<T, MODE, ACT, false>(src.data(), yf.data(), nullptr, pf.data(), nullptr, n); });
+    emu_launch(dim3(blocks), kPeerThreads,
+               [&] { fm_peer_mul_bwd_kernel<T, MODE, ACT, false>(dpf.data(), nullptr, src.data(), yf.data(), nullptr, dsrc.data(), dyf.data(), n); });
+  }
+  std::vector<float> partial(blocks);
+  float out = 0.f, gout = 0.7f;
+  float* pp = partial.data();
+  float* op = &out;
+  const float* gp = &gout;
+  const bool both = ri(0, 1);
+  emu_launch(dim3(blocks), kPeerThreads, [&] { mse_partial_kernel<T>(pf.data(), yf.data(), n, pp); });
+  emu_launch(dim3(1), kPeerThreads, [&] { mse_finish_kernel(pp, blocks, n, op); });
+  emu_launch(dim3(blocks), kPeerThreads, [&] { mse_bwd_kernel<T>(pf.data(), yf.data(), gp, da.data(), both ? db.data() : nullptr, n); });
+  if (!(out >= 0.f)) { printf("fuzz_peer: bad mse\n"); exit(3); }
 }
 
 template <typename T>
@@ -153,6 +224,12 @@ int main(int argc, char** argv) {
     fuzz_gate<__nv_bfloat16>();
     fuzz_seg();
     fuzz_pfc();
+    fuzz_bn_chain<__nv_bfloat16, true>();
+    fuzz_bn_chain<float, false>();
+    fuzz_sgd_flat();
+    fuzz_peer<__nv_bfloat16, 1, MSML_ACT_SIGMOID>();
+    fuzz_peer<float, 0, MSML_ACT_SIGMOID>();
+    fuzz_peer<float, 1, MSML_ACT_TANH>();
   }
   printf("fuzz: %d iterations clean\n", iters);
   return 0;
