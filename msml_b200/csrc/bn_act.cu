@@ -30,6 +30,8 @@ static int bn_geom(int64_t P, int64_t C, int dtype, BnGeom* g) {
 // separate unhinted path had cost registers and spilled): 14.89 -> 14.79 ms.
 // MSML_BN_L2_KEEP=0 disables, MSML_BN_L2_KEEP_MB sets the limit.
 static void bn_l2_hint(BnGeom* g, int dtype, int tensors) {
+  static const int fused = getenv("MSML_BN_FUSED") ? atoi(getenv("MSML_BN_FUSED")) : 0;   // the single cooperative launch (comparison
+  if (fused) return;                                                                      // mode) has no per-phase policy
   static const int on = getenv("MSML_BN_L2_KEEP") ? atoi(getenv("MSML_BN_L2_KEEP")) : 1;
   static const double cap_mb = getenv("MSML_BN_L2_KEEP_MB") ? atof(getenv("MSML_BN_L2_KEEP_MB")) : 64.0;
   if (!on) return;
